@@ -1,1 +1,47 @@
-"""differt_b200 — B200-native DiffeRT geometric hot path."""
+"""differt_b200 — the DiffeRT geometric hot path as hand-written CUDA for NVIDIA B200 (sm_100a).
+
+Drop-in for ``differt.geometry``'s ray–triangle, visibility and image-method functions and for the
+fused trace-and-validate step behind ``Scene.trace_paths`` (see DESIGN.md / INTEGRATION.md).
+Importing the package loads ``libdiffert_b200.so``; there is no CPU or PyTorch fallback.
+"""
+
+from . import _lib  # noqa: F401  (fails loudly if the CUDA library is missing)
+from . import geometry, rt, scenes, solvers
+from .geometry import (
+    consecutive_vertices_are_on_same_side_of_mirror,
+    fibonacci_lattice,
+    first_triangle_hit_by_ray,
+    image_method,
+    image_of_vertex_with_respect_to_mirror,
+    intersection_of_ray_with_plane,
+    ray_intersect_any_triangle,
+    ray_intersect_triangle,
+    triangles_visible_from_vertex,
+    viewing_frustum,
+)
+from .mesh import Mesh, TracedPaths
+from .solvers import generate_all_path_candidates, trace_path_candidates, trace_paths
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "Mesh",
+    "TracedPaths",
+    "consecutive_vertices_are_on_same_side_of_mirror",
+    "fibonacci_lattice",
+    "first_triangle_hit_by_ray",
+    "generate_all_path_candidates",
+    "geometry",
+    "image_method",
+    "image_of_vertex_with_respect_to_mirror",
+    "intersection_of_ray_with_plane",
+    "ray_intersect_any_triangle",
+    "ray_intersect_triangle",
+    "rt",
+    "scenes",
+    "solvers",
+    "trace_path_candidates",
+    "trace_paths",
+    "triangles_visible_from_vertex",
+    "viewing_frustum",
+]

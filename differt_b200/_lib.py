@@ -1,0 +1,94 @@
+"""ctypes binding of ``libdiffert_b200.so`` (the C ABI declared in ``include/differt_b200.h``).
+
+There is deliberately no fallback: if the CUDA library is missing, importing this module raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libdiffert_b200.so"
+
+i32, i64, f32, u32 = C.c_int32, C.c_int64, C.c_float, C.c_uint32
+ptr, size_t = C.c_void_p, C.c_size_t
+p_i64 = C.POINTER(C.c_int64)
+
+# name → (restype, argtypes); mirrors include/differt_b200.h one to one
+PROTOTYPES: dict[str, tuple] = {
+    "drt_abi_version": (C.c_int, []),
+    "drt_error_string": (C.c_char_p, [C.c_int]),
+    "drt_mesh_pack_bytes": (size_t, [i64]),
+    "drt_mesh_pack": (C.c_int, [ptr, i64, i64, ptr, ptr, ptr, ptr]),
+    "drt_mesh_pack_triangle_vertices": (C.c_int, [ptr, i64, ptr, ptr, ptr]),
+    "drt_ray_intersect_triangle": (
+        C.c_int, [ptr, i32, p_i64, ptr, p_i64, ptr, p_i64, ptr, p_i64, f32, ptr, ptr]),
+    "drt_ray_intersect_any_triangle": (C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, f32, ptr, ptr]),
+    "drt_first_triangle_hit_by_ray": (
+        C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, i64, ptr, ptr, ptr]),
+    "drt_first_triangle_hit_by_ray_vjp": (
+        C.c_int, [ptr, i64, i64, i64, ptr, ptr, ptr, ptr, ptr, ptr, ptr, ptr, ptr]),
+    "drt_triangles_visible_from_vertex": (
+        C.c_int, [ptr, i64, i64, ptr, ptr, ptr, i64, f32, ptr, ptr]),
+    "drt_image_method": (
+        C.c_int, [ptr, i32, p_i64, i32, ptr, p_i64, ptr, p_i64, ptr, p_i64, ptr, p_i64, ptr]),
+    "drt_image_method_vjp": (
+        C.c_int,
+        [ptr, i32, p_i64, i32, ptr, p_i64, ptr, p_i64, ptr, p_i64, ptr, p_i64, ptr, ptr, ptr, ptr, ptr]),
+    "drt_image_of_vertex_with_respect_to_mirror": (
+        C.c_int, [ptr, i32, p_i64, ptr, p_i64, ptr, p_i64, ptr, p_i64, ptr]),
+    "drt_intersection_of_ray_with_plane": (
+        C.c_int, [ptr, i32, p_i64, ptr, p_i64, ptr, p_i64, ptr, p_i64, ptr, p_i64, ptr]),
+    "drt_consecutive_vertices_are_on_same_side_of_mirror": (
+        C.c_int, [ptr, i32, p_i64, i32, ptr, p_i64, ptr, p_i64, ptr, p_i64, ptr]),
+    "drt_trace_workspace_bytes": (size_t, [i64, i64, i64, i64]),
+    "drt_trace_path_candidates": (
+        C.c_int,
+        [ptr, i64, i64, ptr, ptr, ptr, i32, i64, ptr, i64, ptr, i64, i32, ptr, f32, f32, f32, u32,
+         ptr, size_t, ptr, ptr, ptr, ptr]),
+    "drt_trace_path_candidates_vjp": (
+        C.c_int, [ptr, i64, i64, ptr, ptr, i64, ptr, i64, ptr, i64, i32, ptr, ptr, ptr, ptr, ptr]),
+    "drt_compact_workspace_bytes": (size_t, [i64]),
+    "drt_compact_valid_paths": (
+        C.c_int, [ptr, i64, i32, ptr, ptr, ptr, i64, ptr, size_t, ptr, ptr, ptr, ptr]),
+    "drt_complete_graph_candidates": (C.c_int, [ptr, i64, i32, i64, i64, i32, ptr]),
+}
+
+DRT_TRACE_DENSE_BLOCKAGE = 1
+DRT_MAX_ORDER = 8
+DRT_MAX_BATCH_DIMS = 4
+DRT_TILE_TRIANGLES = 512
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m differt_b200.build` "
+            "(differt_b200 has no CPU or PyTorch fallback)"
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export the ABI
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.drt_abi_version() != 1:
+        raise ImportError("libdiffert_b200.so ABI version mismatch; rebuild the library")
+    return lib
+
+
+lib = _load()
+
+
+class DrtError(RuntimeError):
+    pass
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise DrtError(f"differt_b200: {lib.drt_error_string(rc).decode()} (code {rc})")
+
+
+def i64_array(values) -> C.Array:
+    values = [int(v) for v in values]
+    return (C.c_int64 * max(len(values), 1))(*values)

@@ -1,0 +1,689 @@
+// K6 fused trace + validate, its reverse mode, TracedPaths.masked() compaction and the on-device
+// path-candidate decode.
+// Reference: differt/src/differt/geometry/_solvers.py:499-770 (`_trace_path_candidates`),
+// differt/src/differt/geometry/_paths.py:299-328 (`masked`),
+// differt-core/src/geometry/graph.rs:286-491 (complete-graph candidates).
+//
+// Stage A (one thread per (tx, rx, candidate)): gather mirrors from the packed mesh → image method →
+//   inside-triangle / same-side / min-length / finite tests in registers → writes the dense
+//   TracedPaths fields and a work list of the candidates that still need the blockage test.
+// Stage B (all-pairs engine, one warp per candidate, its k+1 segments register-blocked): any-hit of
+//   every segment against the whole mesh; a hit on any segment retires the candidate.
+#include "image_core.cuh"
+#include "intersect_core.cuh"
+
+namespace drt {
+
+__device__ __forceinline__ float sgn(float x) { return float(x > 0.0f) - float(x < 0.0f); }
+
+struct TraceArgs {
+    const Tri48 *pack;        // geometry of every triangle (mask NOT applied)
+    const uint8_t *tri_mask;  // nullable
+    const float *tx, *rx;
+    const int32_t *cand;
+    int64_t T, ntx, nrx, C, P;
+    float eps, min_len;
+    float *out_vertices;
+    int32_t *out_objects;
+    uint8_t *out_mask;
+    uint32_t *list;           // nullable (dense blockage): indices of candidates to test
+    int64_t *list_count;
+};
+
+template <int K, bool QUADS>
+__global__ void __launch_bounds__(256)
+trace_stage_a_kernel(const TraceArgs a) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = blockIdx.x * int64_t(blockDim.x) + threadIdx.x - lane; base < a.P;
+         base += stride) {
+        const int64_t p = base + lane;
+        bool prevalid = false;
+        if (p < a.P) {
+            const int64_t c = p % a.C;
+            const int64_t irx = (p / a.C) % a.nrx;
+            const int64_t itx = p / (a.C * a.nrx);
+            constexpr int KK = K > 0 ? K : 1;
+            float3 full[K + 2], mv[KK], mn[KK];
+            int32_t ci[KK];
+            bool active = true;
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                int32_t t = a.cand[c * K + i];
+                ci[i] = t;
+                t = min(max(t, 0), int32_t(a.T - (QUADS ? 2 : 1)));
+                const float4 ta = a.pack[t].a, tc = a.pack[t].c;
+                mv[i] = make_float3(ta.x, ta.y, ta.z);
+                mn[i] = make_float3(tc.y, tc.z, tc.w);
+                if (a.tri_mask != nullptr) {
+                    active = active && a.tri_mask[t] != 0;
+                    if (QUADS) active = active && a.tri_mask[t + 1] != 0;
+                }
+            }
+            full[0] = ld3(a.tx + 3 * itx);
+            full[K + 1] = ld3(a.rx + 3 * irx);
+            image_method_path<K>(full, mv, mn);
+
+            bool inside = true, same = true, small = false, finite = true;
+#pragma unroll
+            for (int i = 0; i <= K; ++i) {
+                const float3 o = full[i];
+                const float3 d = sub3(full[i + 1], full[i]);
+                small = small || (dot3(d, d) < a.min_len);
+                if (i < K) {
+                    const int32_t t = min(max(ci[i], 0), int32_t(a.T - (QUADS ? 2 : 1)));
+                    float tt;
+                    bool hit = mt_exact(o, d, unpack(a.pack[t].a, a.pack[t].b, a.pack[t].c), a.eps, tt);
+                    if (QUADS)
+                        hit = hit || mt_exact(o, d, unpack(a.pack[t + 1].a, a.pack[t + 1].b, a.pack[t + 1].c),
+                                              a.eps, tt);
+                    inside = inside && hit;
+                    const float dp = dot3(sub3(full[i], mv[i]), mn[i]);
+                    const float dn = dot3(sub3(full[i + 2], mv[i]), mn[i]);
+                    same = same && (sgn(dp) == sgn(dn)) && (dp == dp) && (dn == dn);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < K + 2; ++i) finite = finite && finite3(full[i]);
+
+            float *ov = a.out_vertices + p * (K + 2) * 3;
+#pragma unroll
+            for (int i = 0; i < K + 2; ++i)
+                st3(ov + 3 * i, finite ? full[i] : make_float3(0.f, 0.f, 0.f));
+            int32_t *oo = a.out_objects + p * (K + 2);
+            oo[0] = int32_t(itx);
+#pragma unroll
+            for (int i = 0; i < K; ++i) oo[i + 1] = ci[i];
+            oo[K + 1] = int32_t(irx);
+            prevalid = inside && same && !small && finite && active;
+            a.out_mask[p] = prevalid ? 1 : 0;
+        }
+        if (a.list != nullptr) {  // warp-aggregated append
+            const unsigned m = __ballot_sync(kFull, prevalid);
+            if (m) {
+                int64_t start = 0;
+                if (lane == 0)
+                    start = (int64_t)atomicAdd(reinterpret_cast<unsigned long long *>(a.list_count),
+                                               (unsigned long long)__popc(m));
+                start = __shfl_sync(kFull, start, 0);
+                if (prevalid) a.list[start + __popc(m & ((1u << lane) - 1u))] = uint32_t(p);
+            }
+        }
+    }
+}
+
+// Stage-B sources: the k+1 segments of candidate `p` read back from the dense vertices output.
+template <int NSEG>
+struct PathRays {
+    const float *vertices;  // [P, NSEG+1, 3]
+    const uint32_t *list;   // nullable → unit == path index
+    __device__ __forceinline__ int64_t path_of(int64_t unit) const {
+        return list != nullptr ? int64_t(list[unit]) : unit;
+    }
+    __device__ __forceinline__ uint32_t load(int64_t unit, float3 (&o)[NSEG], float3 (&d)[NSEG]) const {
+        const float *v = vertices + path_of(unit) * (NSEG + 1) * 3;
+        float3 prev = ld3(v);
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) {
+            const float3 next = ld3(v + 3 * (s + 1));
+            o[s] = prev;
+            d[s] = sub3(next, prev);  // jnp.diff (_solvers.py:593)
+            prev = next;
+        }
+        return (1u << NSEG) - 1u;
+    }
+};
+
+template <int NSEG>
+struct PathSink {
+    uint8_t *mask;
+    const uint32_t *list;
+    __device__ __forceinline__ void any(int64_t unit, uint32_t hit, uint32_t) const {
+        if (hit) mask[list != nullptr ? int64_t(list[unit]) : unit] = 0;
+    }
+    __device__ __forceinline__ void first(int64_t, int, int32_t, float) const {}
+};
+
+// generic order: flat (slot, segment) rays, RPW per warp, no path-level early exit
+template <int RPW>
+struct SegRays {
+    const float *vertices;
+    const uint32_t *list;
+    const int64_t *count_dev;  // number of slots (device) or null
+    int64_t count_host;
+    int nseg;
+    __device__ __forceinline__ uint32_t load(int64_t unit, float3 (&o)[RPW], float3 (&d)[RPW]) const {
+        const int64_t n = (count_dev != nullptr ? *count_dev : count_host) * nseg;
+        uint32_t valid = 0;
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+            const int64_t ray = unit * RPW + r;
+            o[r] = d[r] = make_float3(0.f, 0.f, 0.f);
+            if (ray < n) {
+                const int64_t slot = ray / nseg;
+                const int s = int(ray % nseg);
+                const int64_t p = list != nullptr ? int64_t(list[slot]) : slot;
+                const float *v = vertices + (p * (nseg + 1) + s) * 3;
+                o[r] = ld3(v);
+                d[r] = sub3(ld3(v + 3), o[r]);
+                valid |= 1u << r;
+            }
+        }
+        return valid;
+    }
+};
+
+template <int RPW>
+struct SegSink {
+    uint8_t *mask;
+    const uint32_t *list;
+    int nseg;
+    __device__ __forceinline__ void any(int64_t unit, uint32_t hit, uint32_t valid) const {
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+            if ((hit & valid) & (1u << r)) {
+                const int64_t slot = (unit * RPW + r) / nseg;
+                mask[list != nullptr ? int64_t(list[slot]) : slot] = 0;
+            }
+    }
+    __device__ __forceinline__ void first(int64_t, int, int32_t, float) const {}
+};
+
+__global__ void seg_units_kernel(const int64_t *count, int nseg, int rpw, int64_t *units) {
+    *units = (*count * nseg + rpw - 1) / rpw;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reverse mode
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void atomic_add3(float *p, float3 v) {
+    if (v.x != 0.f) atomicAdd(p, v.x);
+    if (v.y != 0.f) atomicAdd(p + 1, v.y);
+    if (v.z != 0.f) atomicAdd(p + 2, v.z);
+}
+
+// sum over the lanes that share `key` with lane 0's... simple form: if the whole warp shares the key
+// do one shuffle reduction and a single atomic, else fall back to per-lane atomics.
+__device__ __forceinline__ void warp_accumulate3(float *base, int64_t key, float3 v, bool live) {
+    const int64_t k0 = __shfl_sync(kFull, key, 0);
+    const bool uniform = __all_sync(kFull, !live || key == k0);
+    if (uniform) {
+        if (!live) v = make_float3(0.f, 0.f, 0.f);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            v.x += __shfl_xor_sync(kFull, v.x, off);
+            v.y += __shfl_xor_sync(kFull, v.y, off);
+            v.z += __shfl_xor_sync(kFull, v.z, off);
+        }
+        const unsigned any_live = __ballot_sync(kFull, live);
+        if (any_live && (threadIdx.x & 31) == (__ffs(any_live) - 1)) {
+            const int64_t kk = key;
+            atomic_add3(base + 3 * kk, v);
+        }
+    } else if (live) {
+        atomic_add3(base + 3 * key, v);
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+trace_vjp_kernel(int64_t V, int64_t T, const float *__restrict__ verts,
+                 const int32_t *__restrict__ tris, int64_t ntx, const float *__restrict__ tx,
+                 int64_t nrx, const float *__restrict__ rx, int64_t C,
+                 const int32_t *__restrict__ cand, const float *__restrict__ g_out, int64_t P,
+                 float *g_tx, float *g_rx, float *g_verts) {
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    constexpr int KK = K > 0 ? K : 1;
+    for (int64_t base = blockIdx.x * int64_t(blockDim.x) + threadIdx.x - lane; base < P;
+         base += stride) {
+        const int64_t p = base + lane;
+        bool live = false;
+        int64_t itx = 0, irx = 0;
+        float3 g_from = make_float3(0.f, 0.f, 0.f), g_to = make_float3(0.f, 0.f, 0.f);
+        if (p < P) {
+            const float *g = g_out + p * (K + 2) * 3;
+            float3 gp[KK];
+            bool nz = false;
+            const float3 g0 = ld3(g), g1 = ld3(g + 3 * (K + 1));
+            nz = (g0.x != 0.f) || (g0.y != 0.f) || (g0.z != 0.f) || (g1.x != 0.f) || (g1.y != 0.f) ||
+                 (g1.z != 0.f);
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                gp[i] = ld3(g + 3 * (i + 1));
+                nz = nz || (gp[i].x != 0.f) || (gp[i].y != 0.f) || (gp[i].z != 0.f);
+            }
+            if (nz) {
+                const int64_t c = p % C;
+                irx = (p / C) % nrx;
+                itx = p / (C * nrx);
+                int64_t vi[KK][3];
+                float3 v0[KK], v1[KK], v2[KK], mn[KK];
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    const int64_t t = min(max(int64_t(cand[c * K + i]), int64_t(0)), T - 1);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                        vi[i][q] = min(max(int64_t(tris[3 * t + q]), int64_t(0)), V - 1);
+                    v0[i] = ld3(verts + 3 * vi[i][0]);
+                    v1[i] = ld3(verts + 3 * vi[i][1]);
+                    v2[i] = ld3(verts + 3 * vi[i][2]);
+                    mn[i] = unit_normal(v0[i], v1[i], v2[i]);
+                }
+                float3 full[K + 2];
+                full[0] = ld3(tx + 3 * itx);
+                full[K + 1] = ld3(rx + 3 * irx);
+                image_method_path<K>(full, v0, mn);
+                bool finite = true;
+#pragma unroll
+                for (int i = 0; i < K + 2; ++i) finite = finite && finite3(full[i]);
+                if (finite) {  // where(is_finite, full_paths, 0): no gradient otherwise
+                    live = true;
+                    float3 g_mv[KK], g_mn[KK];
+#pragma unroll
+                    for (int i = 0; i < KK; ++i)
+                        g_mv[i] = g_mn[i] = make_float3(0.f, 0.f, 0.f);
+                    g_from = g0;
+                    g_to = g1;
+                    if (K > 0)
+                        image_method_reverse<K>(full[0], full[K + 1], v0, mn, gp, g_from, g_to, g_mv,
+                                                g_mn);
+#pragma unroll
+                    for (int i = 0; i < K; ++i) {
+                        // n = N / len, N = A × B, A = v1 - v0, B = v2 - v1
+                        const float3 A = sub3(v1[i], v0[i]), B = sub3(v2[i], v1[i]);
+                        const float3 N = cross3(A, B);
+                        const float len = __fsqrt_rn(dot3(N, N));
+                        float3 gN;
+                        if (len == 0.0f) {
+                            gN = g_mn[i];
+                        } else {
+                            const float proj = dot3(mn[i], g_mn[i]);
+                            gN = scale3(sub3(g_mn[i], scale3(mn[i], proj)), __fdiv_rn(1.0f, len));
+                        }
+                        const float3 gA = cross3(B, gN), gB = cross3(gN, A);
+                        atomic_add3(g_verts + 3 * vi[i][0], sub3(g_mv[i], gA));
+                        atomic_add3(g_verts + 3 * vi[i][1], sub3(gA, gB));
+                        atomic_add3(g_verts + 3 * vi[i][2], gB);
+                    }
+                }
+            }
+        }
+        warp_accumulate3(g_tx, itx, g_from, live);
+        warp_accumulate3(g_rx, irx, g_to, live);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// compaction of valid paths (stable, row-major order)
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kCompactThreads = 256;
+constexpr int kCompactItems = 16;
+constexpr int kCompactChunk = kCompactThreads * kCompactItems;  // 4096 paths per block
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
+    __shared__ int warp_sums[kCompactThreads / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(kFull, x, off);
+        if (lane >= off) x += y;
+    }
+    if (lane == 31) warp_sums[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < kCompactThreads / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(kFull, s, off);
+            if (lane >= off) s += y;
+        }
+        if (lane < kCompactThreads / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const int before = w > 0 ? warp_sums[w - 1] : 0;
+    *total = warp_sums[kCompactThreads / 32 - 1];
+    __syncthreads();
+    return before + x - v;
+}
+
+__global__ void __launch_bounds__(kCompactThreads)
+compact_count_kernel(int64_t P, const uint8_t *__restrict__ mask, int32_t *__restrict__ block_counts) {
+    const int64_t start = int64_t(blockIdx.x) * kCompactChunk + threadIdx.x * kCompactItems;
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < kCompactItems; ++i)
+        if (start + i < P) n += mask[start + i] != 0;
+    int total;
+    block_exclusive_scan(n, &total);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+compact_scan_kernel(int64_t num_blocks, const int32_t *__restrict__ block_counts,
+                    int64_t *__restrict__ block_offsets, int64_t *out_count) {
+    __shared__ int64_t warp_sums[32];
+    __shared__ int64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int64_t base = 0; base < num_blocks; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t v = i < num_blocks ? block_counts[i] : 0;
+        int64_t x = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int64_t y = __shfl_up_sync(kFull, x, off);
+            if (lane >= off) x += y;
+        }
+        if (lane == 31) warp_sums[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int64_t s = warp_sums[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int64_t y = __shfl_up_sync(kFull, s, off);
+                if (lane >= off) s += y;
+            }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        const int64_t before = (w > 0 ? warp_sums[w - 1] : 0) + carry_s;
+        if (i < num_blocks) block_offsets[i] = before + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = before + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out_count = carry_s;
+}
+
+__global__ void __launch_bounds__(kCompactThreads)
+compact_scatter_kernel(int64_t P, int nvert, const float *__restrict__ vertices,
+                       const int32_t *__restrict__ objects, const uint8_t *__restrict__ mask,
+                       const int64_t *__restrict__ block_offsets, int64_t capacity,
+                       int64_t *__restrict__ out_index, float *__restrict__ out_vertices,
+                       int32_t *__restrict__ out_objects) {
+    const int64_t start = int64_t(blockIdx.x) * kCompactChunk + threadIdx.x * kCompactItems;
+    int n = 0;
+    unsigned bits = 0;
+#pragma unroll
+    for (int i = 0; i < kCompactItems; ++i)
+        if (start + i < P && mask[start + i] != 0) {
+            bits |= 1u << i;
+            ++n;
+        }
+    int total;
+    int64_t pos = block_offsets[blockIdx.x] + block_exclusive_scan(n, &total);
+    for (int i = 0; i < kCompactItems; ++i) {
+        if (bits & (1u << i)) {
+            if (pos < capacity) {
+                const int64_t p = start + i;
+                if (out_index != nullptr) out_index[pos] = p;
+                if (out_vertices != nullptr)
+                    for (int q = 0; q < nvert * 3; ++q)
+                        out_vertices[pos * nvert * 3 + q] = vertices[p * nvert * 3 + q];
+                if (out_objects != nullptr)
+                    for (int q = 0; q < nvert; ++q)
+                        out_objects[pos * nvert + q] = objects[p * nvert + q];
+            }
+            ++pos;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// N1: complete-graph candidates from the linear index
+// ------------------------------------------------------------------------------------------------
+
+__global__ void complete_graph_candidates_kernel(int64_t n, int order, int64_t start, int64_t count,
+                                                 int mult, int32_t *__restrict__ out) {
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= count) return;
+    const int64_t base = n > 1 ? n - 1 : 1;
+    int64_t rem = start + i;
+    int64_t digits[DRT_MAX_ORDER * 2];
+    for (int j = order - 1; j >= 1; --j) {
+        digits[j] = rem % base;
+        rem /= base;
+    }
+    digits[0] = rem;
+    int64_t prev = digits[0];
+    out[i * order] = int32_t(prev * mult);
+    for (int j = 1; j < order; ++j) {
+        const int64_t node = digits[j] + (digits[j] >= prev ? 1 : 0);
+        out[i * order + j] = int32_t(node * mult);
+        prev = node;
+    }
+}
+
+struct TraceWorkspace {
+    size_t pack_geom, pack_active, list, counters, total;
+};
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+inline TraceWorkspace trace_workspace_layout(int64_t T, int64_t P) {
+    TraceWorkspace w;
+    const size_t pack = drt_mesh_pack_bytes(T);
+    size_t off = 0;
+    w.pack_geom = off;
+    off += align256(pack);
+    w.pack_active = off;
+    off += align256(pack);
+    w.counters = off;
+    off += 256;
+    w.list = off;
+    off += align256(size_t(P > 0 ? P : 1) * sizeof(uint32_t));
+    w.total = off;
+    return w;
+}
+
+template <int K>
+int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, const Tri48 *pack_active,
+                 float hit_tol, int64_t *tests_done, int64_t *units_scratch) {
+    const int threads = 256;
+    const int64_t blocks = (a.P + threads - 1) / threads;
+    const unsigned grid = unsigned(blocks < 148 * 8 ? blocks : 148 * 8);
+    if (quads)
+        trace_stage_a_kernel<K, true><<<grid, threads, 0, s>>>(a);
+    else
+        trace_stage_a_kernel<K, false><<<grid, threads, 0, s>>>(a);
+    if (cudaGetLastError() != cudaSuccess) return DRT_ERR_CUDA;
+    if (a.T == 0) return DRT_OK;  // empty mesh: nothing can block (_mesh.py:3053-3057)
+
+    CoreParams p{};
+    p.pack = pack_active;
+    p.num_tiles = int(drt_mesh_pack_bytes(a.T) / sizeof(Tri48) / kTile);
+    p.eps = a.eps;
+    p.thr = 1.0f - hit_tol;
+    p.num_triangles = a.T;
+    p.tests_done = tests_done;
+    const uint32_t *list = dense ? nullptr : a.list;
+    constexpr int NSEG = K + 1;
+    cudaError_t e;
+    if constexpr (NSEG <= 6) {
+        p.num_units = a.P;
+        p.num_units_dev = dense ? nullptr : a.list_count;
+        PathRays<NSEG> src{a.out_vertices, list};
+        PathSink<NSEG> sink{a.out_mask, list};
+        e = launch_intersect<NSEG, MODE_ANY, true>(s, p, src, sink, a.P);
+    } else {
+        constexpr int RPW = 3;
+        p.num_units = (a.P * NSEG + RPW - 1) / RPW;
+        p.num_units_dev = nullptr;
+        if (!dense) {
+            seg_units_kernel<<<1, 1, 0, s>>>(a.list_count, NSEG, RPW, units_scratch);
+            p.num_units_dev = units_scratch;
+        }
+        SegRays<RPW> src{a.out_vertices, list, dense ? nullptr : a.list_count, a.P, NSEG};
+        SegSink<RPW> sink{a.out_mask, list, NSEG};
+        e = launch_intersect<RPW, MODE_ANY, false>(s, p, src, sink, p.num_units);
+    }
+    return e == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
+}
+
+}  // namespace drt
+
+using namespace drt;
+
+extern "C" {
+
+size_t drt_trace_workspace_bytes(int64_t T, int64_t ntx, int64_t nrx, int64_t C) {
+    if (T < 0 || ntx < 0 || nrx < 0 || C < 0) return 0;
+    return trace_workspace_layout(T, ntx * nrx * C).total;
+}
+
+int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const float *vertices,
+                              const int32_t *triangles, const uint8_t *triangle_mask,
+                              int32_t assume_quads, int64_t ntx, const float *tx, int64_t nrx,
+                              const float *rx, int64_t C, int32_t order, const int32_t *cand,
+                              float epsilon, float hit_tol, float min_len, uint32_t flags,
+                              void *workspace, size_t workspace_bytes, float *out_vertices,
+                              int32_t *out_objects, uint8_t *out_mask, int64_t *stats) {
+    if (V < 0 || T < 0 || ntx < 0 || nrx < 0 || C < 0 || order < 0) return DRT_ERR_BAD_EXTENT;
+    if (order > DRT_MAX_ORDER) return DRT_ERR_UNSUPPORTED;
+    const int64_t P = ntx * nrx * C;
+    if (P >= (int64_t(1) << 32)) return DRT_ERR_BAD_EXTENT;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (stats != nullptr && cudaMemsetAsync(stats, 0, 4 * sizeof(int64_t), s) != cudaSuccess)
+        return DRT_ERR_CUDA;
+    if (P == 0) return DRT_OK;
+    if (!tx || !rx || !out_vertices || !out_objects || !out_mask || !workspace)
+        return DRT_ERR_NULL_POINTER;
+    if (order > 0 && cand == nullptr) return DRT_ERR_NULL_POINTER;
+    if (order > 0 && T < (assume_quads ? 2 : 1)) return DRT_ERR_BAD_EXTENT;  // candidates index triangles
+    const TraceWorkspace w = trace_workspace_layout(T, P);
+    if (workspace_bytes < w.total) return DRT_ERR_WORKSPACE;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    Tri48 *pack_geom = reinterpret_cast<Tri48 *>(ws + w.pack_geom);
+    Tri48 *pack_active = pack_geom;
+    int rc = drt_mesh_pack(stream, V, T, vertices, triangles, nullptr, pack_geom);
+    if (rc != DRT_OK) return rc;
+    if (triangle_mask != nullptr) {
+        pack_active = reinterpret_cast<Tri48 *>(ws + w.pack_active);
+        rc = drt_mesh_pack(stream, V, T, vertices, triangles, triangle_mask, pack_active);
+        if (rc != DRT_OK) return rc;
+    }
+    int64_t *counters = reinterpret_cast<int64_t *>(ws + w.counters);
+    if (cudaMemsetAsync(counters, 0, 256, s) != cudaSuccess) return DRT_ERR_CUDA;
+    const bool dense = (flags & DRT_TRACE_DENSE_BLOCKAGE) != 0;
+
+    TraceArgs a{};
+    a.pack = pack_geom;
+    a.tri_mask = triangle_mask;
+    a.tx = tx;
+    a.rx = rx;
+    a.cand = cand;
+    a.T = T;
+    a.ntx = ntx;
+    a.nrx = nrx;
+    a.C = C;
+    a.P = P;
+    a.eps = epsilon;
+    a.min_len = min_len;
+    a.out_vertices = out_vertices;
+    a.out_objects = out_objects;
+    a.out_mask = out_mask;
+    a.list = reinterpret_cast<uint32_t *>(ws + w.list);
+    a.list_count = counters;
+    int64_t *tests_done = stats;  // stats[0]
+    int64_t *units_scratch = counters + 1;
+    const bool quads = assume_quads != 0;
+#define DRT_TRACE_CASE(K)                                                                         \
+    case K:                                                                                       \
+        rc = trace_launch<K>(s, a, quads, dense, pack_active, hit_tol, tests_done, units_scratch); \
+        break;
+    switch (order) {
+        DRT_TRACE_CASE(0) DRT_TRACE_CASE(1) DRT_TRACE_CASE(2) DRT_TRACE_CASE(3) DRT_TRACE_CASE(4)
+        DRT_TRACE_CASE(5) DRT_TRACE_CASE(6) DRT_TRACE_CASE(7) DRT_TRACE_CASE(8)
+    }
+#undef DRT_TRACE_CASE
+    if (rc != DRT_OK) return rc;
+    if (stats != nullptr &&
+        cudaMemcpyAsync(stats + 1, counters, sizeof(int64_t), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+        return DRT_ERR_CUDA;
+    return DRT_OK;
+}
+
+int drt_trace_path_candidates_vjp(drt_stream_t stream, int64_t V, int64_t T, const float *vertices,
+                                  const int32_t *triangles, int64_t ntx, const float *tx,
+                                  int64_t nrx, const float *rx, int64_t C, int32_t order,
+                                  const int32_t *cand, const float *g_out, float *g_tx, float *g_rx,
+                                  float *g_vertices) {
+    if (V < 0 || T < 0 || ntx < 0 || nrx < 0 || C < 0 || order < 0) return DRT_ERR_BAD_EXTENT;
+    if (order > DRT_MAX_ORDER) return DRT_ERR_UNSUPPORTED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (ntx > 0 && g_tx == nullptr) return DRT_ERR_NULL_POINTER;
+    if (nrx > 0 && g_rx == nullptr) return DRT_ERR_NULL_POINTER;
+    if (V > 0 && g_vertices == nullptr) return DRT_ERR_NULL_POINTER;
+    if (ntx > 0 && cudaMemsetAsync(g_tx, 0, size_t(ntx) * 12, s) != cudaSuccess) return DRT_ERR_CUDA;
+    if (nrx > 0 && cudaMemsetAsync(g_rx, 0, size_t(nrx) * 12, s) != cudaSuccess) return DRT_ERR_CUDA;
+    if (V > 0 && cudaMemsetAsync(g_vertices, 0, size_t(V) * 12, s) != cudaSuccess) return DRT_ERR_CUDA;
+    const int64_t P = ntx * nrx * C;
+    if (P == 0) return DRT_OK;
+    if (!tx || !rx || !g_out) return DRT_ERR_NULL_POINTER;
+    if (order > 0 && (!cand || !vertices || !triangles || T == 0 || V == 0)) return DRT_ERR_NULL_POINTER;
+    const int threads = 256;
+    const int64_t blocks = (P + threads - 1) / threads;
+    const unsigned grid = unsigned(blocks < 148 * 8 ? blocks : 148 * 8);
+#define DRT_VJP_CASE(K)                                                                          \
+    case K:                                                                                      \
+        trace_vjp_kernel<K><<<grid, threads, 0, s>>>(V, T, vertices, triangles, ntx, tx, nrx, rx, \
+                                                     C, cand, g_out, P, g_tx, g_rx, g_vertices);  \
+        break;
+    switch (order) {
+        DRT_VJP_CASE(0) DRT_VJP_CASE(1) DRT_VJP_CASE(2) DRT_VJP_CASE(3) DRT_VJP_CASE(4)
+        DRT_VJP_CASE(5) DRT_VJP_CASE(6) DRT_VJP_CASE(7) DRT_VJP_CASE(8)
+    }
+#undef DRT_VJP_CASE
+    return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
+}
+
+size_t drt_compact_workspace_bytes(int64_t P) {
+    if (P < 0) return 0;
+    const int64_t nb = (P + kCompactChunk - 1) / kCompactChunk;
+    return align256(size_t(nb > 0 ? nb : 1) * sizeof(int32_t)) +
+           align256(size_t(nb > 0 ? nb : 1) * sizeof(int64_t));
+}
+
+int drt_compact_valid_paths(drt_stream_t stream, int64_t P, int32_t order, const float *vertices,
+                            const int32_t *objects, const uint8_t *mask, int64_t capacity,
+                            void *workspace, size_t workspace_bytes, int64_t *out_count,
+                            int64_t *out_index, float *out_vertices, int32_t *out_objects) {
+    if (P < 0 || order < 0 || capacity < 0) return DRT_ERR_BAD_EXTENT;
+    if (out_count == nullptr) return DRT_ERR_NULL_POINTER;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (P == 0) {
+        return cudaMemsetAsync(out_count, 0, sizeof(int64_t), s) == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
+    }
+    if (!mask || !workspace) return DRT_ERR_NULL_POINTER;
+    if ((out_vertices && !vertices) || (out_objects && !objects)) return DRT_ERR_NULL_POINTER;
+    if (workspace_bytes < drt_compact_workspace_bytes(P)) return DRT_ERR_WORKSPACE;
+    const int64_t nb = (P + kCompactChunk - 1) / kCompactChunk;
+    int32_t *counts = static_cast<int32_t *>(workspace);
+    int64_t *offsets = reinterpret_cast<int64_t *>(static_cast<unsigned char *>(workspace) +
+                                                   align256(size_t(nb) * sizeof(int32_t)));
+    compact_count_kernel<<<unsigned(nb), kCompactThreads, 0, s>>>(P, mask, counts);
+    compact_scan_kernel<<<1, 1024, 0, s>>>(nb, counts, offsets, out_count);
+    compact_scatter_kernel<<<unsigned(nb), kCompactThreads, 0, s>>>(
+        P, order + 2, vertices, objects, mask, offsets, capacity, out_index, out_vertices, out_objects);
+    return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
+}
+
+int drt_complete_graph_candidates(drt_stream_t stream, int64_t num_nodes, int32_t order,
+                                  int64_t start, int64_t count, int32_t stride_multiplier,
+                                  int32_t *out) {
+    if (num_nodes < 0 || order < 0 || start < 0 || count < 0) return DRT_ERR_BAD_EXTENT;
+    if (order > 2 * DRT_MAX_ORDER) return DRT_ERR_UNSUPPORTED;
+    if (count == 0 || order == 0) return DRT_OK;
+    if (out == nullptr) return DRT_ERR_NULL_POINTER;
+    complete_graph_candidates_kernel<<<unsigned((count + 255) / 256), 256, 0,
+                                       static_cast<cudaStream_t>(stream)>>>(
+        num_nodes, order, start, count, stride_multiplier > 0 ? stride_multiplier : 1, out);
+    return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
+}
+
+}  // extern "C"

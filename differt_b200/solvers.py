@@ -1,0 +1,165 @@
+"""The fused trace-and-validate step behind ``Scene.trace_paths``.
+
+Mirror of ``_trace_path_candidates`` (reference ``differt/src/differt/geometry/_solvers.py:499-770``)
+with the same arguments and defaults; the candidate enumeration of ``ExhaustivePathTracer``
+(``_solvers.py:803-848`` → ``differt-core/src/geometry/graph.rs:286-491``) is available as an on-device
+decode (``generate_all_path_candidates``).
+"""
+
+from __future__ import annotations
+
+from typing import Iterator
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+from ._tensor import F32_EPS, Placement, ptr, stream_ptr
+from .mesh import Mesh, TracedPaths
+from .scenes import num_complete_graph_candidates
+
+__all__ = [
+    "generate_all_path_candidates",
+    "generate_all_path_candidates_chunks_iter",
+    "trace_path_candidates",
+    "trace_paths",
+]
+
+
+class _TraceVertices(torch.autograd.Function):
+    """``vertices`` of the traced paths with the reference's gradient: through the image method to
+    ``tx``, ``rx`` and ``mesh.vertices`` (mirror vertex gather + normals), none through the mask."""
+
+    @staticmethod
+    def forward(ctx, mesh_vertices, tx, rx, triangles, cand, out_vertices):
+        ctx.save_for_backward(mesh_vertices, tx, rx, triangles, cand)
+        return out_vertices
+
+    @staticmethod
+    def backward(ctx, g):
+        mesh_vertices, tx, rx, triangles, cand = ctx.saved_tensors
+        g = g.contiguous().to(torch.float32)
+        g_v = torch.empty_like(mesh_vertices)
+        g_tx = torch.empty_like(tx)
+        g_rx = torch.empty_like(rx)
+        check(
+            lib.drt_trace_path_candidates_vjp(
+                stream_ptr(), mesh_vertices.shape[0], triangles.shape[0], ptr(mesh_vertices),
+                ptr(triangles), tx.shape[0], ptr(tx), rx.shape[0], ptr(rx), cand.shape[0], cand.shape[1],
+                ptr(cand), ptr(g), ptr(g_tx), ptr(g_rx), ptr(g_v),
+            )
+        )
+        return g_v, g_tx, g_rx, None, None, None
+
+
+def trace_path_candidates(
+    mesh: Mesh,
+    tx_vertices,
+    rx_vertices,
+    path_candidates,
+    interaction_types=None,
+    *,
+    epsilon=None,
+    hit_tol=None,
+    min_len=None,
+    smoothing_factor=None,
+    confidence_threshold: float = 0.5,
+    batch_size: int | None = 512,
+    dense_blockage: bool = False,
+    with_stats: bool = False,
+) -> TracedPaths:
+    """Trace every ``(tx, rx, candidate)`` with the image method and validate it.
+
+    Returns ``TracedPaths`` with ``vertices [Ntx,Nrx,C,k+2,3]``, ``objects [Ntx,Nrx,C,k+2]``,
+    ``mask [Ntx,Nrx,C]`` and ``interaction_types [Ntx,Nrx,C,k]``, exactly the reference's fields.
+    ``dense_blockage=True`` makes the blockage stage test every candidate (the amount of work the
+    reference does); the default skips candidates that already failed a cheaper test — identical
+    outputs.  ``batch_size`` is accepted and ignored.
+    """
+    if smoothing_factor is not None:
+        raise NotImplementedError("smoothing_factor is not supported by the CUDA path (SURVEY.md §8a)")
+    del batch_size
+    pl = Placement()
+    pl.device = mesh.vertices.device
+    tx = pl.put(tx_vertices, torch.float32).reshape(-1, 3).contiguous()
+    rx = pl.put(rx_vertices, torch.float32).reshape(-1, 3).contiguous()
+    cand = pl.put(path_candidates, torch.int32).contiguous()
+    if cand.ndim != 2:
+        raise TypeError("path_candidates must have shape [num_path_candidates, order]")
+    dev = mesh.vertices.device
+    ntx, nrx, (C, k) = tx.shape[0], rx.shape[0], cand.shape
+    if k > _lib.DRT_MAX_ORDER:
+        raise NotImplementedError(f"order {k} > {_lib.DRT_MAX_ORDER} is not supported")
+    T = mesh.num_triangles
+    out_v = torch.empty((ntx, nrx, C, k + 2, 3), dtype=torch.float32, device=dev)
+    out_o = torch.empty((ntx, nrx, C, k + 2), dtype=torch.int32, device=dev)
+    out_m = torch.empty((ntx, nrx, C), dtype=torch.uint8, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev) if with_stats else None
+    ws = torch.empty(max(lib.drt_trace_workspace_bytes(T, ntx, nrx, C), 1), dtype=torch.uint8, device=dev)
+    check(
+        lib.drt_trace_path_candidates(
+            stream_ptr(), mesh.vertices.shape[0], T, ptr(mesh.vertices.detach()), ptr(mesh.triangles),
+            ptr(mesh._mask_u8()), int(mesh.assume_quads), ntx, ptr(tx.detach()), nrx, ptr(rx.detach()),
+            C, k, ptr(cand),
+            10.0 * F32_EPS if epsilon is None else float(epsilon),
+            100.0 * F32_EPS if hit_tol is None else float(hit_tol),
+            10.0 * F32_EPS if min_len is None else float(min_len),
+            _lib.DRT_TRACE_DENSE_BLOCKAGE if dense_blockage else 0,
+            ptr(ws), ws.numel(), ptr(out_v), ptr(out_o), ptr(out_m), ptr(stats),
+        )
+    )
+    if torch.is_grad_enabled() and any(x.requires_grad for x in (mesh.vertices, tx, rx)):
+        out_v = _TraceVertices.apply(mesh.vertices, tx, rx, mesh.triangles, cand, out_v)
+    if interaction_types is not None:
+        it = pl.put(interaction_types, torch.int32).expand(ntx, nrx, C, k)
+    else:
+        it = torch.zeros((1, 1, 1, 1), dtype=torch.int32, device=dev).expand(ntx, nrx, C, k)
+    paths = TracedPaths(
+        vertices=out_v,
+        objects=out_o,
+        mask=out_m.bool(),
+        interaction_types=it,
+        confidence_threshold=confidence_threshold,
+    )
+    if with_stats:
+        s = stats.cpu().tolist()
+        paths.stats = {"tests_done": s[0], "candidates_blockage_tested": s[1]}
+    return paths
+
+
+def generate_all_path_candidates(
+    num_primitives: int, order: int, *, assume_quads: bool = False, start: int = 0,
+    count: int | None = None, device=None,
+) -> torch.Tensor:
+    """All ``n (n-1)^(k-1)`` candidates of the complete graph in the reference's order
+    (``_solvers.py:803-848``), decoded on the device from the linear index; under ``assume_quads``
+    the indices are the even triangles (``2 *`` primitive index, ``_solvers.py:836-838``)."""
+    total = num_complete_graph_candidates(num_primitives, order)
+    count = total - start if count is None else max(min(count, total - start), 0)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    out = torch.empty((count, order), dtype=torch.int32, device=dev)
+    check(
+        lib.drt_complete_graph_candidates(
+            stream_ptr(), num_primitives, order, start, count, 2 if assume_quads else 1, ptr(out)
+        )
+    )
+    return out
+
+
+def generate_all_path_candidates_chunks_iter(
+    num_primitives: int, order: int, chunk_size: int = 1000, *, assume_quads: bool = False
+) -> Iterator[torch.Tensor]:
+    """Chunked variant (reference ``_solvers.py:850-934``)."""
+    total = num_complete_graph_candidates(num_primitives, order)
+    for start in range(0, total, chunk_size):
+        yield generate_all_path_candidates(
+            num_primitives, order, assume_quads=assume_quads, start=start, count=chunk_size
+        )
+
+
+def trace_paths(mesh: Mesh, tx_vertices, rx_vertices, order: int, **kwargs) -> TracedPaths:
+    """Exhaustive ``Scene.trace_paths(order)`` (reference ``_scene.py:650-764``) for one mesh."""
+    cand = generate_all_path_candidates(
+        mesh.num_primitives, order, assume_quads=mesh.assume_quads, device=mesh.vertices.device
+    )
+    return trace_path_candidates(mesh, tx_vertices, rx_vertices, cand, **kwargs)

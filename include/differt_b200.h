@@ -1,0 +1,225 @@
+/* differt_b200 — C ABI of the B200-native DiffeRT geometric hot path.
+ *
+ * This is the drop-in boundary: flat device buffers + a CUDA stream, exactly the shape of the
+ * launchers the reference registers with XLA through `wp.jax_callable`
+ * (reference: differt/src/differt/geometry/_mesh.py:160-181, 202-223, 369-401, 3082-3092) and of the
+ * pure-JAX functions those launchers accelerate (differt/src/differt/geometry/_utils.py:1157-1960,
+ * _solver_image_method.py:11-454, _solvers.py:499-770).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - all floats are IEEE binary32, all indices int32, all masks/booleans one byte (0/1);
+ *   - calls are asynchronous on `stream` (a `cudaStream_t`), never synchronise, never allocate,
+ *     are re-entrant and keep no global mutable state;
+ *   - return value: DRT_OK (0) or a negative DRT_ERR_* code (`drt_error_string`); nothing throws;
+ *   - degenerate extents (0 rays, 0 triangles, 0 candidates) are legal and produce the constant
+ *     outputs the reference produces (`False`, `(-1, +inf)`, empty);
+ *   - arithmetic follows the reference's pure-JAX operation order without fused multiply-add, so
+ *     boolean outputs are bit-identical to the CPU algorithm ("Parity contract").
+ *
+ * Semantics delta (documented in DESIGN.md): the entry points implement the *pure-JAX* definitions
+ * (`t > epsilon`, `t < 1 - hit_tol` on the un-normalised ray).  The reference's Warp launchers
+ * instead shorten the normalised ray by `hit_tol` at both ends (_mesh.py:3065-3070) and offset the
+ * first-hit origin by 1e-5 (_mesh.py:195-199); the reference's own tests pin both forms to the same
+ * results (differt/tests/geometry/test_mesh.py:1984-2090).
+ */
+#ifndef DIFFERT_B200_H
+#define DIFFERT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRT_ABI_VERSION 1
+
+#define DRT_OK 0
+#define DRT_ERR_NULL_POINTER (-1)     /* a required pointer is NULL */
+#define DRT_ERR_BAD_EXTENT (-2)       /* a negative extent, or one beyond the int32 index range */
+#define DRT_ERR_UNSUPPORTED (-3)      /* order > DRT_MAX_ORDER, ndim > DRT_MAX_BATCH_DIMS ... */
+#define DRT_ERR_WORKSPACE (-4)        /* workspace too small (see *_workspace_bytes) */
+#define DRT_ERR_CUDA (-5)             /* a CUDA runtime call failed (sticky error on the context) */
+
+#define DRT_MAX_ORDER 8               /* mirrors per path candidate the fused kernels are built for */
+#define DRT_MAX_BATCH_DIMS 4          /* broadcast batch dims of the element-wise entry points */
+
+/* trace flags */
+#define DRT_TRACE_DENSE_BLOCKAGE 1u   /* test every candidate's segments against the mesh, like the
+                                         reference does; default (0) skips candidates that already
+                                         failed a cheaper test — same outputs, less work */
+
+typedef void *drt_stream_t;           /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define DRT_API __attribute__((visibility("default")))
+#else
+#define DRT_API
+#endif
+
+DRT_API int drt_abi_version(void);
+DRT_API const char *drt_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * Packed mesh.  48 bytes per triangle: v0, e1 = v1-v0, e2 = v2-v0, unit normal; padded to whole
+ * tiles of DRT_TILE_TRIANGLES with never-hit triangles.  Inactive triangles (mask[j] == 0) are
+ * stored as never-hit triangles when `mask` is given.  Replaces the per-call `wp.Mesh(...)` BVH
+ * build + `_WARP_MESHES_CACHE` (_mesh.py:55, 170-174): packing is stateless and takes microseconds.
+ * ------------------------------------------------------------------------------------------- */
+#define DRT_TILE_TRIANGLES 512
+DRT_API size_t drt_mesh_pack_bytes(int64_t num_triangles);
+
+/* from Mesh.vertices [V,3] + Mesh.triangles [T,3] (reference layout: _mesh.py:612-700) */
+DRT_API int drt_mesh_pack(drt_stream_t stream, int64_t num_vertices, int64_t num_triangles,
+                  const float *vertices, const int32_t *triangles, const uint8_t *mask /*nullable*/,
+                  void *pack_out);
+/* from triangle_vertices [T,3,3] (the form the pure-JAX functions take: _utils.py:1353-1364) */
+DRT_API int drt_mesh_pack_triangle_vertices(drt_stream_t stream, int64_t num_triangles,
+                                    const float *triangle_vertices,
+                                    const uint8_t *mask /*nullable*/, void *pack_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  ray_intersect_triangle — element-wise Möller–Trumbore over a broadcast batch
+ *     (reference: _utils.py:1157-1322).  Operand element (i0..i3) lives at
+ *     base + sum_d i_d * stride_d (strides in floats; 0 broadcasts).  Outputs are contiguous.
+ * ------------------------------------------------------------------------------------------- */
+DRT_API int drt_ray_intersect_triangle(drt_stream_t stream, int32_t ndim, const int64_t *shape_host,
+                               const float *ray_origins, const int64_t *o_strides_host,
+                               const float *ray_directions, const int64_t *d_strides_host,
+                               const float *triangle_vertices, const int64_t *tri_strides_host,
+                               float epsilon, float *t_out, uint8_t *hit_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  ray_intersect_any_triangle (reference: _utils.py:1353-1537; launcher _mesh.py:160-181).
+ *     out[r] = any_j [ hit(r,j; epsilon) and t(r,j) < 1 - hit_tol ].
+ *     `tests_done` (nullable, device int64) is incremented by the ray–triangle tests evaluated.
+ * ------------------------------------------------------------------------------------------- */
+DRT_API int drt_ray_intersect_any_triangle(drt_stream_t stream, int64_t num_rays, const float *ray_origins,
+                                   const float *ray_directions, const void *pack,
+                                   int64_t num_triangles, float epsilon, float hit_tol,
+                                   uint8_t *out, int64_t *tests_done /*nullable*/);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  first_triangle_hit_by_ray (reference: _utils.py:1775-1960; launcher _mesh.py:202-223).
+ *     miss = (-1, +inf).  `batch_size` reproduces the reference's tie rule on exactly equal
+ *     distances (lowest index inside a batch, latest batch across batches); <= 0 means one batch.
+ * K3b VJP of the hit distance w.r.t. vertices / origins / directions with the winning faces fixed
+ *     (reference: _mesh.py:226-255, 308-338).  g_vertices [V,3] is zero-filled by the callee.
+ * ------------------------------------------------------------------------------------------- */
+DRT_API int drt_first_triangle_hit_by_ray(drt_stream_t stream, int64_t num_rays, const float *ray_origins,
+                                  const float *ray_directions, const void *pack,
+                                  int64_t num_triangles, float epsilon, int64_t batch_size,
+                                  int32_t *out_index, float *out_t,
+                                  int64_t *tests_done /*nullable*/);
+DRT_API int drt_first_triangle_hit_by_ray_vjp(drt_stream_t stream, int64_t num_rays, int64_t num_vertices,
+                                      int64_t num_triangles, const float *vertices,
+                                      const int32_t *triangles, const float *ray_origins,
+                                      const float *ray_directions, const int32_t *faces,
+                                      const float *g_t, float *g_vertices, float *g_origins,
+                                      float *g_directions);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  triangles_visible_from_vertex with the ray directions supplied by the caller, as the
+ *     reference's own launcher takes them (_mesh.py:369-401; pure JAX: _utils.py:1702-1772).
+ *     vertices [B,3], ray_directions [B,num_rays,3] → out [B,T]; the callee zero-fills `out`.
+ * ------------------------------------------------------------------------------------------- */
+DRT_API int drt_triangles_visible_from_vertex(drt_stream_t stream, int64_t num_vertices_batch,
+                                      int64_t num_rays, const float *vertices,
+                                      const float *ray_directions, const void *pack,
+                                      int64_t num_triangles, float epsilon, uint8_t *out,
+                                      int64_t *tests_done /*nullable*/);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5  image_method over a broadcast batch (reference: _solver_image_method.py:206-363).
+ *     from/to: vec3 per batch element; mirrors: [k,3] per batch element (inner layout contiguous);
+ *     out [N,k,3] contiguous.
+ * K5b reverse mode; cotangent g_paths [N,k,3] contiguous; gradients are written per batch element
+ *     ([N,3],[N,3],[N,k,3],[N,k,3], contiguous) — the caller reduces over broadcast axes.
+ * ------------------------------------------------------------------------------------------- */
+DRT_API int drt_image_method(drt_stream_t stream, int32_t ndim, const int64_t *shape_host, int32_t order,
+                     const float *from_vertices, const int64_t *from_strides_host,
+                     const float *to_vertices, const int64_t *to_strides_host,
+                     const float *mirror_vertices, const int64_t *mv_strides_host,
+                     const float *mirror_normals, const int64_t *mn_strides_host, float *out_paths);
+DRT_API int drt_image_method_vjp(drt_stream_t stream, int32_t ndim, const int64_t *shape_host,
+                         int32_t order, const float *from_vertices,
+                         const int64_t *from_strides_host, const float *to_vertices,
+                         const int64_t *to_strides_host, const float *mirror_vertices,
+                         const int64_t *mv_strides_host, const float *mirror_normals,
+                         const int64_t *mn_strides_host, const float *g_paths, float *g_from,
+                         float *g_to, float *g_mirror_vertices, float *g_mirror_normals);
+
+/* a5 / a6 / a8 as stand-alone element-wise entry points over a broadcast batch
+ * (reference: _solver_image_method.py:11-79, 82-135, 386-454).  Outputs contiguous. */
+DRT_API int drt_image_of_vertex_with_respect_to_mirror(
+    drt_stream_t stream, int32_t ndim, const int64_t *shape_host, const float *vertex,
+    const int64_t *vertex_strides_host, const float *mirror_vertex, const int64_t *mv_strides_host,
+    const float *mirror_normal, const int64_t *mn_strides_host, float *out);
+DRT_API int drt_intersection_of_ray_with_plane(
+    drt_stream_t stream, int32_t ndim, const int64_t *shape_host, const float *ray_origin,
+    const int64_t *o_strides_host, const float *ray_direction, const int64_t *d_strides_host,
+    const float *plane_vertex, const int64_t *pv_strides_host, const float *plane_normal,
+    const int64_t *pn_strides_host, float *out);
+/* vertices: [k+2,3] per batch element, mirrors: [k,3] per batch element → out [N,k] u8 */
+DRT_API int drt_consecutive_vertices_are_on_same_side_of_mirror(
+    drt_stream_t stream, int32_t ndim, const int64_t *shape_host, int32_t order,
+    const float *vertices, const int64_t *v_strides_host, const float *mirror_vertices,
+    const int64_t *mv_strides_host, const float *mirror_normals, const int64_t *mn_strides_host,
+    uint8_t *out);
+
+/* ---------------------------------------------------------------------------------------------
+ * K6  fused trace + validate (reference: _solvers.py:499-770, non-smoothing branch).
+ *     Inputs in the reference's own layouts: Mesh.vertices [V,3], Mesh.triangles [T,3],
+ *     Mesh.mask [T] (nullable), tx [Ntx,3], rx [Nrx,3], path_candidates [C,k] int32.
+ *     Outputs = the fields of TracedPaths (_paths.py:77-116), dense and contiguous:
+ *       vertices [Ntx,Nrx,C,k+2,3] f32, objects [Ntx,Nrx,C,k+2] i32, mask [Ntx,Nrx,C] u8.
+ *     `stats` (nullable, device int64[4]): [0] ray–triangle tests evaluated, [1] candidates that
+ *     reached the blockage test, [2..3] reserved.  The callee zero-fills it.
+ * K6b reverse mode of `vertices` w.r.t. tx, rx and Mesh.vertices (mask carries no cotangent,
+ *     reference: _mesh.py:3087-3094).  g_* outputs are zero-filled by the callee.
+ * ------------------------------------------------------------------------------------------- */
+DRT_API size_t drt_trace_workspace_bytes(int64_t num_triangles, int64_t num_tx, int64_t num_rx,
+                                 int64_t num_candidates);
+DRT_API int drt_trace_path_candidates(drt_stream_t stream, int64_t num_vertices, int64_t num_triangles,
+                              const float *vertices, const int32_t *triangles,
+                              const uint8_t *triangle_mask /*nullable*/, int32_t assume_quads,
+                              int64_t num_tx, const float *tx, int64_t num_rx, const float *rx,
+                              int64_t num_candidates, int32_t order, const int32_t *path_candidates,
+                              float epsilon, float hit_tol, float min_len, uint32_t flags,
+                              void *workspace, size_t workspace_bytes, float *out_vertices,
+                              int32_t *out_objects, uint8_t *out_mask,
+                              int64_t *stats /*nullable*/);
+DRT_API int drt_trace_path_candidates_vjp(drt_stream_t stream, int64_t num_vertices, int64_t num_triangles,
+                                  const float *vertices, const int32_t *triangles,
+                                  int64_t num_tx, const float *tx, int64_t num_rx, const float *rx,
+                                  int64_t num_candidates, int32_t order,
+                                  const int32_t *path_candidates, const float *g_out_vertices,
+                                  float *g_tx, float *g_rx, float *g_vertices);
+
+/* ---------------------------------------------------------------------------------------------
+ * TracedPaths.masked() (reference: _paths.py:299-328): stable compaction of the valid paths in
+ * row-major (tx, rx, candidate) order.  out_count: device int64 = number of valid paths (may
+ * exceed `capacity`; only the first `capacity` are stored).  out_index: flat path index of each
+ * survivor.  workspace: drt_compact_workspace_bytes(num_paths).
+ * ------------------------------------------------------------------------------------------- */
+DRT_API size_t drt_compact_workspace_bytes(int64_t num_paths);
+DRT_API int drt_compact_valid_paths(drt_stream_t stream, int64_t num_paths, int32_t order,
+                            const float *vertices, const int32_t *objects, const uint8_t *mask,
+                            int64_t capacity, void *workspace, size_t workspace_bytes,
+                            int64_t *out_count, int64_t *out_index, float *out_vertices,
+                            int32_t *out_objects);
+
+/* ---------------------------------------------------------------------------------------------
+ * N1  path candidates of the complete graph, decoded on the device from the linear index
+ *     (reference: differt-core/src/geometry/graph.rs:286-491, count formula :356-362).
+ *     out [count, order] int32 = candidates start .. start+count-1 in the reference's order.
+ * ------------------------------------------------------------------------------------------- */
+DRT_API int drt_complete_graph_candidates(drt_stream_t stream, int64_t num_nodes, int32_t order,
+                                  int64_t start, int64_t count, int32_t stride_multiplier,
+                                  int32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFERT_B200_H */

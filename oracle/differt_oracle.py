@@ -611,3 +611,56 @@ def image_method_vjp(from_vertex, to_vertex, mirror_vertices, mirror_normals, g_
             g_mn[:, i] += g_c[:, None] * inc - F32(2.0) * c[:, None] * gI
         del g_next
     return g_img[:, 0].copy(), g_to, g_mv, g_mn
+
+
+def trace_vjp(vertices, triangles, tx, rx, path_candidates, g_out_vertices):
+    """Reverse mode of :func:`trace_path_candidates`'s ``vertices`` output w.r.t. ``tx``, ``rx`` and
+    the mesh ``vertices`` (``_solvers.py:535-586, 696-699`` under JAX autodiff): through the image
+    method, the mirror-vertex gather and ``Mesh.normals``; non-finite paths get zero gradient.
+    """
+    V = _f(vertices)
+    tris = np.asarray(triangles, np.int64)
+    tx, rx = _f(tx).reshape(-1, 3), _f(rx).reshape(-1, 3)
+    cand = np.asarray(path_candidates, np.int64)
+    C, k = cand.shape
+    ntx, nrx = tx.shape[0], rx.shape[0]
+    g = _f(g_out_vertices).reshape(ntx, nrx, C, k + 2, 3)
+    tri = V[tris[cand]]                                      # [C,k,3,3]
+    v0, v1, v2 = tri[..., 0, :], tri[..., 1, :], tri[..., 2, :]
+    with np.errstate(all="ignore"):
+        A, B = v1 - v0, v2 - v1
+        Nv = cross3(A, B)
+        L = np.sqrt(dot3(Nv, Nv))
+        Ls = np.where(L == 0.0, F32(1.0), L)
+        n = Nv / Ls[..., None]
+        N = ntx * nrx * C
+        fv = np.broadcast_to(tx[:, None, None, :], (ntx, nrx, C, 3)).reshape(N, 3)
+        tv = np.broadcast_to(rx[None, :, None, :], (ntx, nrx, C, 3)).reshape(N, 3)
+        mv = np.broadcast_to(v0[None, None], (ntx, nrx, C, k, 3)).reshape(N, k, 3)
+        mn = np.broadcast_to(n[None, None], (ntx, nrx, C, k, 3)).reshape(N, k, 3)
+        paths = image_method(fv, tv, mv, mn) if k > 0 else np.empty((N, 0, 3), np.float32)
+        finite = np.isfinite(paths).all(axis=(-1, -2)) & np.isfinite(fv).all(-1) & np.isfinite(tv).all(-1)
+        gf = np.where(finite[:, None, None], g.reshape(N, k + 2, 3), F32(0.0)).astype(np.float32)
+        if k > 0:
+            g_from, g_to, g_mv, g_mn = image_method_vjp(fv, tv, mv, mn, gf[:, 1:-1])
+            for arr in (g_from, g_to, g_mv, g_mn):
+                arr[~finite] = 0.0
+        else:
+            g_from = np.zeros((N, 3), np.float32)
+            g_to = np.zeros((N, 3), np.float32)
+            g_mv = g_mn = np.zeros((N, 0, 3), np.float32)
+        g_from = g_from + gf[:, 0]
+        g_to = g_to + gf[:, -1]
+        g_tx = g_from.reshape(ntx, nrx * C, 3).sum(axis=1)
+        g_rx = g_to.reshape(ntx, nrx, C, 3).sum(axis=(0, 2))
+        g_mv = g_mv.reshape(ntx * nrx, C, k, 3).sum(axis=0)
+        g_mn = g_mn.reshape(ntx * nrx, C, k, 3).sum(axis=0)
+        proj = dot3(n, g_mn)[..., None]
+        gN = np.where((L == 0.0)[..., None], g_mn, (g_mn - n * proj) / Ls[..., None])
+        gA, gB = cross3(B, gN), cross3(gN, A)
+    gV = np.zeros_like(V)
+    ti = tris[cand]                                           # [C,k,3]
+    np.add.at(gV, ti[..., 0], (g_mv - gA).astype(np.float32))
+    np.add.at(gV, ti[..., 1], (gA - gB).astype(np.float32))
+    np.add.at(gV, ti[..., 2], gB.astype(np.float32))
+    return g_tx.astype(np.float32), g_rx.astype(np.float32), gV

@@ -1,0 +1,676 @@
+"""GPU parity tests: the CUDA path (through the public API → C ABI) against the CPU oracle.
+
+Bar (BASELINE.json north_star): boolean / index outputs bit-exact; fp32 hit distances and path
+vertices within 1e-5 relative — in practice they are bit-exact too, because the kernels follow the
+oracle's operation order without FMA, and the tests assert that stronger property where it holds.
+Gradients (float atomics, different summation order) are compared at rtol 1e-4.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+from differt_b200 import scenes
+from oracle import c_oracle as co
+from oracle import differt_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north-star tolerance for fp32 hit points / path vertices
+
+
+@pytest.fixture(scope="module")
+def drt():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import differt_b200
+
+    return differt_b200
+
+
+def bits(x):
+    return np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+
+
+def scene_rays(rng, v, n):
+    lo, hi = v.min(0), v.max(0)
+    o = rng.uniform(lo, hi, size=(n, 3)).astype(np.float32)
+    e = rng.uniform(lo, hi, size=(n, 3)).astype(np.float32)
+    o[:, 2] = rng.uniform(0.5, 45.0, n)
+    e[:, 2] = rng.uniform(0.5, 45.0, n)
+    return o, (e - o).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# K1
+# ------------------------------------------------------------------------------------------------
+
+
+def test_k1_reference_kats(drt, kats):
+    k = kats["ray_intersect_triangle_hit_table"]  # test_utils.py:555-577
+    tri = np.array([k["triangle"]], np.float32)
+    for case in k["cases"]:
+        o = np.array(case["orig"], np.float32)
+        d = np.array(case["dest"], np.float32) - o
+        t, hit = drt.ray_intersect_triangle(o, d, tri)
+        assert bool(((t < 1.0) & hit)[0]) == case["expected"]
+    k = kats["ray_intersect_triangle_t_and_hit"]  # test_utils.py:580-606
+    o = np.array(k["ray_origin"], np.float32)
+    d = np.array(k["ray_directions"], np.float32)
+    tri = np.array(k["triangles"], np.float32)
+    t, hit = drt.ray_intersect_triangle(o[None, None, :], d[:, None, :], tri)
+    np.testing.assert_array_equal(t.numpy(), np.array(k["expected_t"], np.float32))
+    np.testing.assert_array_equal(hit.numpy(), np.array(k["expected_hit"]))
+
+
+@pytest.mark.parametrize(
+    "shapes", [((3,), (3,), (3, 3)), ((15, 5, 3), (15, 5, 3), (5, 3, 3)), ((7, 1, 3), (1, 9, 3), (7, 9, 3, 3)),
+               ((2, 3, 4, 5, 6, 3), (6, 3), (5, 1, 3, 3))]
+)
+@pytest.mark.parametrize("epsilon", [None, 1e-3])
+def test_k1_bit_exact_vs_oracle(drt, rng, shapes, epsilon):
+    o = rng.uniform(size=shapes[0]).astype(np.float32)
+    d = rng.uniform(-1, 1, size=shapes[1]).astype(np.float32)
+    tri = rng.uniform(size=shapes[2]).astype(np.float32)
+    t0, h0 = orc.ray_intersect_triangle(o, d, tri, epsilon=epsilon)
+    t1, h1 = drt.ray_intersect_triangle(o, d, tri, epsilon=epsilon)
+    assert tuple(t1.shape) == t0.shape
+    np.testing.assert_array_equal(bits(t1.numpy()), bits(t0))
+    np.testing.assert_array_equal(h1.numpy(), h0)
+    assert np.where(h0, t0 > 0, True).all()
+
+
+def test_k1_degenerate_inputs(drt):
+    # parallel ray (a == 0 → t = 0), zero-area triangle, NaN input: no hit, finite-or-NaN t like oracle
+    tri = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]], [[0, 0, 0], [0, 0, 0], [0, 0, 0]],
+                    [[np.nan, 0, 0], [1, 0, 0], [0, 1, 0]]], np.float32)
+    o = np.array([[0.2, 0.2, 1.0]] * 3, np.float32)
+    d = np.array([[1.0, 0.0, 0.0], [0.0, 0.0, -1.0], [0.0, 0.0, -1.0]], np.float32)
+    t0, h0 = orc.ray_intersect_triangle(o, d, tri)
+    t1, h1 = drt.ray_intersect_triangle(o, d, tri)
+    np.testing.assert_array_equal(h1.numpy(), h0)
+    assert not h0.any()
+    np.testing.assert_array_equal(np.isnan(t1.numpy()), np.isnan(t0))
+    np.testing.assert_array_equal(t1.numpy()[~np.isnan(t0)], t0[~np.isnan(t0)])
+
+
+# ------------------------------------------------------------------------------------------------
+# K2
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("epsilon", [None, 1e-6, 1e-2])
+@pytest.mark.parametrize("hit_tol", [None, 0.0, 1e-3, 0.5, -0.5])
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_k2_any_equals_any_of_elementwise(drt, rng, epsilon, hit_tol, use_mask):
+    # test_utils.py:649-714
+    o = rng.uniform(size=(21, 3)).astype(np.float32)
+    d = rng.uniform(-1, 1, size=(21, 3)).astype(np.float32)
+    tri = rng.uniform(size=(30, 3, 3)).astype(np.float32)
+    active = rng.uniform(size=30) > 0.5 if use_mask else None
+    kw = {} if epsilon is None else {"epsilon": epsilon}
+    got = drt.ray_intersect_any_triangle(o, d, tri, active, hit_tol=hit_tol, batch_size=11, **kw)
+    exp = orc.ray_intersect_any_triangle(o, d, tri, active, hit_tol=hit_tol, epsilon=epsilon)
+    np.testing.assert_array_equal(got.numpy(), exp)
+
+
+@pytest.mark.parametrize("grid,n_rays", [((1, 1), 37), ((3, 3), 4001), ((7, 7), 3000), ((29, 29), 2048)])
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_k2_scene_bit_exact(drt, rng, grid, n_rays, use_mask):
+    # T = 14 / 110 (one tile), 590 (two tiles, resident ring), 10 094 (20 tiles, streamed ring)
+    v, t = scenes.urban_grid(*grid)
+    tri = orc.triangle_vertices(v, t)
+    o, d = scene_rays(rng, v, n_rays)
+    active = rng.uniform(size=t.shape[0]) > 0.5 if use_mask else None
+    exp = co.ray_intersect_any_triangle(o, d, tri, active)
+    got = drt.ray_intersect_any_triangle(o, d, tri, active)
+    np.testing.assert_array_equal(got.numpy(), exp)
+    assert 0.02 < exp.mean() < 0.98
+    mesh = drt.Mesh.from_numpy(v, t, active)
+    got2 = mesh.ray_intersect_any_triangle(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda())
+    np.testing.assert_array_equal(got2.cpu().numpy(), exp)
+
+
+def test_k2_empty_and_ragged(drt, rng):
+    o = rng.uniform(size=(5, 3)).astype(np.float32)
+    d = rng.uniform(size=(5, 3)).astype(np.float32)
+    out = drt.ray_intersect_any_triangle(o, d, np.empty((0, 3, 3), np.float32))  # _utils.py:1441-1450
+    assert out.shape == (5,) and not out.any()
+    out = drt.ray_intersect_any_triangle(np.empty((0, 3), np.float32), np.empty((0, 3), np.float32),
+                                         rng.uniform(size=(4, 3, 3)).astype(np.float32))
+    assert out.shape == (0,)
+    # broadcast: one origin, many directions; batched meshes
+    tri = rng.uniform(size=(3, 6, 3, 3)).astype(np.float32)
+    dd = rng.uniform(-1, 1, size=(4, 1, 3)).astype(np.float32)
+    got = drt.ray_intersect_any_triangle(o[0], dd, tri)
+    exp = np.stack([orc.ray_intersect_any_triangle(o[0], dd[:, 0], tri[j]) for j in range(3)], axis=-1)
+    np.testing.assert_array_equal(got.numpy(), exp)
+
+
+def test_k2_counts_tests(drt, rng):
+    from differt_b200 import _lib
+    from differt_b200._tensor import ptr, stream_ptr
+    from differt_b200.geometry import pack_triangle_vertices
+
+    v, t = scenes.urban_grid(5, 5)
+    tri = torch.from_numpy(orc.triangle_vertices(v, t)).cuda()
+    o, d = scene_rays(rng, v, 1000)
+    # rays that cannot hit anything (pointing up from above the roofs): no early exit → R * T_pad tests
+    o[:, 2] = 100.0
+    d[:] = (0.0, 0.0, 1.0)
+    oc, dc = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    pack = pack_triangle_vertices(tri)
+    out = torch.empty(1000, dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.lib.drt_ray_intersect_any_triangle(
+        stream_ptr(), 1000, ptr(oc), ptr(dc), ptr(pack), t.shape[0], 1e-6, 1e-5, ptr(out), ptr(cnt)))
+    assert not out.any()
+    assert int(cnt.item()) == 1000 * 512
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 (+ K3b)
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("grid,n_rays", [((2, 2), 999), ((7, 7), 2000), ((29, 29), 1024)])
+@pytest.mark.parametrize("batch_size", [None, 7, 512])
+def test_k3_first_hit_bit_exact(drt, rng, grid, n_rays, batch_size):
+    v, t = scenes.urban_grid(*grid)
+    tri = orc.triangle_vertices(v, t)
+    o, d = scene_rays(rng, v, n_rays)
+    active = rng.uniform(size=t.shape[0]) > 0.2
+    i0, t0 = co.first_triangle_hit_by_ray(o, d, tri, active, batch_size=batch_size)
+    i1, t1 = drt.first_triangle_hit_by_ray(o, d, tri, active, batch_size=batch_size)
+    np.testing.assert_array_equal(bits(t1.numpy()), bits(t0))
+    np.testing.assert_array_equal(i1.numpy(), i0)  # includes the reference's tie rule on shared edges
+    assert (i0 == -1).any() and (i0 >= 0).any()
+    assert np.isinf(t0[i0 == -1]).all()
+
+
+def test_k3_tie_rule_and_empty(drt):
+    tri = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]]] * 3, np.float32)
+    o = np.array([[0.2, 0.2, 1.0]], np.float32)
+    d = np.array([[0.0, 0.0, -1.0]], np.float32)
+    assert int(drt.first_triangle_hit_by_ray(o, d, tri, batch_size=1)[0][0]) == 2   # latest batch wins
+    assert int(drt.first_triangle_hit_by_ray(o, d, tri, batch_size=2)[0][0]) == 2   # remainder batch wins
+    assert int(drt.first_triangle_hit_by_ray(o, d, tri, batch_size=None)[0][0]) == 0  # first in batch
+    assert int(drt.first_triangle_hit_by_ray(o, d, tri)[0][0]) == 0
+    i, t = drt.first_triangle_hit_by_ray(o, d, np.empty((0, 3, 3), np.float32))  # _utils.py:1848-1857
+    assert int(i[0]) == -1 and np.isinf(float(t[0]))
+
+
+def test_k3_mesh_method_matches_function(drt, rng):
+    # test_mesh.py:2004-2027: Mesh method == function on triangle_vertices
+    v, t = scenes.urban_grid(3, 3)
+    o, d = scene_rays(rng, v, 500)
+    mesh = drt.Mesh.from_numpy(v, t)
+    i0, t0 = drt.first_triangle_hit_by_ray(o, d, orc.triangle_vertices(v, t))
+    i1, t1 = mesh.first_triangle_hit_by_ray(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda())
+    np.testing.assert_array_equal(i1.cpu().numpy(), i0.numpy())
+    np.testing.assert_array_equal(bits(t1.cpu().numpy()), bits(t0.numpy()))
+
+
+def test_k3b_vjp_vs_oracle(drt, rng):
+    v, t = scenes.urban_grid(3, 3)
+    o, d = scene_rays(rng, v, 800)
+    mesh = drt.Mesh.from_numpy(v, t)
+    mesh.vertices.requires_grad_(True)
+    oc = torch.from_numpy(o).cuda().requires_grad_(True)
+    dc = torch.from_numpy(d).cuda().requires_grad_(True)
+    idx, tt = mesh.first_triangle_hit_by_ray(oc, dc)
+    assert not idx.requires_grad
+    g = rng.normal(size=800).astype(np.float32)
+    hit = (idx >= 0)
+    (torch.where(hit, tt, torch.zeros_like(tt)) * torch.from_numpy(g).cuda()).sum().backward()
+    faces = idx.cpu().numpy()
+    gV, gO, gD = orc.first_hit_vjp(v, t, o, d, faces, np.where(faces >= 0, g, 0).astype(np.float32))
+    np.testing.assert_allclose(oc.grad.cpu().numpy(), gO, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(dc.grad.cpu().numpy(), gD, rtol=1e-4, atol=1e-6)
+    scale = np.abs(gV).max()
+    np.testing.assert_allclose(mesh.vertices.grad.cpu().numpy(), gV, rtol=1e-3, atol=1e-5 * scale)
+
+
+def test_k3b_jacobian_structure_box(drt):
+    # test_mesh.py:2029-2073: 2x2x2 box, axis-aligned rays; Jacobians of t vs the brute-force path
+    v, t = scenes.box(2.0, 2.0, 2.0, with_top=True)
+    o = np.array([[0.1, 0.2, 3.0], [0.1, 3.0, 0.2], [3.0, 0.1, 0.2]], np.float32)
+    d = np.array([[0.0, 0.0, -1.0], [0.0, -1.0, 0.0], [-1.0, 0.0, 0.0]], np.float32)
+    mesh = drt.Mesh.from_numpy(v, t)
+    for r in range(3):
+        mesh.vertices.grad = None
+        mesh.vertices.requires_grad_(True)
+        oc = torch.from_numpy(o).cuda().requires_grad_(True)
+        dc = torch.from_numpy(d).cuda().requires_grad_(True)
+        idx, tt = mesh.first_triangle_hit_by_ray(oc, dc)
+        np.testing.assert_allclose(tt.detach().cpu().numpy(), 2.0, rtol=1e-6)
+        tt[r].backward()
+        e = np.zeros(3, np.float32)
+        e[r] = 1.0
+        gV, gO, gD = orc.first_hit_vjp(v, t, o, d, idx.cpu().numpy(), e)
+        np.testing.assert_allclose(oc.grad.cpu().numpy(), gO, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(dc.grad.cpu().numpy(), gD, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(mesh.vertices.grad.cpu().numpy(), gV, rtol=1e-5, atol=1e-5)
+        assert np.count_nonzero(gO[np.arange(3) != r]) == 0
+
+
+def test_k1_t_gradient(drt, rng):
+    o = rng.uniform(size=(40, 3)).astype(np.float32)
+    d = rng.uniform(-1, 1, size=(40, 3)).astype(np.float32)
+    tri = rng.uniform(size=(40, 3, 3)).astype(np.float32)
+    oc = torch.from_numpy(o).cuda().requires_grad_(True)
+    tc = torch.from_numpy(tri).cuda().requires_grad_(True)
+    t, _ = drt.ray_intersect_triangle(oc, torch.from_numpy(d).cuda(), tc)
+    g = rng.normal(size=40).astype(np.float32)
+    (t * torch.from_numpy(g).cuda()).sum().backward()
+    gV, gO, _ = orc.first_hit_vjp(tri.reshape(-1, 3), np.arange(120).reshape(40, 3), o, d, np.arange(40), g)
+    np.testing.assert_allclose(oc.grad.cpu().numpy(), gO, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(tc.grad.cpu().numpy().reshape(-1, 3), gV, rtol=1e-4, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# K4
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("num_rays", [20, 10_000])
+def test_k4_cube_counts(drt, kats, num_rays):  # test_utils.py:717-767
+    v, t = scenes.box(with_top=True)
+    tri = orc.triangle_vertices(v, t)
+    for case in kats["cube_visibility"]["cases"]:
+        vis = drt.triangles_visible_from_vertex(np.array(case["vertex"], np.float32), tri, num_rays=num_rays)
+        assert int(vis.sum()) == case["expected_number"]
+
+
+def test_k4_box_in_box_masked(drt, kats):  # test_utils.py:770-806
+    k = kats["box_in_box_visibility"]
+    vo, to = scenes.box(*k["outer"])
+    vi, ti = scenes.box(*k["inner"])
+    v, t = np.concatenate((vo, vi)), np.concatenate((to, ti + 8))
+    mask = np.concatenate((np.ones(len(to), bool), np.zeros(len(ti), bool)))
+    mesh = drt.Mesh.from_numpy(v, t, mask)
+    both = mesh.triangles_visible_from_vertex(np.array([k["tx"], k["rx"]], np.float32), num_rays=100_000)
+    both = both.cpu().numpy()
+    np.testing.assert_array_equal(both[0], both[1])
+    assert int(both[0].sum()) == k["expected_masked_count"]
+    np.testing.assert_array_equal(both[0], mask)
+
+
+def test_k4_bit_exact_with_shared_directions(drt, rng):
+    v, t = scenes.urban_grid(4, 4)
+    tri = orc.triangle_vertices(v, t)
+    active = rng.uniform(size=t.shape[0]) > 0.3
+    vertices = np.array([[45.0, 45.0, 60.0], [15.0, 45.0, 1.5], [-10.0, -10.0, 5.0]], np.float32)
+    dirs = np.stack([orc.visibility_directions(p, tri, active, 3001) for p in vertices])
+    got = drt.triangles_visible_from_vertex(vertices, tri, active, ray_directions=dirs)
+    exp = co.triangles_visible_from_vertex_dirs(vertices, dirs, tri, active)
+    np.testing.assert_array_equal(got.numpy(), exp)
+    assert exp.any() and not exp[:, ~active].any()
+
+
+def test_ray_generation_matches_oracle(drt, rng):
+    v, t = scenes.urban_grid(2, 2)
+    tri = orc.triangle_vertices(v, t)
+    world = np.concatenate((tri, tri.mean(axis=-2, keepdims=True)), axis=-2).reshape(-1, 3)
+    for p in ([15.0, 15.0, 60.0], [-30.0, 10.0, 1.5], [15.0, 15.0, 5.0]):
+        p = np.array(p, np.float32)
+        fr0 = orc.viewing_frustum(p, world)
+        fr1 = drt.viewing_frustum(p, world).numpy()
+        np.testing.assert_allclose(fr1, fr0, rtol=1e-6, atol=1e-6)
+        d0 = orc.fibonacci_lattice(500, fr0)
+        d1 = drt.fibonacci_lattice(500, frustum=fr0).numpy()
+        np.testing.assert_allclose(d1, d0, atol=2e-6)
+    np.testing.assert_allclose(drt.fibonacci_lattice(100).cpu().numpy(), orc.fibonacci_lattice(100), atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# K5 (+ K5b) and the small element-wise kernels
+# ------------------------------------------------------------------------------------------------
+
+
+def test_image_kats(drt, kats):
+    k = kats["image_of_vertex"]  # test_image_method.py:19-29
+    got = drt.image_of_vertex_with_respect_to_mirror(
+        np.array(k["vertices"], np.float32), np.array(k["mirror_vertices"], np.float32),
+        np.array(k["mirror_normals"], np.float32))
+    np.testing.assert_array_equal(got.numpy(), np.array(k["expected"], np.float32))
+    k = kats["intersection_of_ray_with_plane"]  # test_image_method.py:70-91
+    o = np.array(k["ray_origins"], np.float32)
+    d = np.array(k["ray_end"], np.float32)[None] - o
+    got = drt.intersection_of_ray_with_plane(o, d, np.array(k["plane_vertices"], np.float32),
+                                             np.array(k["plane_normals"], np.float32))
+    np.testing.assert_allclose(got.numpy(), np.array(k["expected"], np.float32), atol=1e-7)
+    k = kats["intersection_of_ray_with_plane_parallel"]  # test_image_method.py:94-130
+    n = np.array(k["plane_normals"], np.float32)
+    got = drt.intersection_of_ray_with_plane(o, d, np.array(k["plane_vertices_off"], np.float32), n)
+    assert torch.isposinf(got).all()
+    got = drt.intersection_of_ray_with_plane(o, d, np.array(k["plane_vertices_on"], np.float32), n)
+    np.testing.assert_array_equal(got.numpy(), o)
+
+
+@pytest.mark.parametrize("batch", [(), (10,), (10, 20, 30)])
+def test_k5_corridor(drt, kats, batch, rng):  # test_image_method.py:160-191
+    k = kats["corridor"]
+    mv = np.broadcast_to(np.array(k["mirror_vertices"], np.float32), (*batch, 4, 3)).copy()
+    mn = np.broadcast_to(np.array(k["mirror_normals"], np.float32), (*batch, 4, 3)).copy()
+    shift = rng.normal(size=mv.shape).astype(np.float32) * np.float32(0.1)
+    shift = shift - orc.dot3(shift, mn)[..., None] * mn
+    sign = rng.choice(np.array([1.0, -1.0], np.float32), size=mv.shape[:-1])
+    args = (np.array(k["from"], np.float32), np.array(k["to"], np.float32), mv + shift, mn * sign[..., None])
+    got = drt.image_method(*args).numpy()
+    np.testing.assert_allclose(got, np.broadcast_to(np.array(k["paths"], np.float32), got.shape), atol=1e-6)
+    np.testing.assert_array_equal(bits(got), bits(orc.image_method(*args)))
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 12])
+def test_k5_bit_exact_with_inf_cases(drt, rng, k):
+    N = 300
+    fv = rng.uniform(size=(N, 3)).astype(np.float32)
+    tv = rng.uniform(size=(N, 3)).astype(np.float32)
+    mv = rng.uniform(size=(N, k, 3)).astype(np.float32)
+    mn = orc.normalize(rng.uniform(-1, 1, size=(N, k, 3)).astype(np.float32))[0]
+    mv[::7] = 0.0
+    mn[::7] = np.array([0.0, 0.0, 1.0], np.float32)
+    fv[::7, 2] = 1.0
+    tv[::7, 2] = 1.0 if k % 2 == 0 else -1.0  # k-th image sits at z = ±1 → last ray parallel
+    exp = orc.image_method(fv, tv, mv, mn)
+    got = drt.image_method(fv, tv, mv, mn).numpy()
+    np.testing.assert_array_equal(bits(got), bits(exp))
+    assert np.isinf(exp).any()
+    # broadcast form used by the solver: [Ntx,1,1] x [1,Nrx,1] x [C,k]
+    got = drt.image_method(fv[:3, None, None], tv[None, :4, None], mv[:50], mn[:50]).numpy()
+    exp = orc.image_method(fv[:3, None, None], tv[None, :4, None], mv[:50], mn[:50])
+    assert got.shape == (3, 4, 50, k, 3)
+    np.testing.assert_array_equal(bits(got), bits(exp))
+
+
+def test_k5_zero_mirrors_and_same_side(drt, rng):
+    out = drt.image_method(np.zeros((4, 3), np.float32), np.ones((4, 3), np.float32),
+                           np.zeros((4, 0, 3), np.float32), np.zeros((4, 0, 3), np.float32))
+    assert tuple(out.shape) == (4, 0, 3)  # _solver_image_method.py:349-358
+    v = rng.uniform(-1, 1, size=(6, 7, 5, 3)).astype(np.float32)
+    mv = rng.uniform(-1, 1, size=(7, 3, 3)).astype(np.float32)
+    mn = rng.uniform(-1, 1, size=(6, 1, 3, 3)).astype(np.float32)
+    got = drt.consecutive_vertices_are_on_same_side_of_mirror(v, mv, mn)
+    exp = orc.consecutive_vertices_are_on_same_side_of_mirror(v, mv, mn)
+    np.testing.assert_array_equal(got.numpy(), exp)
+    with pytest.raises(TypeError):  # _solver_image_method.py:422-424
+        drt.consecutive_vertices_are_on_same_side_of_mirror(v[..., :4, :], mv, mn)
+
+
+@pytest.mark.parametrize("k", [1, 3, 8])
+def test_k5b_vjp_vs_oracle(drt, rng, k):
+    N = 64
+    fv = rng.uniform(size=(N, 3)).astype(np.float32)
+    tv = rng.uniform(size=(N, 3)).astype(np.float32)
+    mv = rng.uniform(size=(N, k, 3)).astype(np.float32)
+    mn = orc.normalize(rng.uniform(-1, 1, size=(N, k, 3)).astype(np.float32))[0]
+    g = rng.normal(size=(N, k, 3)).astype(np.float32)
+    ts = [torch.from_numpy(a).cuda().requires_grad_(True) for a in (fv, tv, mv, mn)]
+    (drt.image_method(*ts) * torch.from_numpy(g).cuda()).sum().backward()
+    exp = orc.image_method_vjp(fv, tv, mv, mn, g)
+    for tns, e in zip(ts, exp):
+        got = tns.grad.cpu().numpy()
+        scale = max(np.abs(e).max(), 1.0)
+        np.testing.assert_allclose(got, e, rtol=1e-4, atol=1e-5 * scale)
+
+
+def test_k5b_vjp_broadcast_reduction(drt, rng):
+    k = 2
+    fv = rng.uniform(size=(2, 1, 1, 3)).astype(np.float32)
+    tv = rng.uniform(size=(1, 3, 1, 3)).astype(np.float32)
+    mv = rng.uniform(size=(5, k, 3)).astype(np.float32)
+    mn = orc.normalize(rng.uniform(-1, 1, size=(5, k, 3)).astype(np.float32))[0]
+    g = rng.normal(size=(2, 3, 5, k, 3)).astype(np.float32)
+    ts = [torch.from_numpy(a).cuda().requires_grad_(True) for a in (fv, tv, mv, mn)]
+    (drt.image_method(*ts) * torch.from_numpy(g).cuda()).sum().backward()
+    N = 30
+    bf = np.broadcast_to(fv, (2, 3, 5, 3)).reshape(N, 3)
+    bt = np.broadcast_to(tv, (2, 3, 5, 3)).reshape(N, 3)
+    bv = np.broadcast_to(mv, (2, 3, 5, k, 3)).reshape(N, k, 3)
+    bn = np.broadcast_to(mn, (2, 3, 5, k, 3)).reshape(N, k, 3)
+    gf, gt, gv, gn = orc.image_method_vjp(bf, bt, bv, bn, g.reshape(N, k, 3))
+    np.testing.assert_allclose(ts[0].grad.cpu().numpy(), gf.reshape(2, 3, 5, 3).sum((1, 2))[:, None, None], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(ts[1].grad.cpu().numpy(), gt.reshape(2, 3, 5, 3).sum((0, 2))[None, :, None], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(ts[2].grad.cpu().numpy(), gv.reshape(6, 5, k, 3).sum(0), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(ts[3].grad.cpu().numpy(), gn.reshape(6, 5, k, 3).sum(0), rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# K6 (+ K6b), compaction, candidates
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("assume_quads", [False, True])
+@pytest.mark.parametrize("use_mask", [False, True])
+@pytest.mark.parametrize("order", [0, 1, 2, 3, 4])
+def test_k6_two_buildings_golden(drt, kats, two_buildings, order, assume_quads, use_mask):
+    # test_scene.py:116-260 (exhaustive solver; order 4 = 292 008 candidates without quads)
+    v, t = two_buildings
+    k = kats["two_buildings_scene"]
+    tx, rx = np.array(k["tx"], np.float32), np.array(k["rx"], np.float32)
+    mask = np.ones(t.shape[0], bool) if use_mask else None
+    mesh = drt.Mesh.from_numpy(v, t, mask, assume_quads)
+    paths = drt.trace_paths(mesh, tx, rx, order)
+    exp = k["orders"][str(order)]
+    exp_obj = np.array(exp["objects"], np.int32)
+    if assume_quads:
+        exp_obj = exp_obj - exp_obj % 2
+    exp_v = np.concatenate((tx[None], np.array(exp["vertices"], np.float32).reshape(-1, 3), rx[None]))
+    assert paths.mask.shape[:2] == (1, 1)
+    assert paths.num_valid_paths == 1
+    m = paths.masked()
+    np.testing.assert_allclose(m.vertices.cpu().numpy()[0], exp_v, rtol=k["rtol"])
+    np.testing.assert_array_equal(m.objects.cpu().numpy()[0], exp_obj)
+    # reflection law (test_scene.py:248-260)
+    if order > 0:
+        nrm = mesh.normals.cpu().numpy()[m.objects.cpu().numpy()[0, 1:-1]]
+        rays = orc.normalize(np.diff(m.vertices.cpu().numpy()[0], axis=0))[0]
+        np.testing.assert_allclose(-orc.dot3(rays[:-1], nrm), orc.dot3(rays[1:], nrm), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("assume_quads,use_mask,dense", [(False, False, False), (False, False, True),
+                                                         (True, False, False), (False, True, False),
+                                                         (True, True, True)])
+def test_k6_bit_exact_vs_oracle(drt, rng, order, assume_quads, use_mask, dense):
+    v, t = scenes.urban_grid(3, 3)
+    tx = np.array([[30.0, 30.0, 50.0], [0.0, 60.0, 45.0]], np.float32)
+    rx = scenes.receivers_grid(v, 4, 3)
+    n = t.shape[0] // 2 if assume_quads else t.shape[0]
+    cand = scenes.sampled_candidates(n, order, 300) * (2 if assume_quads else 1)
+    # make sure some valid paths exist: add the exhaustive order-1 set for the first receiver rows
+    if order == 1:
+        cand = np.concatenate((cand, (np.arange(n, dtype=np.int32) * (2 if assume_quads else 1))[:, None]))
+    mask = rng.uniform(size=t.shape[0]) > 0.15 if use_mask else None
+    if mask is not None and assume_quads:
+        mask = np.repeat(mask[::2], 2)
+    ev, eo, em, st = co.trace_path_candidates(v, t, tx, rx, cand, mask=mask, assume_quads=assume_quads, stages=True)
+    mesh = drt.Mesh.from_numpy(v, t, mask, assume_quads)
+    got = drt.trace_path_candidates(mesh, tx, rx, cand, dense_blockage=dense, with_stats=True)
+    np.testing.assert_array_equal(got.mask.cpu().numpy(), em)
+    np.testing.assert_array_equal(got.objects.cpu().numpy(), eo)
+    np.testing.assert_array_equal(bits(got.vertices.cpu().numpy()), bits(ev))
+    assert got.interaction_types.shape == (2, 12, cand.shape[0], order) and not got.interaction_types.any()
+    prevalid = st["inside"] & st["same_side"] & ~st["too_small"] & st["finite"]
+    if dense:
+        assert got.stats["tests_done"] > 0
+    elif mask is None:
+        assert got.stats["candidates_blockage_tested"] == int(prevalid.sum())
+    if order == 1 and not use_mask:
+        assert em.any()
+    m = got.masked()
+    np.testing.assert_array_equal(bits(m.vertices.cpu().numpy()), bits(ev[em]))
+    np.testing.assert_array_equal(m.objects.cpu().numpy(), eo[em])
+
+
+def test_k6_order_five_and_seven(drt, rng):
+    # K+1 = 6 uses the path-per-warp kernel, K+1 = 8 the generic segment kernel
+    v, t = scenes.urban_grid(2, 2)
+    tx = np.array([[15.0, 15.0, 60.0]], np.float32)
+    rx = scenes.receivers_grid(v, 2)
+    for order in (5, 7):
+        cand = scenes.sampled_candidates(t.shape[0], order, 64)
+        ev, eo, em = co.trace_path_candidates(v, t, tx, rx, cand)
+        for dense in (False, True):
+            got = drt.trace_path_candidates(drt.Mesh.from_numpy(v, t), tx, rx, cand, dense_blockage=dense)
+            np.testing.assert_array_equal(got.mask.cpu().numpy(), em)
+            np.testing.assert_array_equal(bits(got.vertices.cpu().numpy()), bits(ev))
+
+
+def test_k6_edge_cases(drt):
+    v, t = scenes.box(with_top=True)
+    mesh = drt.Mesh.from_numpy(v, t)
+    tx = np.array([[2.0, 0.0, 0.0]], np.float32)
+    rx = np.array([[3.0, 0.5, 0.2], [-3.0, 0.0, 0.0]], np.float32)
+    # zero candidates (_solvers.py:566-573)
+    p = drt.trace_path_candidates(mesh, tx, rx, np.empty((0, 2), np.int32))
+    assert p.vertices.shape == (1, 2, 0, 4, 3) and p.mask.shape == (1, 2, 0) and p.masked().vertices.shape[0] == 0
+    # order 0 = line of sight: first rx visible, second behind the cube
+    p = drt.trace_paths(mesh, tx, rx, 0)
+    np.testing.assert_array_equal(p.mask.cpu().numpy().ravel(), [True, False])
+    ev, eo, em = orc.trace_path_candidates(v, t, tx, rx, np.empty((1, 0), np.int32))
+    np.testing.assert_array_equal(p.mask.cpu().numpy(), em)
+    np.testing.assert_array_equal(p.objects.cpu().numpy(), eo)
+    # all triangles masked out ⇒ nothing valid at order 1 (test_scene.py:649-678)
+    mesh0 = drt.Mesh.from_numpy(v, t, np.zeros(12, bool))
+    assert drt.trace_paths(mesh0, tx, rx, 1).num_valid_paths == 0
+    # empty mesh, order 0: always line of sight
+    empty = drt.Mesh.from_numpy(np.empty((0, 3), np.float32), np.empty((0, 3), np.int32))
+    assert drt.trace_paths(empty, tx, rx, 0).mask.all()
+    with pytest.raises(NotImplementedError):
+        drt.trace_path_candidates(mesh, tx, rx, np.zeros((1, 1), np.int32), smoothing_factor=1.0)
+
+
+def test_k6_masked_mesh_equals_submesh(drt, two_buildings, kats):  # test_scene.py:585-647
+    v, t = two_buildings
+    k = kats["two_buildings_scene"]
+    tx, rx = np.array(k["tx"], np.float32), np.array(k["rx"], np.float32)
+    mask = np.random.default_rng(7).uniform(size=t.shape[0]) > 0.3
+    keep = np.nonzero(mask)[0]
+    sub = drt.trace_paths(drt.Mesh.from_numpy(v, t[keep]), tx, rx, 2)
+    cand_full = keep[sub.objects[0, 0, :, 1:-1].cpu().numpy()].astype(np.int32)
+    full = drt.trace_path_candidates(drt.Mesh.from_numpy(v, t, mask), tx, rx, cand_full)
+    np.testing.assert_array_equal(full.mask.cpu().numpy(), sub.mask.cpu().numpy())
+    np.testing.assert_array_equal(bits(full.vertices.cpu().numpy()), bits(sub.vertices.cpu().numpy()))
+
+
+@pytest.mark.parametrize("order", [0, 1, 3])
+def test_k6b_vjp_vs_oracle(drt, rng, order):
+    v, t = scenes.urban_grid(2, 2)
+    tx = np.array([[15.0, 15.0, 60.0], [40.0, -5.0, 55.0]], np.float32)
+    rx = scenes.receivers_grid(v, 3, 2)
+    cand = scenes.sampled_candidates(t.shape[0], order, 40) if order else np.empty((1, 0), np.int32)
+    mesh = drt.Mesh.from_numpy(v, t)
+    mesh.vertices.requires_grad_(True)
+    txc = torch.from_numpy(tx).cuda().requires_grad_(True)
+    rxc = torch.from_numpy(rx).cuda().requires_grad_(True)
+    paths = drt.trace_path_candidates(mesh, txc, rxc, cand)
+    g = rng.normal(size=tuple(paths.vertices.shape)).astype(np.float32)
+    (paths.vertices * torch.from_numpy(g).cuda()).sum().backward()
+    gtx, grx, gV = orc.trace_vjp(v, t, tx, rx, cand, g)
+    for got, exp in ((txc.grad, gtx), (rxc.grad, grx), (mesh.vertices.grad, gV)):
+        scale = max(np.abs(exp).max(), 1.0)
+        np.testing.assert_allclose(got.cpu().numpy(), exp, rtol=2e-3, atol=2e-5 * scale)
+
+
+def test_k6b_gradient_only_through_valid_paths(drt):
+    # the masked (valid) paths keep the autograd graph; a loss on them reaches tx
+    v, t = scenes.urban_grid(2, 2)
+    mesh = drt.Mesh.from_numpy(v, t)
+    tx = torch.tensor([[15.0, 15.0, 60.0]], device="cuda", requires_grad=True)
+    rx = torch.from_numpy(scenes.receivers_grid(v, 3)).cuda()
+    paths = drt.trace_paths(mesh, tx, rx, 1)
+    valid = paths.masked()
+    assert valid.vertices.shape[0] > 0
+    valid.vertices.sum().backward()
+    assert tx.grad is not None and torch.isfinite(tx.grad).all() and tx.grad.abs().sum() > 0
+
+
+def test_compaction_order_and_capacity(drt, rng):
+    from differt_b200 import _lib
+    from differt_b200._tensor import ptr, stream_ptr
+
+    P, k = 70_001, 2
+    mask = rng.uniform(size=P) < 0.03
+    verts = rng.normal(size=(P, k + 2, 3)).astype(np.float32)
+    objs = rng.integers(0, 1000, size=(P, k + 2)).astype(np.int32)
+    paths = drt.TracedPaths(torch.from_numpy(verts).cuda(), torch.from_numpy(objs).cuda(),
+                            torch.from_numpy(mask).cuda(), torch.zeros((P, k), dtype=torch.int32, device="cuda"))
+    m = paths.masked()
+    np.testing.assert_array_equal(m.vertices.cpu().numpy(), verts[mask])
+    np.testing.assert_array_equal(m.objects.cpu().numpy(), objs[mask])
+    # fused gather with a capacity smaller than the number of survivors
+    cap = 100
+    dv, do, dm = paths.vertices, paths.objects, paths.mask.to(torch.uint8)
+    ws = torch.empty(_lib.lib.drt_compact_workspace_bytes(P), dtype=torch.uint8, device="cuda")
+    count = torch.zeros(1, dtype=torch.int64, device="cuda")
+    idx = torch.full((cap,), -1, dtype=torch.int64, device="cuda")
+    ov = torch.zeros((cap, k + 2, 3), dtype=torch.float32, device="cuda")
+    oo = torch.zeros((cap, k + 2), dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib.drt_compact_valid_paths(stream_ptr(), P, k, ptr(dv), ptr(do), ptr(dm), cap, ptr(ws),
+                                                ws.numel(), ptr(count), ptr(idx), ptr(ov), ptr(oo)))
+    assert int(count.item()) == int(mask.sum())
+    np.testing.assert_array_equal(idx.cpu().numpy(), np.nonzero(mask)[0][:cap])
+    np.testing.assert_array_equal(ov.cpu().numpy(), verts[mask][:cap])
+    np.testing.assert_array_equal(oo.cpu().numpy(), objs[mask][:cap])
+
+
+@pytest.mark.parametrize("n,order", [(5, 1), (5, 3), (24, 2), (12, 4), (1, 1), (1, 2)])
+def test_candidate_decode_matches_host_enumeration(drt, n, order):
+    got = drt.generate_all_path_candidates(n, order).cpu().numpy()
+    exp = scenes.complete_graph_candidates(n, order)
+    np.testing.assert_array_equal(got, exp)
+    assert got.shape[0] == scenes.num_complete_graph_candidates(n, order)
+    if got.shape[0] and order > 1:
+        assert (np.diff(got, axis=1) != 0).all()
+    part = drt.generate_all_path_candidates(n, order, start=3, count=7, assume_quads=True).cpu().numpy()
+    np.testing.assert_array_equal(part, 2 * exp[3:10])
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE sizes (the oracle cannot reach these in seconds)
+# ------------------------------------------------------------------------------------------------
+
+
+def test_properties_at_scale(drt, rng):
+    v, t = scenes.urban_grid(29, 29)  # 10 094 triangles
+    tri = torch.from_numpy(orc.triangle_vertices(v, t)).cuda()
+    o, d = scene_rays(rng, v, 200_000)
+    oc, dc = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    any_hit = drt.ray_intersect_any_triangle(oc, dc, tri)
+    idx, tt = drt.first_triangle_hit_by_ray(oc, dc, tri)
+    thr = np.float32(1.0) - np.float32(100 * orc.EPS)
+    # any-hit ⇔ the nearest hit lies before the threshold
+    np.testing.assert_array_equal(any_hit.cpu().numpy(), (tt.cpu().numpy() < thr))
+    # permutation invariance of both reductions
+    perm = torch.from_numpy(rng.permutation(t.shape[0])).cuda()
+    np.testing.assert_array_equal(drt.ray_intersect_any_triangle(oc, dc, tri[perm]).cpu().numpy(),
+                                  any_hit.cpu().numpy())
+    idx2, tt2 = drt.first_triangle_hit_by_ray(oc, dc, tri[perm], batch_size=None)
+    np.testing.assert_array_equal(bits(tt2.cpu().numpy()), bits(tt.cpu().numpy()))
+    # the winning triangle reproduces t through the element-wise kernel
+    sel = (idx >= 0).nonzero().squeeze(-1)[:50_000]
+    t_el, hit_el = drt.ray_intersect_triangle(oc[sel], dc[sel], tri[idx[sel].long()])
+    assert hit_el.all()
+    np.testing.assert_array_equal(bits(t_el.cpu().numpy()), bits(tt[sel].cpu().numpy()))
+    # spot-check 2 000 rays against the C oracle
+    exp = co.ray_intersect_any_triangle(o[:2000], d[:2000], tri.cpu().numpy())
+    np.testing.assert_array_equal(any_hit[:2000].cpu().numpy(), exp)
+
+
+def test_trace_dense_equals_pruned_at_scale(drt):
+    v, t = scenes.urban_grid(29, 29)
+    mesh = drt.Mesh.from_numpy(v, t)
+    tx = np.array([[420.0, 420.0, 48.0]], np.float32)
+    rx = scenes.receivers_grid(v, 16)
+    cand = scenes.sampled_candidates(t.shape[0], 3, 512)
+    a = drt.trace_path_candidates(mesh, tx, rx, cand, with_stats=True)
+    b = drt.trace_path_candidates(mesh, tx, rx, cand, dense_blockage=True, with_stats=True)
+    assert torch.equal(a.mask, b.mask) and torch.equal(a.vertices, b.vertices)
+    assert b.stats["tests_done"] >= a.stats["tests_done"]
+    ev, eo, em = co.trace_path_candidates(v, t, tx, rx[:8], cand[:64], early_exit=True)
+    np.testing.assert_array_equal(a.mask[:, :8, :64].cpu().numpy(), em)
+    np.testing.assert_array_equal(bits(a.vertices[:, :8, :64].cpu().numpy()), bits(ev))
