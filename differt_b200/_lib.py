@@ -49,6 +49,9 @@ PROTOTYPES: dict[str, tuple] = {
          ptr, size_t, ptr, ptr, ptr, ptr]),
     "drt_trace_path_candidates_vjp": (
         C.c_int, [ptr, i64, i64, ptr, ptr, i64, ptr, i64, ptr, i64, i32, ptr, ptr, ptr, ptr, ptr]),
+    "drt_profile_reset": (C.c_int, []),
+    "drt_profile_count": (C.c_int, []),
+    "drt_profile_elapsed_ms": (C.c_int, [i32, C.POINTER(C.c_float)]),
     "drt_compact_workspace_bytes": (size_t, [i64]),
     "drt_compact_valid_paths": (
         C.c_int, [ptr, i64, i32, ptr, ptr, ptr, i64, ptr, size_t, ptr, ptr, ptr, ptr]),
@@ -56,6 +59,7 @@ PROTOTYPES: dict[str, tuple] = {
 }
 
 DRT_TRACE_DENSE_BLOCKAGE = 1
+DRT_TRACE_PROFILE = 2
 DRT_MAX_ORDER = 8
 DRT_MAX_BATCH_DIMS = 4
 DRT_TILE_TRIANGLES = 512

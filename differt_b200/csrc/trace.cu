@@ -481,9 +481,26 @@ inline TraceWorkspace trace_workspace_layout(int64_t T, int64_t P) {
     return w;
 }
 
+// per-thread profile ring (DRT_TRACE_PROFILE): event pairs around the blockage kernel
+struct ProfileRing {
+    cudaEvent_t start[DRT_PROFILE_SLOTS], stop[DRT_PROFILE_SLOTS];
+    int count = 0;
+    bool created = false;
+    bool ensure() {
+        if (created) return true;
+        for (int i = 0; i < DRT_PROFILE_SLOTS; ++i)
+            if (cudaEventCreate(&start[i]) != cudaSuccess || cudaEventCreate(&stop[i]) != cudaSuccess)
+                return false;
+        created = true;
+        return true;
+    }
+};
+static thread_local ProfileRing g_profile;
+
 template <int K>
-int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, const Tri48 *pack_active,
-                 float hit_tol, int64_t *tests_done, int64_t *units_scratch) {
+int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, bool profile,
+                 const Tri48 *pack_active, float hit_tol, int64_t *tests_done,
+                 int64_t *units_scratch) {
     const int threads = 256;
     const int64_t blocks = (a.P + threads - 1) / threads;
     const unsigned grid = unsigned(blocks < 148 * 8 ? blocks : 148 * 8);
@@ -504,6 +521,11 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, con
     const uint32_t *list = dense ? nullptr : a.list;
     constexpr int NSEG = K + 1;
     cudaError_t e;
+    int slot = -1;
+    if (profile && g_profile.ensure() && g_profile.count < DRT_PROFILE_SLOTS) {
+        slot = g_profile.count++;
+        cudaEventRecord(g_profile.start[slot], s);
+    }
     if constexpr (NSEG <= 6) {
         p.num_units = a.P;
         p.num_units_dev = dense ? nullptr : a.list_count;
@@ -522,6 +544,7 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, con
         SegSink<RPW> sink{a.out_mask, list, NSEG};
         e = launch_intersect<RPW, MODE_ANY, false>(s, p, src, sink, p.num_units);
     }
+    if (slot >= 0) cudaEventRecord(g_profile.stop[slot], s);
     return e == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
 }
 
@@ -570,6 +593,7 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
     int64_t *counters = reinterpret_cast<int64_t *>(ws + w.counters);
     if (cudaMemsetAsync(counters, 0, 256, s) != cudaSuccess) return DRT_ERR_CUDA;
     const bool dense = (flags & DRT_TRACE_DENSE_BLOCKAGE) != 0;
+    const bool profile = (flags & DRT_TRACE_PROFILE) != 0;
 
     TraceArgs a{};
     a.pack = pack_geom;
@@ -594,7 +618,8 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
     const bool quads = assume_quads != 0;
 #define DRT_TRACE_CASE(K)                                                                         \
     case K:                                                                                       \
-        rc = trace_launch<K>(s, a, quads, dense, pack_active, hit_tol, tests_done, units_scratch); \
+        rc = trace_launch<K>(s, a, quads, dense, profile, pack_active, hit_tol, tests_done,        \
+                             units_scratch);                                                      \
         break;
     switch (order) {
         DRT_TRACE_CASE(0) DRT_TRACE_CASE(1) DRT_TRACE_CASE(2) DRT_TRACE_CASE(3) DRT_TRACE_CASE(4)
@@ -640,6 +665,22 @@ int drt_trace_path_candidates_vjp(drt_stream_t stream, int64_t V, int64_t T, con
     }
 #undef DRT_VJP_CASE
     return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
+}
+
+int drt_profile_reset(void) {
+    g_profile.count = 0;
+    return g_profile.ensure() ? DRT_OK : DRT_ERR_CUDA;
+}
+
+int drt_profile_count(void) { return g_profile.count; }
+
+int drt_profile_elapsed_ms(int32_t slot, float *ms_host) {
+    if (ms_host == nullptr) return DRT_ERR_NULL_POINTER;
+    if (slot < 0 || slot >= g_profile.count) return DRT_ERR_BAD_EXTENT;
+    if (cudaEventSynchronize(g_profile.stop[slot]) != cudaSuccess) return DRT_ERR_CUDA;
+    return cudaEventElapsedTime(ms_host, g_profile.start[slot], g_profile.stop[slot]) == cudaSuccess
+               ? DRT_OK
+               : DRT_ERR_CUDA;
 }
 
 size_t drt_compact_workspace_bytes(int64_t P) {

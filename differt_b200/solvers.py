@@ -67,6 +67,8 @@ def trace_path_candidates(
     batch_size: int | None = 512,
     dense_blockage: bool = False,
     with_stats: bool = False,
+    _stats_accumulate: torch.Tensor | None = None,
+    _profile: bool = False,
 ) -> TracedPaths:
     """Trace every ``(tx, rx, candidate)`` with the image method and validate it.
 
@@ -74,7 +76,10 @@ def trace_path_candidates(
     ``mask [Ntx,Nrx,C]`` and ``interaction_types [Ntx,Nrx,C,k]``, exactly the reference's fields.
     ``dense_blockage=True`` makes the blockage stage test every candidate (the amount of work the
     reference does); the default skips candidates that already failed a cheaper test — identical
-    outputs.  ``batch_size`` is accepted and ignored.
+    outputs.  ``batch_size`` is accepted and ignored.  ``_stats_accumulate`` (device int64[4]) and
+    ``_profile`` are measurement hooks for ``bench.py``: the call's counters are added to the tensor
+    on the device (no host read), and an event pair is recorded around the blockage kernel
+    (``DRT_TRACE_PROFILE``).
     """
     if smoothing_factor is not None:
         raise NotImplementedError("smoothing_factor is not supported by the CUDA path (SURVEY.md §8a)")
@@ -94,7 +99,9 @@ def trace_path_candidates(
     out_v = torch.empty((ntx, nrx, C, k + 2, 3), dtype=torch.float32, device=dev)
     out_o = torch.empty((ntx, nrx, C, k + 2), dtype=torch.int32, device=dev)
     out_m = torch.empty((ntx, nrx, C), dtype=torch.uint8, device=dev)
-    stats = torch.zeros(4, dtype=torch.int64, device=dev) if with_stats else None
+    want_stats = with_stats or _stats_accumulate is not None
+    stats = torch.zeros(4, dtype=torch.int64, device=dev) if want_stats else None
+    flags = (_lib.DRT_TRACE_DENSE_BLOCKAGE if dense_blockage else 0) | (_lib.DRT_TRACE_PROFILE if _profile else 0)
     ws = torch.empty(max(lib.drt_trace_workspace_bytes(T, ntx, nrx, C), 1), dtype=torch.uint8, device=dev)
     check(
         lib.drt_trace_path_candidates(
@@ -104,8 +111,7 @@ def trace_path_candidates(
             10.0 * F32_EPS if epsilon is None else float(epsilon),
             100.0 * F32_EPS if hit_tol is None else float(hit_tol),
             10.0 * F32_EPS if min_len is None else float(min_len),
-            _lib.DRT_TRACE_DENSE_BLOCKAGE if dense_blockage else 0,
-            ptr(ws), ws.numel(), ptr(out_v), ptr(out_o), ptr(out_m), ptr(stats),
+            flags, ptr(ws), ws.numel(), ptr(out_v), ptr(out_o), ptr(out_m), ptr(stats),
         )
     )
     if torch.is_grad_enabled() and any(x.requires_grad for x in (mesh.vertices, tx, rx)):
@@ -121,6 +127,8 @@ def trace_path_candidates(
         interaction_types=it,
         confidence_threshold=confidence_threshold,
     )
+    if _stats_accumulate is not None:
+        _stats_accumulate.add_(stats)
     if with_stats:
         s = stats.cpu().tolist()
         paths.stats = {"tests_done": s[0], "candidates_blockage_tested": s[1]}

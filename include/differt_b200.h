@@ -50,6 +50,10 @@ extern "C" {
                                          reference does; default (0) skips candidates that already
                                          failed a cheaper test — same outputs, less work */
 
+#define DRT_TRACE_PROFILE 2u          /* record a CUDA-event pair around the blockage (all-pairs)
+                                         kernel of this call into the calling thread's profile
+                                         ring (drt_profile_*); measurement hook for bench.py */
+
 typedef void *drt_stream_t;           /* cudaStream_t */
 
 #if defined(__GNUC__)
@@ -196,6 +200,15 @@ DRT_API int drt_trace_path_candidates_vjp(drt_stream_t stream, int64_t num_verti
                                   int64_t num_candidates, int32_t order,
                                   const int32_t *path_candidates, const float *g_out_vertices,
                                   float *g_tx, float *g_rx, float *g_vertices);
+
+/* Profile ring (per host thread, 64 slots).  A call made with DRT_TRACE_PROFILE records one event
+ * pair on its stream, immediately before and after the blockage kernel, into the next free slot.
+ * drt_profile_elapsed_ms waits for that slot's stop event and returns the device time between the
+ * two events.  Nothing else in the library keeps state. */
+#define DRT_PROFILE_SLOTS 64
+DRT_API int drt_profile_reset(void);
+DRT_API int drt_profile_count(void);
+DRT_API int drt_profile_elapsed_ms(int32_t slot, float *ms_host);
 
 /* ---------------------------------------------------------------------------------------------
  * TracedPaths.masked() (reference: _paths.py:299-328): stable compaction of the valid paths in
