@@ -20,8 +20,18 @@
 
 namespace drt {
 
-constexpr int kStages = 4;
-constexpr int kWarps = 8;
+#ifndef DRT_STAGES
+#define DRT_STAGES 4
+#endif
+#ifndef DRT_WARPS
+#define DRT_WARPS 8
+#endif
+#ifndef DRT_CTAS_PER_SM
+#define DRT_CTAS_PER_SM 2
+#endif
+constexpr int kStages = DRT_STAGES;
+constexpr int kWarps = DRT_WARPS;
+constexpr int kCtasPerSm = DRT_CTAS_PER_SM;
 constexpr int kThreads = kWarps * 32;
 constexpr size_t kRingBytes = size_t(kStages) * kTile * sizeof(Tri48);
 constexpr size_t kSmemBytes = kRingBytes + kStages * sizeof(uint64_t);
@@ -52,8 +62,14 @@ __device__ __forceinline__ uint32_t tie_key(int64_t j, int64_t bs, int64_t T) {
 // Sink: __device__ void any(int64_t unit, uint32_t hit_mask, uint32_t valid_mask)           (ANY)
 //       __device__ void first(int64_t unit, int r, int32_t idx, float t)                    (FIRST)
 // PATH = true: the unit is finished as soon as any of its rays hits (K6 blockage).
+//
+// Scheduling: the CTA walks the tile ring in lockstep (one barrier per tile, which also hands the
+// consumed slot back to the TMA producer), but every WARP owns its own sequence of work units
+// (unit = global warp id + n * total warps) and moves on to its next unit the moment the current one
+// is decided — after an early exit or after it has seen all NT tiles, wherever in the cycle that
+// happens.  No warp idles while another one of its CTA still works on a long unit.
 template <int RPW, int MODE, bool PATH, class Src, class Sink>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 intersect_kernel(const CoreParams p, const Src src, const Sink sink) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Tri48 *ring = reinterpret_cast<Tri48 *>(smem_raw);
@@ -61,8 +77,8 @@ intersect_kernel(const CoreParams p, const Src src, const Sink sink) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t num_units = p.num_units_dev ? *p.num_units_dev : p.num_units;
-    const int64_t num_blocks = (num_units + kWarps - 1) / kWarps;
-    if (static_cast<int64_t>(blockIdx.x) >= num_blocks) return;
+    const int64_t total_warps = int64_t(gridDim.x) * kWarps;
+    if (int64_t(blockIdx.x) * kWarps >= num_units) return;
 
     const int NT = p.num_tiles;
     const bool resident = NT <= kStages;
@@ -91,17 +107,20 @@ intersect_kernel(const CoreParams p, const Src src, const Sink sink) {
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s) issue();
 
-    int64_t tests = 0;
-    for (int64_t blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
-        const int64_t unit = blk * kWarps + warp;
-        float3 o[RPW], d[RPW];
-        uint32_t valid = 0;
-        if (unit < num_units) valid = src.load(unit, o, d);
-        uint32_t active = valid;  // warp-uniform mask of rays still being tested
-        uint32_t hit_any = 0;     // MODE_ANY: warp-uniform mask of rays that hit
-        float best_t[RPW];
-        uint32_t best_key[RPW];
-        int32_t best_idx[RPW];
+    // per-warp state of the unit in flight
+    int64_t unit = int64_t(blockIdx.x) * kWarps + warp;
+    bool live = unit < num_units;
+    float3 o[RPW], d[RPW];
+    uint32_t valid = 0, active = 0, hit_any = 0;
+    int seen = 0;
+    float best_t[RPW];
+    uint32_t best_key[RPW];
+    int32_t best_idx[RPW];
+    auto begin_unit = [&]() {
+        valid = src.load(unit, o, d);
+        active = valid;
+        hit_any = 0;
+        seen = 0;
         if (MODE == MODE_FIRST) {
 #pragma unroll
             for (int r = 0; r < RPW; ++r) {
@@ -110,84 +129,84 @@ intersect_kernel(const CoreParams p, const Src src, const Sink sink) {
                 best_idx[r] = -1;
             }
         }
+    };
+    if (live) begin_unit();
 
-        for (int tl = 0; tl < NT; ++tl) {
-            issue();
-            const uint32_t stage = resident ? it % static_cast<uint32_t>(NT) : it % kStages;
-            if (!resident || it < static_cast<uint32_t>(NT)) mbar_wait(&bars[stage], (it / kStages) & 1u);
-            const uint32_t tile_index = it % static_cast<uint32_t>(NT);
-            ++it;
+    int64_t tests = 0;
+    while (true) {
+        issue();
+        const uint32_t stage = resident ? it % static_cast<uint32_t>(NT) : it % kStages;
+        if (!resident || it < static_cast<uint32_t>(NT)) mbar_wait(&bars[stage], (it / kStages) & 1u);
+        const uint32_t tile_index = it % static_cast<uint32_t>(NT);
+        ++it;
 
-            if (active) {
-                const Tri48 *tile = ring + size_t(stage) * kTile;
-                uint32_t lane_hits = 0;
+        if (live) {
+            const Tri48 *tile = ring + size_t(stage) * kTile;
+            uint32_t lane_hits = 0;
 #pragma unroll 2
-                for (int j = lane; j < kTile; j += 32) {
-                    const float4 a = tile[j].a, b = tile[j].b, c = tile[j].c;
-                    const Tri tr = unpack(a, b, c);
+            for (int j = lane; j < kTile; j += 32) {
+                const float4 a = tile[j].a, b = tile[j].b, c = tile[j].c;
+                const Tri tr = unpack(a, b, c);
 #pragma unroll
-                    for (int r = 0; r < RPW; ++r) {
-                        if (active & (1u << r)) {
-                            float t;
-                            const bool hit = mt_exact(o[r], d[r], tr, p.eps, t);
-                            if (MODE == MODE_ANY) {
-                                lane_hits |= (hit && (t < p.thr)) ? (1u << r) : 0u;
-                            } else {
-                                if (hit && t <= best_t[r]) {
-                                    const int64_t gj = int64_t(tile_index) * kTile + j;
-                                    const uint32_t key = tie_key(gj, p.batch_size, p.num_triangles);
-                                    if (t < best_t[r] || key < best_key[r]) {
-                                        best_t[r] = t;
-                                        best_key[r] = key;
-                                        best_idx[r] = static_cast<int32_t>(gj);
-                                    }
+                for (int r = 0; r < RPW; ++r) {
+                    // PATH units keep all their rays until the unit is decided: no per-ray branch
+                    if (PATH || (active & (1u << r))) {
+                        float t;
+                        const bool hit = mt_exact(o[r], d[r], tr, p.eps, t);
+                        if (MODE == MODE_ANY) {
+                            lane_hits |= (hit && (t < p.thr)) ? (1u << r) : 0u;
+                        } else {
+                            if (hit && t <= best_t[r]) {
+                                const int64_t gj = int64_t(tile_index) * kTile + j;
+                                const uint32_t key = tie_key(gj, p.batch_size, p.num_triangles);
+                                if (t < best_t[r] || key < best_key[r]) {
+                                    best_t[r] = t;
+                                    best_key[r] = key;
+                                    best_idx[r] = static_cast<int32_t>(gj);
                                 }
                             }
                         }
                     }
                 }
-                tests += int64_t(__popc(active)) * kTile;
-                if (MODE == MODE_ANY) {
-                    const uint32_t m = __reduce_or_sync(kFull, lane_hits);
-                    hit_any |= m;
-                    active = (PATH && m) ? 0u : (active & ~m);
-                }
             }
-            // all warps are done with this stage; the producer may refill it next iteration
-            if (__syncthreads_and(active == 0)) break;
-        }
-
-        if (unit < num_units) {
+            tests += int64_t(__popc(active)) * kTile;
+            ++seen;
             if (MODE == MODE_ANY) {
-                if (lane == 0) sink.any(unit, hit_any, valid);
-            } else {
+                const uint32_t m = __reduce_or_sync(kFull, lane_hits) & active;
+                hit_any |= m;
+                active = (PATH && m) ? 0u : (active & ~m);
+            }
+            if (seen == NT || active == 0) {  // unit decided: emit, move on to this warp's next unit
+                if (MODE == MODE_ANY) {
+                    if (lane == 0) sink.any(unit, hit_any, valid);
+                } else {
 #pragma unroll
-                for (int r = 0; r < RPW; ++r) {
-                    const uint32_t tb = float_order_bits(best_t[r]);
-                    const uint32_t tmin = __reduce_min_sync(kFull, tb);
-                    const uint32_t key = (tb == tmin) ? best_key[r] : 0xffffffffu;
-                    const uint32_t kmin = __reduce_min_sync(kFull, key);
-                    const uint32_t owner = __ballot_sync(kFull, tb == tmin && key == kmin);
-                    const int src_lane = __ffs(owner) - 1;
-                    const int32_t idx = __shfl_sync(kFull, best_idx[r], src_lane);
-                    const float t = __shfl_sync(kFull, best_t[r], src_lane);
-                    if (lane == 0 && (valid & (1u << r))) sink.first(unit, r, idx, t);
+                    for (int r = 0; r < RPW; ++r) {
+                        const uint32_t tb = float_order_bits(best_t[r]);
+                        const uint32_t tmin = __reduce_min_sync(kFull, tb);
+                        const uint32_t key = (tb == tmin) ? best_key[r] : 0xffffffffu;
+                        const uint32_t kmin = __reduce_min_sync(kFull, key);
+                        const uint32_t owner = __ballot_sync(kFull, tb == tmin && key == kmin);
+                        const int src_lane = __ffs(owner) - 1;
+                        const int32_t idx = __shfl_sync(kFull, best_idx[r], src_lane);
+                        const float t = __shfl_sync(kFull, best_t[r], src_lane);
+                        if (lane == 0 && (valid & (1u << r))) sink.first(unit, r, idx, t);
+                    }
                 }
+                unit += total_warps;
+                live = unit < num_units;
+                if (live) begin_unit();
             }
         }
+        // every warp is done with this stage (the producer refills it next iteration); stop when no
+        // warp of the CTA has a unit left
+        if (!__syncthreads_or(live)) break;
     }
 
     // never exit with bulk copies still in flight
-    if (!resident) {
-        while (it < issued) {
-            mbar_wait(&bars[it % kStages], (it / kStages) & 1u);
-            ++it;
-        }
-    } else {
-        while (it < issued) {
-            mbar_wait(&bars[it % kStages], 0u);
-            ++it;
-        }
+    while (it < issued) {
+        mbar_wait(&bars[it % kStages], resident ? 0u : ((it / kStages) & 1u));
+        ++it;
     }
     if (p.tests_done != nullptr) {
         // one atomic per warp (lanes hold identical counts)
@@ -212,7 +231,8 @@ inline cudaError_t launch_intersect(cudaStream_t stream, const CoreParams &p, co
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t blocks = (max_units + kWarps - 1) / kWarps;
     if (blocks <= 0) return cudaSuccess;
-    const int grid = static_cast<int>(blocks < int64_t(sms) * 2 ? blocks : int64_t(sms) * 2);
+    const int64_t resident_ctas = int64_t(sms) * kCtasPerSm;
+    const int grid = static_cast<int>(blocks < resident_ctas ? blocks : resident_ctas);
     kern<<<grid, kThreads, kSmemBytes, stream>>>(p, src, sink);
     return cudaGetLastError();
 }
