@@ -9,8 +9,12 @@ A *step* is one pass of the hot path over one batch of synthetic input: trace-an
 (tx, rx, candidate) of the workload, with the blockage test evaluated for every candidate like the
 reference does ("dense"), followed by the compaction of the valid paths (`TracedPaths.masked()`)
 and — for N > 1, where every rank traces its own shard of the candidates — ONE all-gather of the
-survivors.  The metric is BASELINE.json's: ray–triangle tests per second, counting only
-Möller–Trumbore evaluations that were actually executed (device counter), never skipped ones.
+survivors.  The metric is BASELINE.json's: ray–triangle tests per second, counted as SURVEY.md
+§8(d) defines it — every (ray, triangle) pair the step DECIDES, rays x triangles ("algorithmic",
+what the reference's dense evaluation executes) — so that `value` is whole-job throughput in the
+same unit for both arms.  The Möller–Trumbore evaluations the kernel actually executed (device
+counter; fewer, because an any-hit query stops at the first blocking tile) are reported next to it
+as `executed_tests_per_s`, and the roofline is computed from the EXECUTED count only.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions of `value`, `e2e`,
 `roofline` and `cpu_baseline`.
@@ -213,7 +217,9 @@ def workload_config(wl: dict, world: int, **extra) -> dict:
         "num_rx": int(wl["rx"].shape[0]), "order": int(wl["order"]),
         "candidates_per_gpu": int(wl["cand"].shape[0]), "candidate_pairs_per_gpu": pairs,
         "algorithmic_tests_per_gpu_step": pairs * (wl["order"] + 1) * T,
-        "blockage": "dense (every candidate, like the reference); tests counted = executed",
+        "blockage": "dense: every segment of every candidate is submitted to the any-hit kernel, like "
+                    "the reference; value counts rays x triangles decided, executed_tests_per_s the "
+                    "Moller-Trumbore evaluations actually run",
         "parallelism": f"candidate shards x{world}, one all-gather of valid paths",
         "l2_policy": "no flush: each step writes >1.3 GB of path vertices/objects (L2 is 126 MB); "
                      "the 0.5 MB packed mesh is L2/shared-memory resident by design",
@@ -355,8 +361,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         traffic_file = ROOT / "profiles" / "traffic.json"
         if traffic_file.exists():
             roofline["traffic"] = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch")
+        algo_step = world * workload_config(wl, world)["algorithmic_tests_per_gpu_step"]
         line = {
-            "metric": METRIC, "value": tests / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": algo_step * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(wl, world),
@@ -364,9 +371,10 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             * args.steps / (ms * 1e-3),
             "valid_paths_per_s": valid_total * args.steps / (ms * 1e-3),
             "valid_paths_per_step": valid_total,
-            "executed_fraction_of_algorithmic": tests / max(
-                world * args.steps * workload_config(wl, world)["algorithmic_tests_per_gpu_step"], 1),
-            "e2e": {"value": tests_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "executed_tests_per_s": tests / (ms * 1e-3),
+            "executed_fraction_of_algorithmic": tests / max(args.steps * algo_step, 1),
+            "e2e": {"value": algo_step * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "executed_tests_per_s": tests_e2e / (ms_e2e * 1e-3), "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                     "valid_paths_gathered": num_valid_global},
             "gpu_launches": args.steps * 6,  # pack, stage A, blockage, 3 compaction kernels per step

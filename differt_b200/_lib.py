@@ -6,10 +6,12 @@ There is deliberately no fallback: if the CUDA library is missing, importing thi
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libdiffert_b200.so"
+# DIFFERT_B200_LIB selects a tuning variant of the SAME library (differt_b200.build --variant)
+LIB_PATH = Path(os.environ.get("DIFFERT_B200_LIB") or _PKG / "libdiffert_b200.so")
 
 i32, i64, f32, u32 = C.c_int32, C.c_int64, C.c_float, C.c_uint32
 ptr, size_t = C.c_void_p, C.c_size_t

@@ -58,15 +58,23 @@ def is_stale() -> bool:
     return any(p.stat().st_mtime > t for p in _deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | None = None,
+          out: Path | None = None) -> Path:
+    """Compile every ``csrc/*.cu`` and link ``libdiffert_b200.so``.  ``extra_flags`` / ``out`` build a
+    tuning variant elsewhere (``python -m differt_b200.build --variant NAME -DDRT_STAGES=3 ...``)."""
+    global LIB, OBJ_DIR
+    if out is not None:
+        LIB, OBJ_DIR, force = out, out.parent / "_obj", True
+        out.parent.mkdir(parents=True, exist_ok=True)
     if not force and not is_stale():
         return LIB
     OBJ_DIR.mkdir(exist_ok=True)
     exe = nvcc()
+    flags = [*NVCC_FLAGS, *(extra_flags or [])]
 
     def compile_one(src: Path) -> Path:
         obj = OBJ_DIR / (src.stem + ".o")
-        cmd = [exe, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
+        cmd = [exe, *flags, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         res = subprocess.run(cmd, capture_output=True, text=True)
@@ -88,4 +96,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:  # tuning builds: variants/<name>/libdiffert_b200.so (+ DIFFERT_B200_LIB)
+        name = sys.argv[sys.argv.index("--variant") + 1]
+        defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+        print(build(extra_flags=defs, out=PKG.parent / "variants" / name / "libdiffert_b200.so",
+                    verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

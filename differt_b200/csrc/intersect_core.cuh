@@ -21,10 +21,13 @@
 namespace drt {
 
 #ifndef DRT_STAGES
-#define DRT_STAGES 4
+#define DRT_STAGES 2
 #endif
 #ifndef DRT_WARPS
-#define DRT_WARPS 8
+#define DRT_WARPS 16
+#endif
+#ifndef DRT_UNROLL
+#define DRT_UNROLL 2
 #endif
 #ifndef DRT_CTAS_PER_SM
 #define DRT_CTAS_PER_SM 2
@@ -32,6 +35,7 @@ namespace drt {
 constexpr int kStages = DRT_STAGES;
 constexpr int kWarps = DRT_WARPS;
 constexpr int kCtasPerSm = DRT_CTAS_PER_SM;
+constexpr int kUnroll = DRT_UNROLL;
 constexpr int kThreads = kWarps * 32;
 constexpr size_t kRingBytes = size_t(kStages) * kTile * sizeof(Tri48);
 constexpr size_t kSmemBytes = kRingBytes + kStages * sizeof(uint64_t);
@@ -143,7 +147,7 @@ intersect_kernel(const CoreParams p, const Src src, const Sink sink) {
         if (live) {
             const Tri48 *tile = ring + size_t(stage) * kTile;
             uint32_t lane_hits = 0;
-#pragma unroll 2
+#pragma unroll kUnroll
             for (int j = lane; j < kTile; j += 32) {
                 const float4 a = tile[j].a, b = tile[j].b, c = tile[j].c;
                 const Tri tr = unpack(a, b, c);

@@ -1,0 +1,186 @@
+// XLA typed-FFI handlers over the differt_b200 C ABI — the reference-side shim a DiffeRT maintainer
+// would compile next to jaxlib (`g++ -shared -fPIC -I$(python -c "import jax; print(jax.ffi.include_dir())")
+// -I include integration/xla_ffi.cc -L differt_b200 -ldiffert_b200 -o libdiffert_b200_xla.so`).
+//
+// NOT BUILT IN THIS IMAGE: jaxlib (and therefore xla/ffi/api/ffi.h) is not installed, so this file is
+// documentation-grade source, kept out of differt_b200/csrc (build.py compiles *.cu only).  It replaces
+// the three Warp launchers the reference registers through wp.jax_callable:
+//   _ray_intersect_any_triangle_anyhit_func   differt/src/differt/geometry/_mesh.py:160-181
+//   _first_triangle_hit_by_ray_func           differt/src/differt/geometry/_mesh.py:202-223
+//   _triangles_visible_from_vertex_func       differt/src/differt/geometry/_mesh.py:369-401
+// and adds the fused trace step (_solvers.py:499-770) as a fourth target.
+#include <cuda_runtime_api.h>
+
+#include "differt_b200.h"
+#include "xla/ffi/api/ffi.h"
+
+namespace ffi = xla::ffi;
+
+static ffi::Error Check(int rc) {
+    if (rc == DRT_OK) return ffi::Error::Success();
+    return ffi::Error(rc == DRT_ERR_WORKSPACE ? ffi::ErrorCode::kResourceExhausted
+                                              : ffi::ErrorCode::kInvalidArgument,
+                      drt_error_string(rc));
+}
+
+// vertices [V,3] f32, triangles [T,3] i32, mask [T] u8 (T may be 0-sized → no mask),
+// origins / directions [R,3] f32 → hit [R] pred
+static ffi::Error AnyHitImpl(cudaStream_t stream, ffi::ScratchAllocator scratch,
+                             ffi::Buffer<ffi::F32> vertices, ffi::Buffer<ffi::S32> triangles,
+                             ffi::Buffer<ffi::U8> mask, ffi::Buffer<ffi::F32> origins,
+                             ffi::Buffer<ffi::F32> directions, float epsilon, float hit_tol,
+                             ffi::ResultBuffer<ffi::PRED> hit) {
+    const int64_t V = vertices.dimensions()[0], T = triangles.dimensions()[0];
+    const int64_t R = origins.dimensions()[0];
+    auto pack = scratch.Allocate(drt_mesh_pack_bytes(T));
+    if (!pack.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "pack scratch");
+    const uint8_t *m = mask.element_count() ? mask.typed_data() : nullptr;
+    if (int rc = drt_mesh_pack(stream, V, T, vertices.typed_data(), triangles.typed_data(), m, *pack))
+        return Check(rc);
+    return Check(drt_ray_intersect_any_triangle(stream, R, origins.typed_data(),
+                                                directions.typed_data(), *pack, T, epsilon, hit_tol,
+                                                reinterpret_cast<uint8_t *>(hit->typed_data()),
+                                                nullptr));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DrtRayIntersectAnyTriangle, AnyHitImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Ctx<ffi::ScratchAllocator>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Attr<float>("epsilon")
+                                  .Attr<float>("hit_tol")
+                                  .Ret<ffi::Buffer<ffi::PRED>>());
+
+// → face [R] i32, t [R] f32 ; (-1, +inf) on a miss
+static ffi::Error FirstHitImpl(cudaStream_t stream, ffi::ScratchAllocator scratch,
+                               ffi::Buffer<ffi::F32> vertices, ffi::Buffer<ffi::S32> triangles,
+                               ffi::Buffer<ffi::U8> mask, ffi::Buffer<ffi::F32> origins,
+                               ffi::Buffer<ffi::F32> directions, float epsilon, int64_t batch_size,
+                               ffi::ResultBuffer<ffi::S32> face, ffi::ResultBuffer<ffi::F32> t) {
+    const int64_t V = vertices.dimensions()[0], T = triangles.dimensions()[0];
+    auto pack = scratch.Allocate(drt_mesh_pack_bytes(T));
+    if (!pack.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "pack scratch");
+    const uint8_t *m = mask.element_count() ? mask.typed_data() : nullptr;
+    if (int rc = drt_mesh_pack(stream, V, T, vertices.typed_data(), triangles.typed_data(), m, *pack))
+        return Check(rc);
+    return Check(drt_first_triangle_hit_by_ray(stream, origins.dimensions()[0], origins.typed_data(),
+                                               directions.typed_data(), *pack, T, epsilon, batch_size,
+                                               face->typed_data(), t->typed_data(), nullptr));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DrtFirstTriangleHitByRay, FirstHitImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Ctx<ffi::ScratchAllocator>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Attr<float>("epsilon")
+                                  .Attr<int64_t>("batch_size")
+                                  .Ret<ffi::Buffer<ffi::S32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>());
+
+// backward of the hit distance (custom_vjp bwd, _mesh.py:308-338)
+static ffi::Error FirstHitVjpImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> vertices,
+                                  ffi::Buffer<ffi::S32> triangles, ffi::Buffer<ffi::F32> origins,
+                                  ffi::Buffer<ffi::F32> directions, ffi::Buffer<ffi::S32> faces,
+                                  ffi::Buffer<ffi::F32> g_t, ffi::ResultBuffer<ffi::F32> g_vertices,
+                                  ffi::ResultBuffer<ffi::F32> g_origins,
+                                  ffi::ResultBuffer<ffi::F32> g_directions) {
+    return Check(drt_first_triangle_hit_by_ray_vjp(
+        stream, origins.dimensions()[0], vertices.dimensions()[0], triangles.dimensions()[0],
+        vertices.typed_data(), triangles.typed_data(), origins.typed_data(), directions.typed_data(),
+        faces.typed_data(), g_t.typed_data(), g_vertices->typed_data(), g_origins->typed_data(),
+        g_directions->typed_data()));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DrtFirstTriangleHitByRayVjp, FirstHitVjpImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>());
+
+// viewing vertices [B,3], ray directions [B,n,3] → visible [B,T] pred
+static ffi::Error VisibleImpl(cudaStream_t stream, ffi::ScratchAllocator scratch,
+                              ffi::Buffer<ffi::F32> vertices, ffi::Buffer<ffi::S32> triangles,
+                              ffi::Buffer<ffi::U8> mask, ffi::Buffer<ffi::F32> viewers,
+                              ffi::Buffer<ffi::F32> directions, float epsilon,
+                              ffi::ResultBuffer<ffi::PRED> visible) {
+    const int64_t V = vertices.dimensions()[0], T = triangles.dimensions()[0];
+    auto pack = scratch.Allocate(drt_mesh_pack_bytes(T));
+    if (!pack.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "pack scratch");
+    const uint8_t *m = mask.element_count() ? mask.typed_data() : nullptr;
+    if (int rc = drt_mesh_pack(stream, V, T, vertices.typed_data(), triangles.typed_data(), m, *pack))
+        return Check(rc);
+    return Check(drt_triangles_visible_from_vertex(
+        stream, viewers.dimensions()[0], directions.dimensions()[1], viewers.typed_data(),
+        directions.typed_data(), *pack, T, epsilon, reinterpret_cast<uint8_t *>(visible->typed_data()),
+        nullptr));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DrtTrianglesVisibleFromVertex, VisibleImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Ctx<ffi::ScratchAllocator>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Attr<float>("epsilon")
+                                  .Ret<ffi::Buffer<ffi::PRED>>());
+
+// fused _trace_path_candidates: → vertices [Ntx,Nrx,C,k+2,3], objects [Ntx,Nrx,C,k+2], mask [Ntx,Nrx,C]
+static ffi::Error TraceImpl(cudaStream_t stream, ffi::ScratchAllocator scratch,
+                            ffi::Buffer<ffi::F32> vertices, ffi::Buffer<ffi::S32> triangles,
+                            ffi::Buffer<ffi::U8> mask, ffi::Buffer<ffi::F32> tx,
+                            ffi::Buffer<ffi::F32> rx, ffi::Buffer<ffi::S32> candidates,
+                            bool assume_quads, float epsilon, float hit_tol, float min_len,
+                            ffi::ResultBuffer<ffi::F32> out_vertices,
+                            ffi::ResultBuffer<ffi::S32> out_objects,
+                            ffi::ResultBuffer<ffi::PRED> out_mask) {
+    const int64_t V = vertices.dimensions()[0], T = triangles.dimensions()[0];
+    const int64_t ntx = tx.dimensions()[0], nrx = rx.dimensions()[0];
+    const int64_t C = candidates.dimensions()[0], k = candidates.dimensions()[1];
+    const size_t ws_bytes = drt_trace_workspace_bytes(T, ntx, nrx, C);
+    auto ws = scratch.Allocate(ws_bytes);
+    if (!ws.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "trace workspace");
+    const uint8_t *m = mask.element_count() ? mask.typed_data() : nullptr;
+    return Check(drt_trace_path_candidates(
+        stream, V, T, vertices.typed_data(), triangles.typed_data(), m, assume_quads ? 1 : 0, ntx,
+        tx.typed_data(), nrx, rx.typed_data(), C, static_cast<int32_t>(k), candidates.typed_data(),
+        epsilon, hit_tol, min_len, /*flags=*/0u, *ws, ws_bytes, out_vertices->typed_data(),
+        out_objects->typed_data(), reinterpret_cast<uint8_t *>(out_mask->typed_data()), nullptr));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DrtTracePathCandidates, TraceImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Ctx<ffi::ScratchAllocator>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Attr<bool>("assume_quads")
+                                  .Attr<float>("epsilon")
+                                  .Attr<float>("hit_tol")
+                                  .Attr<float>("min_len")
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::S32>>()
+                                  .Ret<ffi::Buffer<ffi::PRED>>());

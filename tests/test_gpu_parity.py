@@ -674,3 +674,29 @@ def test_trace_dense_equals_pruned_at_scale(drt):
     ev, eo, em = co.trace_path_candidates(v, t, tx, rx[:8], cand[:64], early_exit=True)
     np.testing.assert_array_equal(a.mask[:, :8, :64].cpu().numpy(), em)
     np.testing.assert_array_equal(bits(a.vertices[:, :8, :64].cpu().numpy()), bits(ev))
+
+
+# ------------------------------------------------------------------------------------------------
+# sharded trace + gather (world size 1 here; the world-size-2 merge logic is covered on CPU with gloo)
+# ------------------------------------------------------------------------------------------------
+
+
+def test_sharded_trace_gathers_valid_paths_in_reference_order(drt):
+    from differt_b200.distributed import trace_path_candidates_sharded
+
+    v, t = scenes.street_canyon(3)
+    mesh = drt.Mesh.from_numpy(v, t)
+    tx = np.array([[10.0, 0.0, 30.0], [12.0, 1.0, 25.0]], np.float32)
+    rx = np.array([[x, y, 1.5] for x in (2.0, 11.0, 19.0) for y in (-6.0, 5.0)], np.float32)
+    cand = scenes.complete_graph_candidates(t.shape[0], 2)
+    for capacity in (1 << 12, 2):  # 2 forces the overflow → retry path
+        paths, valid = trace_path_candidates_sharded(mesh, tx, rx, torch.from_numpy(cand).cuda(),
+                                                     capacity=capacity, dense_blockage=True)
+        ev, eo, em = co.trace_path_candidates(v, t, tx, rx, cand, early_exit=True)
+        idx = np.flatnonzero(em.reshape(-1))
+        assert idx.size > 0
+        np.testing.assert_array_equal(valid.index.cpu().numpy(), idx)
+        np.testing.assert_array_equal(bits(valid.vertices.cpu().numpy()), bits(ev.reshape(-1, 4, 3)[idx]))
+        np.testing.assert_array_equal(valid.objects.cpu().numpy(), eo.reshape(-1, 4)[idx])
+        m = paths.masked()
+        assert torch.equal(m.vertices, valid.vertices) and torch.equal(m.objects, valid.objects)
