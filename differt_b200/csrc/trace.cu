@@ -144,6 +144,127 @@ struct PathSink {
     __device__ __forceinline__ void first(int64_t, int, int32_t, float) const {}
 };
 
+// ------------------------------------------------------------------------------------------------
+// Blockage, head pass: every candidate against the first tiles of the area-sorted pack, which stay
+// resident in shared memory.  No ring, no CTA barrier after the initial load: warps run free, one
+// candidate at a time, with the next candidate's vertices prefetched (one float per lane) while the
+// current one is tested.  A hit retires the candidate (mask = 0); survivors are appended to `out_list`
+// (32 at a time per warp) for the ring pass over the remaining tiles.
+// ------------------------------------------------------------------------------------------------
+
+#ifndef DRT_PATH_HEAD_TILES
+#define DRT_PATH_HEAD_TILES 8
+#endif
+#ifndef DRT_PATH_HEAD_WARPS
+#define DRT_PATH_HEAD_WARPS 24
+#endif
+#ifndef DRT_PATH_HEAD_CTAS
+#define DRT_PATH_HEAD_CTAS 1
+#endif
+constexpr int kPathHead = DRT_PATH_HEAD_TILES;
+constexpr int kPathHeadWarps = DRT_PATH_HEAD_WARPS;
+constexpr size_t kPathHeadSmem = size_t(kPathHead) * kTile * sizeof(Tri48) + 16;
+
+template <int NSEG>
+__global__ void __launch_bounds__(kPathHeadWarps * 32, DRT_PATH_HEAD_CTAS)
+path_head_kernel(const Tri48 *__restrict__ pack, const int num_head_tiles, const int64_t num_units_host,
+                 const int64_t *__restrict__ num_units_dev, const float *__restrict__ vertices,
+                 const uint32_t *__restrict__ list, const float eps, const float thr,
+                 uint8_t *__restrict__ mask, uint32_t *__restrict__ out_list, int64_t *out_count,
+                 int64_t *tests_done) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Tri48 *head = reinterpret_cast<Tri48 *>(smem_raw);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + size_t(kPathHead) * kTile * sizeof(Tri48));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t num_units = num_units_dev ? *num_units_dev : num_units_host;
+    const int64_t total_warps = int64_t(gridDim.x) * kPathHeadWarps;
+    if (int64_t(blockIdx.x) * kPathHeadWarps >= num_units) return;
+    constexpr uint32_t kTileBytes = kTile * sizeof(Tri48);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(bar, uint32_t(num_head_tiles) * kTileBytes);
+        for (int h = 0; h < num_head_tiles; ++h)
+            bulk_g2s(head + size_t(h) * kTile, pack + size_t(h) * kTile, kTileBytes, bar);
+    }
+
+    constexpr int NV = NSEG + 1;  // vertices per path, 3 * NV floats <= 32 lanes
+    static_assert(3 * NV <= 32, "one float per lane prefetch");
+    auto path_of = [&](int64_t u) -> int64_t { return list != nullptr ? int64_t(list[u]) : u; };
+    auto fetch = [&](int64_t path) -> float {
+        return lane < 3 * NV ? vertices[path * (3 * NV) + lane] : 0.0f;
+    };
+
+    int64_t unit = int64_t(blockIdx.x) * kPathHeadWarps + warp;
+    // software pipeline: vertices of `unit` in pf, path id of the unit after it in path_next
+    int64_t path_cur = unit < num_units ? path_of(unit) : 0;
+    float pf = unit < num_units ? fetch(path_cur) : 0.0f;
+    int64_t path_next = unit + total_warps < num_units ? path_of(unit + total_warps) : 0;
+
+    mbar_wait(bar, 0u);
+
+    const bool fast_ok = eps >= 1.17549435e-38f;
+    int64_t tests = 0;
+    uint32_t keep = 0;  // lane i holds the i-th buffered survivor
+    int nkeep = 0;
+    for (; unit < num_units; unit += total_warps) {
+        float3 o[NSEG], d[NSEG];
+        {
+            float3 prev = make_float3(__shfl_sync(kFull, pf, 0), __shfl_sync(kFull, pf, 1),
+                                      __shfl_sync(kFull, pf, 2));
+#pragma unroll
+            for (int sgm = 0; sgm < NSEG; ++sgm) {
+                const float3 next = make_float3(__shfl_sync(kFull, pf, 3 * sgm + 3),
+                                                __shfl_sync(kFull, pf, 3 * sgm + 4),
+                                                __shfl_sync(kFull, pf, 3 * sgm + 5));
+                o[sgm] = prev;
+                d[sgm] = sub3(next, prev);  // jnp.diff (_solvers.py:593)
+                prev = next;
+            }
+        }
+        const int64_t path = path_cur;
+        // prefetch the next candidate
+        path_cur = path_next;
+        if (unit + total_warps < num_units) pf = fetch(path_cur);
+        path_next = unit + 2 * total_warps < num_units ? path_of(unit + 2 * total_warps) : 0;
+
+        bool blocked = false;
+        for (int h = 0; h < num_head_tiles && !blocked; ++h) {
+            int rows;
+            const uint32_t hits = scan_tile_any<NSEG, true>(head + size_t(h) * kTile, lane, o, d,
+                                                            (1u << NSEG) - 1u, eps, thr, fast_ok, rows);
+            tests += int64_t(NSEG) * 32 * rows;
+            blocked = __any_sync(kFull, hits != 0);
+        }
+        if (blocked) {
+            if (lane == 0) mask[path] = 0;
+        } else {
+            if (lane == nkeep) keep = uint32_t(path);
+            if (++nkeep == 32) {
+                int64_t base = 0;
+                if (lane == 0)
+                    base = (int64_t)atomicAdd(reinterpret_cast<unsigned long long *>(out_count), 32ull);
+                base = __shfl_sync(kFull, base, 0);
+                out_list[base + lane] = keep;
+                nkeep = 0;
+            }
+        }
+    }
+    if (nkeep > 0) {
+        int64_t base = 0;
+        if (lane == 0)
+            base = (int64_t)atomicAdd(reinterpret_cast<unsigned long long *>(out_count),
+                                      (unsigned long long)nkeep);
+        base = __shfl_sync(kFull, base, 0);
+        if (lane < nkeep) out_list[base + lane] = keep;
+    }
+    if (tests_done != nullptr && lane == 0 && tests)
+        atomicAdd(reinterpret_cast<unsigned long long *>(tests_done), (unsigned long long)tests);
+}
+
 // generic order: flat (slot, segment) rays, RPW per warp, no path-level early exit
 template <int RPW>
 struct SegRays {
@@ -460,7 +581,7 @@ __global__ void complete_graph_candidates_kernel(int64_t n, int order, int64_t s
 }
 
 struct TraceWorkspace {
-    size_t pack_geom, pack_active, list, counters, total;
+    size_t pack_geom, pack_active, pack_sorted, sort_ws, sort_bytes, list, list2, counters, total;
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -473,9 +594,16 @@ inline TraceWorkspace trace_workspace_layout(int64_t T, int64_t P) {
     off += align256(pack);
     w.pack_active = off;
     off += align256(pack);
+    w.pack_sorted = off;  // blockage pack: active triangles in descending area order (pack_sort.cu)
+    off += align256(pack);
+    w.sort_ws = off;
+    w.sort_bytes = drt_mesh_pack_sort_workspace_bytes(T);
+    off += align256(w.sort_bytes);
     w.counters = off;
     off += 256;
-    w.list = off;
+    w.list = off;  // candidates that reach the blockage test (stage A → head pass)
+    off += align256(size_t(P > 0 ? P : 1) * sizeof(uint32_t));
+    w.list2 = off;  // candidates that survive the head pass (head pass → ring pass)
     off += align256(size_t(P > 0 ? P : 1) * sizeof(uint32_t));
     w.total = off;
     return w;
@@ -500,7 +628,7 @@ static thread_local ProfileRing g_profile;
 template <int K>
 int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, bool profile,
                  const Tri48 *pack_active, float hit_tol, int64_t *tests_done,
-                 int64_t *units_scratch) {
+                 int64_t *units_scratch, uint32_t *list2, int64_t *list2_count) {
     const int threads = 256;
     const int64_t blocks = (a.P + threads - 1) / threads;
     const unsigned grid = unsigned(blocks < 148 * 8 ? blocks : 148 * 8);
@@ -527,11 +655,36 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
         cudaEventRecord(g_profile.start[slot], s);
     }
     if constexpr (NSEG <= 6) {
-        p.num_units = a.P;
-        p.num_units_dev = dense ? nullptr : a.list_count;
-        PathRays<NSEG> src{a.out_vertices, list};
-        PathSink<NSEG> sink{a.out_mask, list};
-        e = launch_intersect<NSEG, MODE_ANY, true>(s, p, src, sink, a.P);
+        // head pass: every candidate against the largest triangles, resident, barrier free
+        const int NT = p.num_tiles;
+        const int NH = NT < kPathHead ? NT : kPathHead;
+        auto hk = path_head_kernel<NSEG>;
+        static bool configured = false;  // benign race: idempotent attribute set
+        if (!configured) {
+            if (cudaFuncSetAttribute(hk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     int(kPathHeadSmem)) != cudaSuccess)
+                return DRT_ERR_CUDA;
+            configured = true;
+        }
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t hblocks = (a.P + kPathHeadWarps - 1) / kPathHeadWarps;
+        const int64_t hres = int64_t(sms) * DRT_PATH_HEAD_CTAS;
+        hk<<<unsigned(hblocks < hres ? hblocks : hres), kPathHeadWarps * 32, kPathHeadSmem, s>>>(
+            pack_active, NH, a.P, dense ? nullptr : a.list_count, a.out_vertices, list, a.eps, p.thr,
+            a.out_mask, list2, list2_count, tests_done);
+        e = cudaGetLastError();
+        if (e == cudaSuccess && NT > NH) {
+            // ring pass: the survivors against the remaining tiles
+            p.pack = pack_active + size_t(NH) * kTile;
+            p.num_tiles = NT - NH;
+            p.num_units = a.P;
+            p.num_units_dev = list2_count;
+            PathRays<NSEG> src{a.out_vertices, list2};
+            PathSink<NSEG> sink{a.out_mask, list2};
+            e = launch_intersect<NSEG, MODE_ANY, true>(s, p, src, sink, a.P);
+        }
     } else {
         constexpr int RPW = 3;
         p.num_units = (a.P * NSEG + RPW - 1) / RPW;
@@ -590,6 +743,12 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
         rc = drt_mesh_pack(stream, V, T, vertices, triangles, triangle_mask, pack_active);
         if (rc != DRT_OK) return rc;
     }
+    if (T > 0) {
+        Tri48 *pack_sorted = reinterpret_cast<Tri48 *>(ws + w.pack_sorted);
+        rc = drt_mesh_pack_sort_by_area(stream, T, pack_active, ws + w.sort_ws, w.sort_bytes, pack_sorted);
+        if (rc != DRT_OK) return rc;
+        pack_active = pack_sorted;
+    }
     int64_t *counters = reinterpret_cast<int64_t *>(ws + w.counters);
     if (cudaMemsetAsync(counters, 0, 256, s) != cudaSuccess) return DRT_ERR_CUDA;
     const bool dense = (flags & DRT_TRACE_DENSE_BLOCKAGE) != 0;
@@ -615,11 +774,12 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
     a.list_count = counters;
     int64_t *tests_done = stats;  // stats[0]
     int64_t *units_scratch = counters + 1;
+    uint32_t *list2 = reinterpret_cast<uint32_t *>(ws + w.list2);
     const bool quads = assume_quads != 0;
 #define DRT_TRACE_CASE(K)                                                                         \
     case K:                                                                                       \
         rc = trace_launch<K>(s, a, quads, dense, profile, pack_active, hit_tol, tests_done,        \
-                             units_scratch);                                                      \
+                             units_scratch, list2, counters + 2);                                 \
         break;
     switch (order) {
         DRT_TRACE_CASE(0) DRT_TRACE_CASE(1) DRT_TRACE_CASE(2) DRT_TRACE_CASE(3) DRT_TRACE_CASE(4)
@@ -627,9 +787,11 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
     }
 #undef DRT_TRACE_CASE
     if (rc != DRT_OK) return rc;
-    if (stats != nullptr &&
-        cudaMemcpyAsync(stats + 1, counters, sizeof(int64_t), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
-        return DRT_ERR_CUDA;
+    if (stats != nullptr) {
+        if (cudaMemcpyAsync(stats + 1, counters, sizeof(int64_t), cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+            cudaMemcpyAsync(stats + 2, counters + 2, sizeof(int64_t), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+            return DRT_ERR_CUDA;
+    }
     return DRT_OK;
 }
 

@@ -46,6 +46,10 @@ __all__ = [
 ]
 
 
+# below this many rays an any-hit call is launch-bound and sorting the pack first does not pay
+_SORT_MIN_RAYS = 4096
+
+
 def _no_smoothing(smoothing_factor: Any) -> None:
     if smoothing_factor is not None:
         raise NotImplementedError(
@@ -84,6 +88,16 @@ def pack_triangle_vertices(triangle_vertices: torch.Tensor, mask: torch.Tensor |
         )
     )
     return pack
+
+
+def sort_pack_by_area(pack: torch.Tensor, num_triangles: int) -> torch.Tensor:
+    """Any-hit ordering of a pack (largest triangles first, ``drt_mesh_pack_sort_by_area``): the
+    result of an any-hit query does not depend on the order, blocked rays just stop sooner."""
+    out = torch.empty_like(pack)
+    ws = torch.empty(max(lib.drt_mesh_pack_sort_workspace_bytes(num_triangles), 1), dtype=torch.uint8,
+                     device=pack.device)
+    check(lib.drt_mesh_pack_sort_by_area(stream_ptr(), num_triangles, ptr(pack), ptr(ws), ws.numel(), ptr(out)))
+    return out
 
 
 def pack_normals(pack: torch.Tensor, num_triangles: int) -> torch.Tensor:
@@ -256,6 +270,8 @@ def ray_intersect_any_triangle(
     for sel, tvi, acti in _mesh_batches(batch, tv, act):
         oi, di = ob[sel].reshape(-1, 3).contiguous(), db[sel].reshape(-1, 3).contiguous()
         pack = pack_triangle_vertices(tvi.contiguous(), None if acti is None else acti.contiguous())
+        if oi.shape[0] >= _SORT_MIN_RAYS:
+            pack = sort_pack_by_area(pack, T)
         res = torch.empty(oi.shape[0], dtype=torch.uint8, device=o.device)
         check(
             lib.drt_ray_intersect_any_triangle(

@@ -106,6 +106,8 @@ class Mesh:
         o = o.detach().expand(*batch, 3).reshape(R, 3).contiguous()
         d = d.detach().expand(*batch, 3).reshape(R, 3).contiguous()
         pack = geometry.pack_mesh(self.vertices.detach(), self.triangles, self._mask_u8())
+        if R >= geometry._SORT_MIN_RAYS:
+            pack = geometry.sort_pack_by_area(pack, self.num_triangles)
         check(
             lib.drt_ray_intersect_any_triangle(
                 stream_ptr(), R, ptr(o), ptr(d), ptr(pack), self.num_triangles,

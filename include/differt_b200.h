@@ -83,6 +83,15 @@ DRT_API int drt_mesh_pack_triangle_vertices(drt_stream_t stream, int64_t num_tri
                                     const float *triangle_vertices,
                                     const uint8_t *mask /*nullable*/, void *pack_out);
 
+/* Any-hit ordering of a pack: the same records in descending triangle-area order (never-hit
+ * records last).  An any-hit query is an OR over triangles, so the order cannot change its result —
+ * only how early a blocked ray stops: the all-pairs engine keeps the first tiles of the pack resident
+ * in shared memory and tests every new ray against them first.  Triangle indices are lost: use the
+ * result with drt_ray_intersect_any_triangle only.  pack_out must not alias pack_in. */
+DRT_API size_t drt_mesh_pack_sort_workspace_bytes(int64_t num_triangles);
+DRT_API int drt_mesh_pack_sort_by_area(drt_stream_t stream, int64_t num_triangles, const void *pack_in,
+                               void *workspace, size_t workspace_bytes, void *pack_out);
+
 /* ---------------------------------------------------------------------------------------------
  * K1  ray_intersect_triangle — element-wise Möller–Trumbore over a broadcast batch
  *     (reference: _utils.py:1157-1322).  Operand element (i0..i3) lives at
@@ -179,7 +188,9 @@ DRT_API int drt_consecutive_vertices_are_on_same_side_of_mirror(
  *     Outputs = the fields of TracedPaths (_paths.py:77-116), dense and contiguous:
  *       vertices [Ntx,Nrx,C,k+2,3] f32, objects [Ntx,Nrx,C,k+2] i32, mask [Ntx,Nrx,C] u8.
  *     `stats` (nullable, device int64[4]): [0] ray–triangle tests evaluated, [1] candidates that
- *     reached the blockage test, [2..3] reserved.  The callee zero-fills it.
+ *     passed the cheap tests (0 in dense mode, where every candidate is blockage-tested),
+ *     [2] candidates still unblocked after the resident head tiles, [3] reserved.
+ *     The callee zero-fills it.
  * K6b reverse mode of `vertices` w.r.t. tx, rx and Mesh.vertices (mask carries no cotangent,
  *     reference: _mesh.py:3087-3094).  g_* outputs are zero-filled by the callee.
  * ------------------------------------------------------------------------------------------- */

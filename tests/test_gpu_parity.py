@@ -700,3 +700,37 @@ def test_sharded_trace_gathers_valid_paths_in_reference_order(drt):
         np.testing.assert_array_equal(valid.objects.cpu().numpy(), eo.reshape(-1, 4)[idx])
         m = paths.masked()
         assert torch.equal(m.vertices, valid.vertices) and torch.equal(m.objects, valid.objects)
+
+
+def test_area_sorted_pack_is_a_permutation_and_keeps_any_hit_results(drt, rng):
+    from differt_b200._lib import check, lib
+    from differt_b200._tensor import ptr, stream_ptr
+    from differt_b200.geometry import pack_triangle_vertices, sort_pack_by_area
+
+    v, t = scenes.urban_grid(7, 7)
+    T = t.shape[0]
+    mask = rng.uniform(size=T) < 0.7
+    tri = torch.from_numpy(orc.triangle_vertices(v, t)).cuda()
+    pack = pack_triangle_vertices(tri, torch.from_numpy(mask.astype(np.uint8)).cuda())
+    srt = sort_pack_by_area(pack, T)
+    a = pack.view(torch.float32).view(-1, 12).cpu().numpy()
+    b = srt.view(torch.float32).view(-1, 12).cpu().numpy()
+    # same multiset of records (NaN-origin never-hit records compare through their bit patterns)
+    key = lambda x: sorted(map(bytes, np.ascontiguousarray(x).view(np.uint8).reshape(x.shape[0], -1)))
+    assert key(a) == key(b)
+    live = ~np.isnan(b[:, 0])
+    assert live.sum() == mask.sum() and live[: live.sum()].all(), "never-hit records must sort last"
+    e1, e2 = b[live, 3:6].astype(np.float64), b[live, 6:9].astype(np.float64)
+    area2 = (np.cross(e1, e2) ** 2).sum(-1)
+    assert (np.diff(area2) <= 1e-6 * area2[:-1]).all(), "areas must be non-increasing"
+    # identical any-hit answers from both orders, and equal to the oracle
+    o, d = scene_rays(rng, v, 5000)
+    oc, dc = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    outs = []
+    for pk in (pack, srt):
+        out = torch.empty(5000, dtype=torch.uint8, device="cuda")
+        check(lib.drt_ray_intersect_any_triangle(stream_ptr(), 5000, ptr(oc), ptr(dc), ptr(pk), T,
+                                                 10 * orc.EPS, 100 * orc.EPS, ptr(out), None))
+        outs.append(out.cpu().numpy().astype(bool))
+    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_array_equal(outs[0], co.ray_intersect_any_triangle(o, d, tri.cpu().numpy(), mask))

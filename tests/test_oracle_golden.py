@@ -308,3 +308,28 @@ def test_image_method_vjp_matches_finite_differences(rng):
             num[i] = (f64(*ap) - f64(*am)) / 2e-6
         scale = max(1.0, float(np.abs(num).max()))
         np.testing.assert_allclose(ga, num, rtol=2e-3, atol=2e-3 * scale)
+
+
+def test_bench_valid_candidates_fixture_is_valid_per_oracle():
+    """tests/golden/urban10k_valid_candidates.npz (found on the GPU by tools/find_valid_candidates.py)
+    holds candidates the ORACLE also accepts for at least one receiver of the bench workload."""
+    import sys
+    from pathlib import Path
+
+    GOLDEN = Path(__file__).resolve().parent / "golden"
+    sys.path.insert(0, str(GOLDEN.parent.parent))
+    import bench
+    from oracle import c_oracle as co
+
+    wl = bench.build_workload("urban10k_1tx_4096rx_order3", 0, 1)
+    known = np.load(GOLDEN / "urban10k_valid_candidates.npz")
+    rx = wl["rx"][:: wl["rx"].shape[0] // 256][:256]
+    for order, limit in ((3, 64), (2, 16), (1, 32)):
+        cand = known[f"order{order}"][:limit]
+        assert cand.shape[0] > 0
+        rx_o = wl["rx"] if order == 1 else rx  # order-1 candidates were searched over every receiver
+        _, _, mask = co.trace_path_candidates(wl["vertices"], wl["triangles"], wl["tx"], rx_o, cand, early_exit=True)
+        assert mask.any(axis=1)[0].all(), f"order-{order} fixture candidate rejected by the oracle"
+    # and the bench workload starts with them
+    n3 = min(known["order3"].shape[0], wl["cand"].shape[0] // 4)
+    np.testing.assert_array_equal(wl["cand"][:n3], known["order3"][:n3])
