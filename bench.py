@@ -165,6 +165,15 @@ def cpu_sample(wl: dict, target_tests: float):
     return wl["cand"][:c], wl["rx"][rx_idx], f"first {c} candidates x {r} strided receivers of {wl['name']}"
 
 
+def cpu_threads() -> int:
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it)."""
+    from oracle import c_oracle as co
+
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    co.set_num_threads(n)
+    return co.num_threads()
+
+
 def cpu_step(wl: dict, cand, rx):
     """One dense (no early exit) trace + validate on the host cores → (tests, seconds, valid)."""
     from oracle import c_oracle as co
@@ -193,6 +202,7 @@ def run_reference(args, rank: int) -> None:
     from oracle import c_oracle as co
 
     wl = build_workload(args.workload, 0, 1)
+    cores = cpu_threads()
     cand, rx, sample = cpu_calibrate(wl, args.cpu_seconds)
     for _ in range(args.warmup):
         cpu_step(wl, cand, rx)
@@ -203,7 +213,6 @@ def run_reference(args, rank: int) -> None:
         tests += n
     dt = time.perf_counter() - t0
     value = tests / dt
-    cores = co.num_threads()
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -355,7 +364,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         tests_per_launch = tests_local / max(args.steps, 1)
         achieved = BYTES_PER_TEST * tests_per_launch / (kms * 1e-3) / 1e9 if kms else None
         roofline = {
-            "kernel": "drt::intersect_kernel<order+1, ANY, PATH> (blockage all-pairs)",
+            "kernel": "blockage pass = drt::path_head_kernel<order+1> (head tiles, ~3/4 of the time) + "
+                      "drt::intersect_kernel<order+1, ANY, PATH> (ring pass over the survivors)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak if achieved else None, "traffic": None,
             "peak_source": peak_src, "bytes_per_test": BYTES_PER_TEST,
@@ -384,15 +394,16 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                     "executed_tests_per_s": tests_e2e / (ms_e2e * 1e-3), "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                     "valid_paths_gathered": num_valid_global},
-            "gpu_launches": args.steps * 6,  # pack, stage A, blockage, 3 compaction kernels per step
+            # pack, area keys + gather, stage A, head pass, ring pass, 3 compaction kernels per step
+            # (+ 4 CUB radix-sort kernels, not counted as ours)
+            "gpu_launches": args.steps * 9,
             "clocks": clocks, "roofline": roofline,
         }
         if world == 1 and not args.no_cpu:
+            cores = cpu_threads()
             cand, rx, sample = cpu_calibrate(wl, args.cpu_seconds)
             n, dt, _ = cpu_step(wl, cand, rx)
-            from oracle import c_oracle as co
-
-            line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": co.num_threads(), "kind": "port",
+            line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": sample, "seconds": dt, "host_cpus": os.cpu_count()}
         print(json.dumps(line))
     if world > 1:
@@ -402,7 +413,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
