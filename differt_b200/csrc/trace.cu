@@ -28,6 +28,7 @@ struct TraceArgs {
     uint8_t *out_mask;
     uint32_t *list;           // nullable (dense blockage): indices of candidates to test
     int64_t *list_count;
+    bool wide_stores;         // out_vertices / out_objects are 16-byte aligned
 };
 
 template <int K, bool QUADS>
@@ -35,6 +36,11 @@ __global__ void __launch_bounds__(256)
 trace_stage_a_kernel(const TraceArgs a) {
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     const int lane = threadIdx.x & 31;
+    constexpr int NV3 = (K + 2) * 3;
+    __shared__ __align__(16) float stage_v_all[8][32 * NV3];
+    __shared__ __align__(16) int32_t stage_o_all[8][32 * (K + 2)];
+    float *stage_v = stage_v_all[threadIdx.x >> 5];
+    int32_t *stage_o = stage_o_all[threadIdx.x >> 5];
     for (int64_t base = blockIdx.x * int64_t(blockDim.x) + threadIdx.x - lane; base < a.P;
          base += stride) {
         const int64_t p = base + lane;
@@ -86,18 +92,39 @@ trace_stage_a_kernel(const TraceArgs a) {
 #pragma unroll
             for (int i = 0; i < K + 2; ++i) finite = finite && finite3(full[i]);
 
-            float *ov = a.out_vertices + p * (K + 2) * 3;
+            // stage the dense outputs in shared memory: the warp's 32 paths are contiguous in HBM
+            float *sv = stage_v + lane * NV3;
 #pragma unroll
-            for (int i = 0; i < K + 2; ++i)
-                st3(ov + 3 * i, finite ? full[i] : make_float3(0.f, 0.f, 0.f));
-            int32_t *oo = a.out_objects + p * (K + 2);
-            oo[0] = int32_t(itx);
+            for (int i = 0; i < K + 2; ++i) st3(sv + 3 * i, finite ? full[i] : make_float3(0.f, 0.f, 0.f));
+            int32_t *so = stage_o + lane * (K + 2);
+            so[0] = int32_t(itx);
 #pragma unroll
-            for (int i = 0; i < K; ++i) oo[i + 1] = ci[i];
-            oo[K + 1] = int32_t(irx);
+            for (int i = 0; i < K; ++i) so[i + 1] = ci[i];
+            so[K + 1] = int32_t(irx);
             prevalid = inside && same && !small && finite && active;
             a.out_mask[p] = prevalid ? 1 : 0;
         }
+        // coalesced 16-byte stores of the warp's block of paths (32 * 12 (K+2) bytes, 16-byte aligned)
+        __syncwarp();
+        {
+            const int64_t n = (a.P - base) < 32 ? (a.P - base) : 32;
+            float *gv = a.out_vertices + base * NV3;
+            int32_t *go = a.out_objects + base * (K + 2);
+            if (n == 32 && a.wide_stores) {
+                float4 *gv4 = reinterpret_cast<float4 *>(gv);
+                const float4 *sv4 = reinterpret_cast<const float4 *>(stage_v);
+#pragma unroll
+                for (int i = lane; i < 8 * NV3; i += 32) gv4[i] = sv4[i];
+                int4 *go4 = reinterpret_cast<int4 *>(go);
+                const int4 *so4 = reinterpret_cast<const int4 *>(stage_o);
+#pragma unroll
+                for (int i = lane; i < 8 * (K + 2); i += 32) go4[i] = so4[i];
+            } else {
+                for (int64_t i = lane; i < n * NV3; i += 32) gv[i] = stage_v[i];
+                for (int64_t i = lane; i < n * (K + 2); i += 32) go[i] = stage_o[i];
+            }
+        }
+        __syncwarp();
         if (a.list != nullptr) {  // warp-aggregated append
             const unsigned m = __ballot_sync(kFull, prevalid);
             if (m) {
@@ -230,6 +257,16 @@ path_head_kernel(const Tri48 *__restrict__ pack, const int num_head_tiles, const
         path_cur = path_next;
         if (unit + total_warps < num_units) pf = fetch(path_cur);
         path_next = unit + 2 * total_warps < num_units ? path_of(unit + 2 * total_warps) : 0;
+
+        // a segment with d == 0 gives h = d x e2 = 0 and a = 0 for every triangle: it can never hit.
+        // Paths whose vertices were zeroed because they are not finite (_solvers.py:696-699) consist of
+        // such segments only: they are unblocked by construction and need no test at all.
+        // (Only for eps >= 0: with a negative epsilon the reference's a == 0 → t = 0 passes `t > eps`.)
+        bool degenerate = eps >= 0.0f;
+#pragma unroll
+        for (int sgm = 0; sgm < NSEG; ++sgm)
+            degenerate = degenerate && d[sgm].x == 0.0f && d[sgm].y == 0.0f && d[sgm].z == 0.0f;
+        if (degenerate) continue;
 
         bool blocked = false;
         for (int h = 0; h < num_head_tiles && !blocked; ++h) {
@@ -770,6 +807,7 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
     a.out_vertices = out_vertices;
     a.out_objects = out_objects;
     a.out_mask = out_mask;
+    a.wide_stores = ((reinterpret_cast<uintptr_t>(out_vertices) | reinterpret_cast<uintptr_t>(out_objects)) & 15) == 0;
     a.list = reinterpret_cast<uint32_t *>(ws + w.list);
     a.list_count = counters;
     int64_t *tests_done = stats;  // stats[0]
