@@ -20,13 +20,21 @@ from .geometry import (
     viewing_frustum,
 )
 from .mesh import Mesh, TracedPaths
-from .solvers import generate_all_path_candidates, trace_path_candidates, trace_paths
+from .solvers import (
+    VisiblePathCandidates,
+    generate_all_path_candidates,
+    generate_visible_path_candidates,
+    trace_path_candidates,
+    trace_paths,
+)
 
 __version__ = "0.1.0"
 
 __all__ = [
     "Mesh",
     "TracedPaths",
+    "VisiblePathCandidates",
+    "generate_visible_path_candidates",
     "consecutive_vertices_are_on_same_side_of_mirror",
     "fibonacci_lattice",
     "first_triangle_hit_by_ray",

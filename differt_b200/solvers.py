@@ -19,6 +19,8 @@ from .mesh import Mesh, TracedPaths
 from .scenes import num_complete_graph_candidates
 
 __all__ = [
+    "VisiblePathCandidates",
+    "generate_visible_path_candidates",
     "generate_all_path_candidates",
     "generate_all_path_candidates_chunks_iter",
     "trace_path_candidates",
@@ -103,10 +105,11 @@ def trace_path_candidates(
     stats = torch.zeros(4, dtype=torch.int64, device=dev) if want_stats else None
     flags = (_lib.DRT_TRACE_DENSE_BLOCKAGE if dense_blockage else 0) | (_lib.DRT_TRACE_PROFILE if _profile else 0)
     ws = torch.empty(max(lib.drt_trace_workspace_bytes(T, ntx, nrx, C), 1), dtype=torch.uint8, device=dev)
+    mask_u8 = mesh._mask_u8()  # named: must outlive the call
     check(
         lib.drt_trace_path_candidates(
             stream_ptr(), mesh.vertices.shape[0], T, ptr(mesh.vertices.detach()), ptr(mesh.triangles),
-            ptr(mesh._mask_u8()), int(mesh.assume_quads), ntx, ptr(tx.detach()), nrx, ptr(rx.detach()),
+            ptr(mask_u8), int(mesh.assume_quads), ntx, ptr(tx.detach()), nrx, ptr(rx.detach()),
             C, k, ptr(cand),
             10.0 * F32_EPS if epsilon is None else float(epsilon),
             100.0 * F32_EPS if hit_tol is None else float(hit_tol),
@@ -165,9 +168,87 @@ def generate_all_path_candidates_chunks_iter(
         )
 
 
-def trace_paths(mesh: Mesh, tx_vertices, rx_vertices, order: int, **kwargs) -> TracedPaths:
-    """Exhaustive ``Scene.trace_paths(order)`` (reference ``_scene.py:650-764``) for one mesh."""
-    cand = generate_all_path_candidates(
-        mesh.num_primitives, order, assume_quads=mesh.assume_quads, device=mesh.vertices.device
+class VisiblePathCandidates:
+    """Candidates of ``HybridPathTracer`` (reference ``_solvers.py:993-1058``): every tuple of
+    primitives without consecutive repeats whose first element is visible from a transmitter, whose
+    last element is visible from a receiver and whose elements are all active, in the reference's
+    (lexicographic DFS, ``graph.rs:1063-1108``) order.  The completion counts live on the device
+    (``drt_digraph_candidates_prepare``); ``chunk(start, count)`` decodes any slice independently."""
+
+    def __init__(self, num_primitives: int, order: int, visible_from_tx, visible_from_rx, active=None,
+                 *, assume_quads: bool = False, device=None) -> None:
+        if num_primitives ** max(order, 1) >= 2 ** 62:
+            raise OverflowError("num_primitives ** order must stay below 2**62")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        u8 = lambda m: None if m is None else torch.as_tensor(m).to(dev, torch.uint8).contiguous()
+        self.n, self.order, self.mult, self.device = int(num_primitives), int(order), 2 if assume_quads else 1, dev
+        self._ws = torch.empty(max(lib.drt_digraph_candidates_workspace_bytes(self.n, self.order), 1),
+                               dtype=torch.uint8, device=dev)
+        total = torch.zeros(1, dtype=torch.int64, device=dev)
+        # keep the three masks alive across the call: temporaries would share one allocator block
+        m_from, m_to, m_active = u8(visible_from_tx), u8(visible_from_rx), u8(active)
+        check(
+            lib.drt_digraph_candidates_prepare(
+                stream_ptr(), self.n, self.order, ptr(m_from), ptr(m_to), ptr(m_active), ptr(self._ws),
+                self._ws.numel(), ptr(total),
+            )
+        )
+        self.total = int(total.item())  # the one host read: sizes the candidate arrays
+
+    def __len__(self) -> int:
+        return self.total
+
+    def chunk(self, start: int = 0, count: int | None = None) -> torch.Tensor:
+        count = self.total - start if count is None else max(min(count, self.total - start), 0)
+        # zero candidates come back as [0, 0] like the reference's empty iterator (graph.rs:40-54)
+        out = torch.empty((count, self.order if self.total > 0 else 0), dtype=torch.int32, device=self.device)
+        if count > 0 and self.order > 0:
+            check(
+                lib.drt_digraph_candidates(
+                    stream_ptr(), self.n, self.order, ptr(self._ws), start, count, self.mult, ptr(out)
+                )
+            )
+        return out
+
+    def chunks_iter(self, chunk_size: int) -> Iterator[torch.Tensor]:
+        for start in range(0, self.total, chunk_size):
+            yield self.chunk(start, chunk_size)
+
+
+def generate_visible_path_candidates(
+    mesh: Mesh, tx_vertices, rx_vertices, order: int, *, num_rays: int = 1_000_000
+) -> VisiblePathCandidates:
+    """``HybridPathTracer.generate_path_candidates`` (reference ``_solvers.py:993-1058``): visibility
+    of every triangle from the transmitters and from the receivers (K4), merged over quads and over
+    the tx / rx batches, then the pruned candidate graph decoded on the device."""
+    pl = Placement()
+    pl.device = mesh.vertices.device
+    tx = pl.put(tx_vertices, torch.float32).reshape(-1, 3)
+    rx = pl.put(rx_vertices, torch.float32).reshape(-1, 3)
+    vis_tx = mesh.triangles_visible_from_vertex(tx, num_rays=num_rays).any(dim=0)
+    vis_rx = mesh.triangles_visible_from_vertex(rx, num_rays=num_rays).any(dim=0)
+    active = mesh.mask
+    if mesh.assume_quads:
+        vis_tx = vis_tx.reshape(-1, 2).any(dim=-1)
+        vis_rx = vis_rx.reshape(-1, 2).any(dim=-1)
+        if active is not None:
+            active = active[0::2] & active[1::2]
+    return VisiblePathCandidates(
+        mesh.num_primitives, order, vis_tx, vis_rx, active, assume_quads=mesh.assume_quads,
+        device=mesh.vertices.device,
     )
+
+
+def trace_paths(mesh: Mesh, tx_vertices, rx_vertices, order: int, *, solver: str = "exhaustive",
+                num_rays: int = 1_000_000, **kwargs) -> TracedPaths:
+    """``Scene.trace_paths(order, solver=...)`` (reference ``_scene.py:650-764``) for one mesh:
+    ``"exhaustive"`` (every candidate of the complete graph) or ``"hybrid"`` (visibility-pruned)."""
+    if solver == "exhaustive":
+        cand = generate_all_path_candidates(
+            mesh.num_primitives, order, assume_quads=mesh.assume_quads, device=mesh.vertices.device
+        )
+    elif solver == "hybrid":
+        cand = generate_visible_path_candidates(mesh, tx_vertices, rx_vertices, order, num_rays=num_rays).chunk()
+    else:
+        raise ValueError(f"Unknown solver: {solver}")  # _scene.py:700-702
     return trace_path_candidates(mesh, tx_vertices, rx_vertices, cand, **kwargs)

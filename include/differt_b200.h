@@ -243,6 +243,27 @@ DRT_API int drt_complete_graph_candidates(drt_stream_t stream, int64_t num_nodes
                                   int64_t start, int64_t count, int32_t stride_multiplier,
                                   int32_t *out);
 
+/* ---------------------------------------------------------------------------------------------
+ * N1b path candidates of the visibility-pruned graph of HybridPathTracer
+ *     (reference: differt/src/differt/geometry/_solvers.py:993-1058;
+ *      differt-core/src/geometry/graph.rs:636-691 insert_from_and_to_nodes, :879-915 filter_by_mask,
+ *      :1063-1108 DFS order): every tuple with c_1 in from_mask, c_k in to_mask, all c_i in
+ *     active_mask, c_i != c_{i-1}, in lexicographic order.  NULL masks mean "every node".
+ *     `prepare` fills the workspace with the per-position completion counts and writes the total
+ *     number of candidates to total_out (device int64); `drt_digraph_candidates` then decodes
+ *     candidates start .. start+count-1 from the prepared workspace.  The caller must keep
+ *     num_nodes^order below 2^63.
+ * ------------------------------------------------------------------------------------------- */
+DRT_API size_t drt_digraph_candidates_workspace_bytes(int64_t num_nodes, int32_t order);
+DRT_API int drt_digraph_candidates_prepare(drt_stream_t stream, int64_t num_nodes, int32_t order,
+                                   const uint8_t *from_mask /*nullable*/,
+                                   const uint8_t *to_mask /*nullable*/,
+                                   const uint8_t *active_mask /*nullable*/, void *workspace,
+                                   size_t workspace_bytes, int64_t *total_out);
+DRT_API int drt_digraph_candidates(drt_stream_t stream, int64_t num_nodes, int32_t order,
+                           const void *workspace, int64_t start, int64_t count,
+                           int32_t stride_multiplier, int32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

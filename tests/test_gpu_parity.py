@@ -734,3 +734,57 @@ def test_area_sorted_pack_is_a_permutation_and_keeps_any_hit_results(drt, rng):
         outs.append(out.cpu().numpy().astype(bool))
     np.testing.assert_array_equal(outs[0], outs[1])
     np.testing.assert_array_equal(outs[0], co.ray_intersect_any_triangle(o, d, tri.cpu().numpy(), mask))
+
+
+# ------------------------------------------------------------------------------------------------
+# N1b: visibility-pruned (HybridPathTracer) candidates decoded on the device
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("n,order", [(1, 1), (2, 2), (6, 1), (6, 2), (7, 3), (9, 4), (5, 5)])
+@pytest.mark.parametrize("use_masks", [False, True])
+def test_digraph_candidates_match_reference_dfs(drt, rng, n, order, use_masks):
+    from oracle.graph_oracle import hybrid_path_candidates
+
+    if use_masks:
+        a, b, m = rng.uniform(size=n) < 0.6, rng.uniform(size=n) < 0.6, rng.uniform(size=n) < 0.8
+    else:
+        a = b = np.ones(n, bool)
+        m = None
+    exp = hybrid_path_candidates(n, order, a, b, m)
+    gen = drt.VisiblePathCandidates(n, order, None if not use_masks else a, None if not use_masks else b, m)
+    assert len(gen) == exp.shape[0]
+    got = gen.chunk().cpu().numpy()
+    np.testing.assert_array_equal(got.reshape(exp.shape), exp)
+    # chunks decode independently and concatenate to the full list
+    if len(gen):
+        parts = [c.cpu().numpy() for c in gen.chunks_iter(5)]
+        np.testing.assert_array_equal(np.concatenate(parts), exp)
+    # quads: indices are the even triangles
+    gen2 = drt.VisiblePathCandidates(n, order, a if use_masks else None, b if use_masks else None, m,
+                                     assume_quads=True)
+    np.testing.assert_array_equal(gen2.chunk().cpu().numpy().reshape(exp.shape), 2 * exp)
+
+
+def test_digraph_order_zero_and_empty(drt):
+    assert len(drt.VisiblePathCandidates(5, 0, None, None)) == 0  # no direct path (graph.rs:1076-1092)
+    assert drt.VisiblePathCandidates(5, 0, None, None).chunk().shape == (0, 0)
+    assert len(drt.VisiblePathCandidates(4, 2, np.zeros(4, bool), None)) == 0
+    assert len(drt.VisiblePathCandidates(0, 2, None, None)) == 0
+
+
+@pytest.mark.parametrize("assume_quads", [False, True])
+@pytest.mark.parametrize("order", [1, 2])
+def test_hybrid_trace_finds_the_golden_paths(drt, kats, two_buildings, order, assume_quads):
+    """test_scene.py:116-160 with method="hybrid": the visibility-pruned candidate set still
+    contains the valid paths, and is (much) smaller than the exhaustive one."""
+    v, t = two_buildings
+    g = kats["two_buildings_scene"]
+    mesh = drt.Mesh.from_numpy(v, t, assume_quads=assume_quads)
+    tx, rx = np.array(g["tx"], np.float32), np.array(g["rx"], np.float32)
+    hyb = drt.trace_paths(mesh, tx, rx, order, solver="hybrid", num_rays=100_000)
+    exh = drt.trace_paths(mesh, tx, rx, order, solver="exhaustive")
+    assert 0 < hyb.mask.numel() < exh.mask.numel()
+    mh, me = hyb.masked(), exh.masked()
+    assert torch.equal(mh.objects, me.objects) and torch.equal(mh.vertices, me.vertices)
+    assert mh.vertices.shape[0] >= 1
