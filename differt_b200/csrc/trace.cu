@@ -28,45 +28,66 @@ struct TraceArgs {
     uint8_t *out_mask;
     uint32_t *list;           // nullable (dense blockage): indices of candidates to test
     int64_t *list_count;
-    bool wide_stores;         // out_vertices / out_objects are 16-byte aligned
 };
 
+// Candidate-major decomposition: thread = (candidate c, transmitter, chunk of receivers).  The
+// candidate's mirrors (first vertex + unit normal) and the triangles of its inside test are gathered
+// from the packed mesh ONCE and kept in registers for every receiver of the chunk — the gather is the
+// uncoalesced part of this stage (ncu: L1TEX-bound when done per path).  Lanes of a warp hold 32
+// consecutive candidates of the same receiver, i.e. 32 consecutive paths: their dense outputs are
+// staged in shared memory and leave as contiguous 16-byte stores.
 template <int K, bool QUADS>
-__global__ void __launch_bounds__(256)
-trace_stage_a_kernel(const TraceArgs a) {
-    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(128)
+trace_stage_a_kernel(const TraceArgs a, const int64_t rx_per_chunk) {
+    constexpr int KK = K > 0 ? K : 1;
+    constexpr int NT = QUADS ? 2 : 1;  // triangles per primitive in the inside test
     constexpr int NV3 = (K + 2) * 3;
-    __shared__ __align__(16) float stage_v_all[8][32 * NV3];
-    __shared__ __align__(16) int32_t stage_o_all[8][32 * (K + 2)];
+    __shared__ __align__(16) float stage_v_all[4][32 * NV3];
+    __shared__ __align__(16) int32_t stage_o_all[4][32 * (K + 2)];
+    const int lane = threadIdx.x & 31;
     float *stage_v = stage_v_all[threadIdx.x >> 5];
     int32_t *stage_o = stage_o_all[threadIdx.x >> 5];
-    for (int64_t base = blockIdx.x * int64_t(blockDim.x) + threadIdx.x - lane; base < a.P;
-         base += stride) {
-        const int64_t p = base + lane;
-        bool prevalid = false;
-        if (p < a.P) {
-            const int64_t c = p % a.C;
-            const int64_t irx = (p / a.C) % a.nrx;
-            const int64_t itx = p / (a.C * a.nrx);
-            constexpr int KK = K > 0 ? K : 1;
-            float3 full[K + 2], mv[KK], mn[KK];
-            int32_t ci[KK];
-            bool active = true;
+
+    const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t c0 = c - lane;  // first candidate of the warp
+    if (c0 >= a.C) return;        // warp-uniform
+    const int64_t itx = blockIdx.z;
+    const int64_t rx0 = int64_t(blockIdx.y) * rx_per_chunk;
+    const int64_t rx1 = rx0 + rx_per_chunk < a.nrx ? rx0 + rx_per_chunk : a.nrx;
+    const bool have = c < a.C;
+    const int n_warp = int((a.C - c0) < 32 ? (a.C - c0) : 32);
+
+    float3 mv[KK], mn[KK];
+    Tri tri[KK][NT];
+    int32_t ci[KK];
+    bool active = true;
+    if (have) {
 #pragma unroll
-            for (int i = 0; i < K; ++i) {
-                int32_t t = a.cand[c * K + i];
-                ci[i] = t;
-                t = min(max(t, 0), int32_t(a.T - (QUADS ? 2 : 1)));
-                const float4 ta = a.pack[t].a, tc = a.pack[t].c;
-                mv[i] = make_float3(ta.x, ta.y, ta.z);
-                mn[i] = make_float3(tc.y, tc.z, tc.w);
-                if (a.tri_mask != nullptr) {
-                    active = active && a.tri_mask[t] != 0;
-                    if (QUADS) active = active && a.tri_mask[t + 1] != 0;
+        for (int i = 0; i < K; ++i) {
+            int32_t t = a.cand[c * K + i];
+            ci[i] = t;
+            t = min(max(t, 0), int32_t(a.T - (QUADS ? 2 : 1)));
+#pragma unroll
+            for (int q = 0; q < NT; ++q) {
+                const float4 ta = a.pack[t + q].a, tb = a.pack[t + q].b, tc = a.pack[t + q].c;
+                tri[i][q] = unpack(ta, tb, tc);
+                if (q == 0) {
+                    mv[i] = make_float3(ta.x, ta.y, ta.z);
+                    mn[i] = make_float3(tc.y, tc.z, tc.w);
                 }
+                if (a.tri_mask != nullptr) active = active && a.tri_mask[t + q] != 0;
             }
-            full[0] = ld3(a.tx + 3 * itx);
+        }
+    }
+    const float3 from = ld3(a.tx + 3 * itx);
+
+    for (int64_t irx = rx0; irx < rx1; ++irx) {
+        const int64_t p0 = (itx * a.nrx + irx) * a.C + c0;  // first path of the warp
+        const int64_t p = p0 + lane;
+        bool prevalid = false;
+        if (have) {
+            float3 full[K + 2];
+            full[0] = from;
             full[K + 1] = ld3(a.rx + 3 * irx);
             image_method_path<K>(full, mv, mn);
 
@@ -77,12 +98,9 @@ trace_stage_a_kernel(const TraceArgs a) {
                 const float3 d = sub3(full[i + 1], full[i]);
                 small = small || (dot3(d, d) < a.min_len);
                 if (i < K) {
-                    const int32_t t = min(max(ci[i], 0), int32_t(a.T - (QUADS ? 2 : 1)));
                     float tt;
-                    bool hit = mt_exact(o, d, unpack(a.pack[t].a, a.pack[t].b, a.pack[t].c), a.eps, tt);
-                    if (QUADS)
-                        hit = hit || mt_exact(o, d, unpack(a.pack[t + 1].a, a.pack[t + 1].b, a.pack[t + 1].c),
-                                              a.eps, tt);
+                    bool hit = mt_exact(o, d, tri[i][0], a.eps, tt);
+                    if (QUADS) hit = hit || mt_exact(o, d, tri[i][NT - 1], a.eps, tt);
                     inside = inside && hit;
                     const float dp = dot3(sub3(full[i], mv[i]), mn[i]);
                     const float dn = dot3(sub3(full[i + 2], mv[i]), mn[i]);
@@ -92,7 +110,6 @@ trace_stage_a_kernel(const TraceArgs a) {
 #pragma unroll
             for (int i = 0; i < K + 2; ++i) finite = finite && finite3(full[i]);
 
-            // stage the dense outputs in shared memory: the warp's 32 paths are contiguous in HBM
             float *sv = stage_v + lane * NV3;
 #pragma unroll
             for (int i = 0; i < K + 2; ++i) st3(sv + 3 * i, finite ? full[i] : make_float3(0.f, 0.f, 0.f));
@@ -104,13 +121,13 @@ trace_stage_a_kernel(const TraceArgs a) {
             prevalid = inside && same && !small && finite && active;
             a.out_mask[p] = prevalid ? 1 : 0;
         }
-        // coalesced 16-byte stores of the warp's block of paths (32 * 12 (K+2) bytes, 16-byte aligned)
         __syncwarp();
         {
-            const int64_t n = (a.P - base) < 32 ? (a.P - base) : 32;
-            float *gv = a.out_vertices + base * NV3;
-            int32_t *go = a.out_objects + base * (K + 2);
-            if (n == 32 && a.wide_stores) {
+            float *gv = a.out_vertices + p0 * NV3;
+            int32_t *go = a.out_objects + p0 * (K + 2);
+            const bool wide = n_warp == 32 &&
+                              ((reinterpret_cast<uintptr_t>(gv) | reinterpret_cast<uintptr_t>(go)) & 15) == 0;
+            if (wide) {
                 float4 *gv4 = reinterpret_cast<float4 *>(gv);
                 const float4 *sv4 = reinterpret_cast<const float4 *>(stage_v);
 #pragma unroll
@@ -120,8 +137,8 @@ trace_stage_a_kernel(const TraceArgs a) {
 #pragma unroll
                 for (int i = lane; i < 8 * (K + 2); i += 32) go4[i] = so4[i];
             } else {
-                for (int64_t i = lane; i < n * NV3; i += 32) gv[i] = stage_v[i];
-                for (int64_t i = lane; i < n * (K + 2); i += 32) go[i] = stage_o[i];
+                for (int i = lane; i < n_warp * NV3; i += 32) gv[i] = stage_v[i];
+                for (int i = lane; i < n_warp * (K + 2); i += 32) go[i] = stage_o[i];
             }
         }
         __syncwarp();
@@ -384,92 +401,115 @@ __device__ __forceinline__ void warp_accumulate3(float *base, int64_t key, float
     }
 }
 
+// Candidate-major decomposition: thread = (candidate c, transmitter, chunk of receivers).  The mirror
+// data of candidate c (gather of the three vertices of each triangle, unit normals) is built once and
+// reused for every receiver of the chunk; the cotangents that flow into the mirrors are accumulated
+// in registers over the chunk, so the scatter into g_vertices costs 9k atomics per THREAD instead of
+// per path, and the chain through `normalize((v1-v0) x (v2-v1))` — linear in the accumulated
+// cotangent — is applied once.  Lanes of a warp hold consecutive candidates of the same receiver, so
+// the cotangent reads are coalesced and g_rx needs one shuffle reduction + one atomic per warp.
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 trace_vjp_kernel(int64_t V, int64_t T, const float *__restrict__ verts,
                  const int32_t *__restrict__ tris, int64_t ntx, const float *__restrict__ tx,
                  int64_t nrx, const float *__restrict__ rx, int64_t C,
-                 const int32_t *__restrict__ cand, const float *__restrict__ g_out, int64_t P,
-                 float *g_tx, float *g_rx, float *g_verts) {
-    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-    const int lane = threadIdx.x & 31;
+                 const int32_t *__restrict__ cand, const float *__restrict__ g_out,
+                 int64_t rx_per_chunk, float *g_tx, float *g_rx, float *g_verts) {
     constexpr int KK = K > 0 ? K : 1;
-    for (int64_t base = blockIdx.x * int64_t(blockDim.x) + threadIdx.x - lane; base < P;
-         base += stride) {
-        const int64_t p = base + lane;
-        bool live = false;
-        int64_t itx = 0, irx = 0;
-        float3 g_from = make_float3(0.f, 0.f, 0.f), g_to = make_float3(0.f, 0.f, 0.f);
-        if (p < P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t itx = blockIdx.z;
+    const int64_t rx0 = int64_t(blockIdx.y) * rx_per_chunk;
+    const int64_t rx1 = rx0 + rx_per_chunk < nrx ? rx0 + rx_per_chunk : nrx;
+    const bool have = c < C;
+
+    int64_t vi[KK][3];
+    float3 v0[KK], v1[KK], v2[KK], mn[KK];
+    if (have) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const int64_t t = min(max(int64_t(cand[c * K + i]), int64_t(0)), T - 1);
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                vi[i][q] = min(max(int64_t(tris[3 * t + q]), int64_t(0)), V - 1);
+            v0[i] = ld3(verts + 3 * vi[i][0]);
+            v1[i] = ld3(verts + 3 * vi[i][1]);
+            v2[i] = ld3(verts + 3 * vi[i][2]);
+            mn[i] = unit_normal(v0[i], v1[i], v2[i]);
+        }
+    }
+    const float3 from = ld3(tx + 3 * itx);
+    float3 acc_from = make_float3(0.f, 0.f, 0.f);
+    float3 acc_mv[KK], acc_mn[KK];
+#pragma unroll
+    for (int i = 0; i < KK; ++i) acc_mv[i] = acc_mn[i] = make_float3(0.f, 0.f, 0.f);
+
+    for (int64_t irx = rx0; irx < rx1; ++irx) {
+        float3 g_to = make_float3(0.f, 0.f, 0.f);
+        if (have) {
+            const int64_t p = (itx * nrx + irx) * C + c;
             const float *g = g_out + p * (K + 2) * 3;
             float3 gp[KK];
-            bool nz = false;
             const float3 g0 = ld3(g), g1 = ld3(g + 3 * (K + 1));
-            nz = (g0.x != 0.f) || (g0.y != 0.f) || (g0.z != 0.f) || (g1.x != 0.f) || (g1.y != 0.f) ||
-                 (g1.z != 0.f);
+            bool nz = (g0.x != 0.f) || (g0.y != 0.f) || (g0.z != 0.f) || (g1.x != 0.f) ||
+                      (g1.y != 0.f) || (g1.z != 0.f);
 #pragma unroll
             for (int i = 0; i < K; ++i) {
                 gp[i] = ld3(g + 3 * (i + 1));
                 nz = nz || (gp[i].x != 0.f) || (gp[i].y != 0.f) || (gp[i].z != 0.f);
             }
             if (nz) {
-                const int64_t c = p % C;
-                irx = (p / C) % nrx;
-                itx = p / (C * nrx);
-                int64_t vi[KK][3];
-                float3 v0[KK], v1[KK], v2[KK], mn[KK];
-#pragma unroll
-                for (int i = 0; i < K; ++i) {
-                    const int64_t t = min(max(int64_t(cand[c * K + i]), int64_t(0)), T - 1);
-#pragma unroll
-                    for (int q = 0; q < 3; ++q)
-                        vi[i][q] = min(max(int64_t(tris[3 * t + q]), int64_t(0)), V - 1);
-                    v0[i] = ld3(verts + 3 * vi[i][0]);
-                    v1[i] = ld3(verts + 3 * vi[i][1]);
-                    v2[i] = ld3(verts + 3 * vi[i][2]);
-                    mn[i] = unit_normal(v0[i], v1[i], v2[i]);
-                }
                 float3 full[K + 2];
-                full[0] = ld3(tx + 3 * itx);
+                full[0] = from;
                 full[K + 1] = ld3(rx + 3 * irx);
                 image_method_path<K>(full, v0, mn);
                 bool finite = true;
 #pragma unroll
                 for (int i = 0; i < K + 2; ++i) finite = finite && finite3(full[i]);
                 if (finite) {  // where(is_finite, full_paths, 0): no gradient otherwise
-                    live = true;
-                    float3 g_mv[KK], g_mn[KK];
-#pragma unroll
-                    for (int i = 0; i < KK; ++i)
-                        g_mv[i] = g_mn[i] = make_float3(0.f, 0.f, 0.f);
-                    g_from = g0;
+                    acc_from = add3(acc_from, g0);
                     g_to = g1;
                     if (K > 0)
-                        image_method_reverse<K>(full[0], full[K + 1], v0, mn, gp, g_from, g_to, g_mv,
-                                                g_mn);
-#pragma unroll
-                    for (int i = 0; i < K; ++i) {
-                        // n = N / len, N = A × B, A = v1 - v0, B = v2 - v1
-                        const float3 A = sub3(v1[i], v0[i]), B = sub3(v2[i], v1[i]);
-                        const float3 N = cross3(A, B);
-                        const float len = __fsqrt_rn(dot3(N, N));
-                        float3 gN;
-                        if (len == 0.0f) {
-                            gN = g_mn[i];
-                        } else {
-                            const float proj = dot3(mn[i], g_mn[i]);
-                            gN = scale3(sub3(g_mn[i], scale3(mn[i], proj)), __fdiv_rn(1.0f, len));
-                        }
-                        const float3 gA = cross3(B, gN), gB = cross3(gN, A);
-                        atomic_add3(g_verts + 3 * vi[i][0], sub3(g_mv[i], gA));
-                        atomic_add3(g_verts + 3 * vi[i][1], sub3(gA, gB));
-                        atomic_add3(g_verts + 3 * vi[i][2], gB);
-                    }
+                        image_method_reverse<K>(full[0], full[K + 1], v0, mn, gp, acc_from, g_to, acc_mv,
+                                                acc_mn);
                 }
             }
         }
-        warp_accumulate3(g_tx, itx, g_from, live);
-        warp_accumulate3(g_rx, irx, g_to, live);
+        // every lane of the warp works on the same receiver
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            g_to.x += __shfl_xor_sync(kFull, g_to.x, off);
+            g_to.y += __shfl_xor_sync(kFull, g_to.y, off);
+            g_to.z += __shfl_xor_sync(kFull, g_to.z, off);
+        }
+        if (lane == 0) atomic_add3(g_rx + 3 * irx, g_to);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        acc_from.x += __shfl_xor_sync(kFull, acc_from.x, off);
+        acc_from.y += __shfl_xor_sync(kFull, acc_from.y, off);
+        acc_from.z += __shfl_xor_sync(kFull, acc_from.z, off);
+    }
+    if (lane == 0) atomic_add3(g_tx + 3 * itx, acc_from);
+    if (have) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            // n = N / len, N = A × B, A = v1 - v0, B = v2 - v1
+            const float3 A = sub3(v1[i], v0[i]), B = sub3(v2[i], v1[i]);
+            const float3 N = cross3(A, B);
+            const float len = __fsqrt_rn(dot3(N, N));
+            float3 gN;
+            if (len == 0.0f) {
+                gN = acc_mn[i];
+            } else {
+                const float proj = dot3(mn[i], acc_mn[i]);
+                gN = scale3(sub3(acc_mn[i], scale3(mn[i], proj)), __fdiv_rn(1.0f, len));
+            }
+            const float3 gA = cross3(B, gN), gB = cross3(gN, A);
+            atomic_add3(g_verts + 3 * vi[i][0], sub3(acc_mv[i], gA));
+            atomic_add3(g_verts + 3 * vi[i][1], sub3(gA, gB));
+            atomic_add3(g_verts + 3 * vi[i][2], gB);
+        }
     }
 }
 
@@ -666,13 +706,19 @@ template <int K>
 int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, bool profile,
                  const Tri48 *pack_active, float hit_tol, int64_t *tests_done,
                  int64_t *units_scratch, uint32_t *list2, int64_t *list2_count) {
-    const int threads = 256;
-    const int64_t blocks = (a.P + threads - 1) / threads;
-    const unsigned grid = unsigned(blocks < 148 * 8 ? blocks : 148 * 8);
+    // candidates along x, receiver chunks along y (enough of them to fill the GPU), transmitters along z
+    const int threads = 128;
+    const int64_t cblocks = (a.C + threads - 1) / threads;
+    if (a.ntx > 65535) return DRT_ERR_UNSUPPORTED;
+    int64_t chunks = (int64_t(148) * 32 + cblocks * a.ntx - 1) / (cblocks * a.ntx);
+    chunks = chunks < 1 ? 1 : (chunks > a.nrx ? a.nrx : chunks);
+    if (chunks > 65535) chunks = 65535;
+    const int64_t rx_per_chunk = (a.nrx + chunks - 1) / chunks;
+    const dim3 grid(unsigned(cblocks), unsigned((a.nrx + rx_per_chunk - 1) / rx_per_chunk), unsigned(a.ntx));
     if (quads)
-        trace_stage_a_kernel<K, true><<<grid, threads, 0, s>>>(a);
+        trace_stage_a_kernel<K, true><<<grid, threads, 0, s>>>(a, rx_per_chunk);
     else
-        trace_stage_a_kernel<K, false><<<grid, threads, 0, s>>>(a);
+        trace_stage_a_kernel<K, false><<<grid, threads, 0, s>>>(a, rx_per_chunk);
     if (cudaGetLastError() != cudaSuccess) return DRT_ERR_CUDA;
     if (a.T == 0) return DRT_OK;  // empty mesh: nothing can block (_mesh.py:3053-3057)
 
@@ -807,7 +853,6 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
     a.out_vertices = out_vertices;
     a.out_objects = out_objects;
     a.out_mask = out_mask;
-    a.wide_stores = ((reinterpret_cast<uintptr_t>(out_vertices) | reinterpret_cast<uintptr_t>(out_objects)) & 15) == 0;
     a.list = reinterpret_cast<uint32_t *>(ws + w.list);
     a.list_count = counters;
     int64_t *tests_done = stats;  // stats[0]
@@ -851,13 +896,20 @@ int drt_trace_path_candidates_vjp(drt_stream_t stream, int64_t V, int64_t T, con
     if (P == 0) return DRT_OK;
     if (!tx || !rx || !g_out) return DRT_ERR_NULL_POINTER;
     if (order > 0 && (!cand || !vertices || !triangles || T == 0 || V == 0)) return DRT_ERR_NULL_POINTER;
-    const int threads = 256;
-    const int64_t blocks = (P + threads - 1) / threads;
-    const unsigned grid = unsigned(blocks < 148 * 8 ? blocks : 148 * 8);
+    // candidates along x, receiver chunks along y (enough of them to fill the GPU), transmitters along z
+    const int threads = 128;
+    const int64_t cblocks = (C + threads - 1) / threads;
+    if (ntx > 65535) return DRT_ERR_UNSUPPORTED;
+    int64_t chunks = (int64_t(148) * 16 + cblocks * ntx - 1) / (cblocks * ntx);
+    chunks = chunks < 1 ? 1 : (chunks > nrx ? nrx : chunks);
+    if (chunks > 65535) chunks = 65535;
+    const int64_t rx_per_chunk = (nrx + chunks - 1) / chunks;
+    const dim3 grid(unsigned(cblocks), unsigned((nrx + rx_per_chunk - 1) / rx_per_chunk), unsigned(ntx));
 #define DRT_VJP_CASE(K)                                                                          \
     case K:                                                                                      \
         trace_vjp_kernel<K><<<grid, threads, 0, s>>>(V, T, vertices, triangles, ntx, tx, nrx, rx, \
-                                                     C, cand, g_out, P, g_tx, g_rx, g_vertices);  \
+                                                     C, cand, g_out, rx_per_chunk, g_tx, g_rx,    \
+                                                     g_vertices);                                 \
         break;
     switch (order) {
         DRT_VJP_CASE(0) DRT_VJP_CASE(1) DRT_VJP_CASE(2) DRT_VJP_CASE(3) DRT_VJP_CASE(4)
