@@ -383,10 +383,20 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             "peak_source": peak_src, "bytes_per_test": BYTES_PER_TEST,
             "tests_per_launch": tests_per_launch, "kernel_ms": kms,
             "kernel_share_of_step": kms * args.steps / ms if kms else None,
+            # what actually bounds the kernel: issue slots; 63 = SASS instructions per
+            # test (cuobjdump of the inner loop), peak = 148 SMs x 4 schedulers x SM clock
+            "fp32_issue": {
+                "sass_instructions_per_test": 63,
+                "achieved_warp_instructions_per_s": 63 * tests_per_launch / 32 / (kms * 1e-3) if kms else None,
+                "peak_warp_instructions_per_s": 148 * 4 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else None,
+            },
             "note": "streamed-operand model (36 B per executed test); the packed mesh is on-chip "
                     "resident so DRAM traffic is far below it and the binding limit is FP32 issue — "
                     "see DESIGN.md and profiles/",
         }
+        fi = roofline["fp32_issue"]
+        if fi["achieved_warp_instructions_per_s"] and fi["peak_warp_instructions_per_s"]:
+            fi["frac"] = fi["achieved_warp_instructions_per_s"] / fi["peak_warp_instructions_per_s"]
         traffic_file = ROOT / "profiles" / "traffic.json"
         if traffic_file.exists():
             roofline["traffic"] = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch")
