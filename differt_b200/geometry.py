@@ -207,7 +207,7 @@ def ray_intersect_triangle(
         t = _FirstHitDistanceGrad.apply(
             t.reshape(n), ve.contiguous(), tris, oe.contiguous(), de.contiguous(), faces
         ).reshape(batch)
-    return pl.out(t), pl.out(hit.bool())
+    return pl.out(t), pl.out(hit.view(torch.bool))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -264,7 +264,7 @@ def ray_intersect_any_triangle(
     out = torch.zeros(batch, dtype=torch.uint8, device=o.device)
     T = int(tv.shape[-3])
     if T == 0 or numel(batch) == 0:
-        return pl.out(out.bool())
+        return pl.out(out.view(torch.bool))
     ob, db = o.expand(*batch, 3), d.expand(*batch, 3)
     eps, tol = _default(kwargs.get("epsilon"), 10.0), _default(hit_tol, 100.0)
     for sel, tvi, acti in _mesh_batches(batch, tv, act):
@@ -279,7 +279,7 @@ def ray_intersect_any_triangle(
             )
         )
         out[sel] = res.view(out[sel].shape)
-    return pl.out(out.bool())
+    return pl.out(out.view(torch.bool))
 
 
 def first_triangle_hit_by_ray(
@@ -465,7 +465,7 @@ def triangles_visible_from_vertex(
     B = numel(batch)
     out = torch.zeros((*batch, T), dtype=torch.uint8, device=vx.device)
     if T == 0 or B == 0:
-        return pl.out(out.bool())
+        return pl.out(out.view(torch.bool))
     tv = tv.contiguous()
     if ray_directions is None:
         centers = tv.mean(dim=-2, keepdim=True)
@@ -485,7 +485,7 @@ def triangles_visible_from_vertex(
             _default(kwargs.get("epsilon"), 10.0), ptr(out), None,
         )
     )
-    return pl.out(out.bool())
+    return pl.out(out.view(torch.bool))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -617,4 +617,4 @@ def consecutive_vertices_are_on_same_side_of_mirror(
                 stream_ptr(), ndim, shape, k, ptr(keep[0]), sv, ptr(keep[1]), sm, ptr(keep[2]), sn, ptr(out)
             )
         )
-    return pl.out(out.bool())
+    return pl.out(out.view(torch.bool))

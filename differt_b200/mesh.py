@@ -102,7 +102,7 @@ class Mesh:
         out = torch.zeros(batch, dtype=torch.uint8, device=o.device)
         R = numel(batch)
         if self.num_triangles == 0 or R == 0:
-            return pl.out(out.bool())
+            return pl.out(out.view(torch.bool))
         o = o.detach().expand(*batch, 3).reshape(R, 3).contiguous()
         d = d.detach().expand(*batch, 3).reshape(R, 3).contiguous()
         pack = geometry.pack_mesh(self.vertices.detach(), self.triangles, self._mask_u8())
@@ -115,7 +115,7 @@ class Mesh:
                 100.0 * F32_EPS if hit_tol is None else float(hit_tol), ptr(out), None,
             )
         )
-        return pl.out(out.bool())
+        return pl.out(out.view(torch.bool))
 
     def first_triangle_hit_by_ray(self, ray_origins, ray_directions, *, epsilon=None, batch_size=512):
         """Reference ``Mesh.first_triangle_hit_by_ray`` (``_mesh.py:3096-3162``): ``(index, t)`` with

@@ -126,7 +126,7 @@ def trace_path_candidates(
     paths = TracedPaths(
         vertices=out_v,
         objects=out_o,
-        mask=out_m.bool(),
+        mask=out_m.view(torch.bool),  # the kernels write exactly 0 / 1: reinterpret, no copy
         interaction_types=it,
         confidence_threshold=confidence_threshold,
     )

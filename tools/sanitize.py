@@ -1,0 +1,46 @@
+"""Small end-to-end run of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck).
+
+    gpurun -- compute-sanitizer --tool memcheck python tools/sanitize.py
+"""
+import sys
+sys.path.insert(0, ".")
+import numpy as np, torch
+import differt_b200 as drt
+from differt_b200 import scenes
+from differt_b200.distributed import trace_path_candidates_sharded
+
+rng = np.random.default_rng(0)
+v, t = scenes.urban_grid(11, 11)           # 1454 triangles: 3 tiles → head + ring both exercised
+mesh = drt.Mesh.from_numpy(v, t)
+tri = mesh.triangle_vertices.contiguous()
+lo, hi = v.min(0), v.max(0)
+o = torch.from_numpy(rng.uniform(lo, hi + [0, 0, 20], (6000, 3)).astype(np.float32)).cuda()
+e = torch.from_numpy(rng.uniform(lo, hi + [0, 0, 20], (6000, 3)).astype(np.float32)).cuda()
+d = e - o
+print("any", int(drt.ray_intersect_any_triangle(o, d, tri).sum()))
+print("mesh any", int(mesh.ray_intersect_any_triangle(o, d).sum()))
+idx, tt = drt.first_triangle_hit_by_ray(o, d, tri)
+print("first", int((idx >= 0).sum()))
+print("visible", int(mesh.triangles_visible_from_vertex(torch.tensor([[150.0, 150.0, 60.0]]).cuda(), num_rays=20000).sum()))
+tx = np.array([[150.0, 150.0, 48.0]], np.float32)
+rx = scenes.receivers_grid(v, 8)
+for order, n in ((1, 1454), (2, 3000), (3, 3000), (6, 500)):
+    cand = scenes.complete_graph_candidates(t.shape[0], 1) if order == 1 else scenes.sampled_candidates(t.shape[0], order, n)
+    for dense in (False, True):
+        p = drt.trace_path_candidates(mesh, tx, rx, cand, dense_blockage=dense, with_stats=True)
+        print("trace", order, dense, p.num_valid_paths, p.stats)
+paths, valid = trace_path_candidates_sharded(mesh, tx, rx, torch.from_numpy(scenes.complete_graph_candidates(t.shape[0], 1)).cuda())
+print("sharded", valid.num_valid_paths)
+mg = drt.Mesh(mesh.vertices.clone().requires_grad_(True), mesh.triangles)
+txg = torch.from_numpy(tx).cuda().requires_grad_(True)
+p = drt.trace_path_candidates(mg, txg, rx, scenes.sampled_candidates(t.shape[0], 2, 512))
+p.vertices.sum().backward()
+print("vjp", float(mg.vertices.grad.abs().sum()), float(txg.grad.abs().sum()))
+f = torch.from_numpy(rng.normal(size=(1000, 3)).astype(np.float32)).cuda().requires_grad_(True)
+mv = torch.from_numpy(rng.normal(size=(1000, 4, 3)).astype(np.float32)).cuda()
+mn = torch.nn.functional.normalize(torch.from_numpy(rng.normal(size=(1000, 4, 3)).astype(np.float32)).cuda(), dim=-1)
+drt.image_method(f, f.detach() + 1.0, mv, mn).sum().backward()
+gen = drt.VisiblePathCandidates(50, 3, rng.uniform(size=50) < 0.5, rng.uniform(size=50) < 0.5, None)
+print("digraph", len(gen), int(gen.chunk().sum()))
+torch.cuda.synchronize()
+print("sanitize run complete")
