@@ -6,7 +6,7 @@ Importing the package loads ``libdiffert_b200.so``; there is no CPU or PyTorch f
 """
 
 from . import _lib  # noqa: F401  (fails loudly if the CUDA library is missing)
-from . import geometry, rt, scenes, solvers
+from . import geometry, launch, rt, scenes, solvers
 from .geometry import (
     consecutive_vertices_are_on_same_side_of_mirror,
     fibonacci_lattice,
@@ -19,6 +19,7 @@ from .geometry import (
     triangles_visible_from_vertex,
     viewing_frustum,
 )
+from .launch import LaunchedPaths, compute_tx_mlm, launch_paths, launch_rays
 from .mesh import Mesh, TracedPaths
 from .solvers import (
     VisiblePathCandidates,
@@ -31,7 +32,11 @@ from .solvers import (
 __version__ = "0.1.0"
 
 __all__ = [
+    "LaunchedPaths",
     "Mesh",
+    "compute_tx_mlm",
+    "launch_paths",
+    "launch_rays",
     "TracedPaths",
     "VisiblePathCandidates",
     "generate_visible_path_candidates",

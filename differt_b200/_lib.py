@@ -60,6 +60,11 @@ PROTOTYPES: dict[str, tuple] = {
     "drt_compact_valid_paths": (
         C.c_int, [ptr, i64, i32, ptr, ptr, ptr, i64, ptr, size_t, ptr, ptr, ptr, ptr]),
     "drt_complete_graph_candidates": (C.c_int, [ptr, i64, i32, i64, i64, i32, ptr]),
+    "drt_sbr_bounce": (C.c_int, [ptr, i64, i64, i64, i64, ptr, ptr, ptr, ptr, ptr, ptr, ptr, f32, ptr, ptr]),
+    "drt_mlm_step": (
+        C.c_int,
+        [ptr, i64, i64, i64, ptr, ptr, ptr, ptr, ptr, ptr, ptr, i32, i32, i32, f32, f32, f32, f32, f32, i32,
+         i32, f32, ptr]),
     "drt_digraph_candidates_workspace_bytes": (size_t, [i64, i32]),
     "drt_digraph_candidates_prepare": (C.c_int, [ptr, i64, i32, ptr, ptr, ptr, ptr, size_t, ptr]),
     "drt_digraph_candidates": (C.c_int, [ptr, i64, i32, ptr, i64, i64, i32, ptr]),

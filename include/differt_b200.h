@@ -264,6 +264,30 @@ DRT_API int drt_digraph_candidates(drt_stream_t stream, int64_t num_nodes, int32
                            const void *workspace, int64_t start, int64_t count,
                            int32_t stride_multiplier, int32_t *out);
 
+/* ---------------------------------------------------------------------------------------------
+ * N3  shooting-and-bouncing rays.  The nearest hit of every ray comes from
+ *     drt_first_triangle_hit_by_ray between the steps; these entry points are the element-wise
+ *     remainder of one bounce.
+ *  drt_sbr_bounce: SBRPathLauncher.launch_paths scan body (reference: _solvers.py:279-356, 407-444):
+ *     masks [num_tx, num_rx, num_rays] u8 of THIS bounce = receiver within sqrt(max_dist) of the ray
+ *     before its hit (filter_rays), then origins / directions / valid [num_tx, num_rays] are bounced
+ *     in place (bounce_rays); vertices_out (nullable) [num_tx, num_rays, 3] receives the new origins.
+ *  drt_mlm_step: one iteration of the multipath-lifetime-map kernel (reference: _scene.py:81-171):
+ *     receiver-plane crossing test + atomic OR of the path hash into output [num_tx, dim_x, dim_y],
+ *     then reflection, hash update (hash constants _scene.py:60-78) and the epsilon offset of the
+ *     next query origin.  Rays that miss are retired (alive = 0).
+ * ------------------------------------------------------------------------------------------- */
+DRT_API int drt_sbr_bounce(drt_stream_t stream, int64_t num_tx, int64_t num_rays, int64_t num_rx,
+                   int64_t num_triangles, const void *pack, float *origins, float *directions,
+                   uint8_t *valid, const int32_t *faces, const float *t_hit, const float *rx,
+                   float max_dist, uint8_t *masks, float *vertices_out /*nullable*/);
+DRT_API int drt_mlm_step(drt_stream_t stream, int64_t num_tx, int64_t num_rays, int64_t num_triangles,
+                 const void *pack, float *origins, float *directions, uint32_t *hashes,
+                 uint8_t *alive, const int32_t *faces, const float *t_first, int32_t iteration,
+                 int32_t min_order, int32_t assume_quads, float receiver_height, float min_x,
+                 float max_x, float min_y, float max_y, int32_t dim_x, int32_t dim_y, float epsilon,
+                 uint32_t *output);
+
 #ifdef __cplusplus
 }
 #endif

@@ -664,3 +664,127 @@ def trace_vjp(vertices, triangles, tx, rx, path_candidates, g_out_vertices):
     np.add.at(gV, ti[..., 1], (gA - gB).astype(np.float32))
     np.add.at(gV, ti[..., 2], gB.astype(np.float32))
     return g_tx.astype(np.float32), g_rx.astype(np.float32), gV
+
+
+# ------------------------------------------------------------------------------------------------
+# N3: shooting-and-bouncing rays (SBRPathLauncher) and the multipath lifetime map
+# ------------------------------------------------------------------------------------------------
+
+
+def sbr_launch_rays(tri, tx, rx, num_rays: int):
+    """``SBRPathLauncher.launch_rays`` (``_solvers.py:1202-1226``): frustum over every triangle vertex
+    and receiver, Fibonacci lattice inside it → ``(origins, directions) [num_tx, num_rays, 3]``."""
+    tx = _f(tx).reshape(-1, 3)
+    world = np.concatenate((_f(tri).reshape(-1, 3), _f(rx).reshape(-1, 3)), axis=0)
+    dirs = np.stack([fibonacci_lattice(num_rays, frustum=viewing_frustum(t, world)) for t in tx])
+    return np.broadcast_to(tx[:, None, :], dirs.shape).copy(), dirs.astype(np.float32)
+
+
+def sbr_launch_paths(vertices, triangles, tx, rx, ray_directions, order: int, *, max_dist=1e-3,
+                     epsilon=None, mask=None, first_hit=None):
+    """``SBRPathLauncher.launch_paths`` (``_solvers.py:358-491``) with the ray directions given.
+
+    ``lax.scan`` over ``order + 1`` bounces of: nearest hit → ``filter_rays`` (``:320-356``) →
+    ``bounce_rays`` (``:279-318``).  The nearest hit uses the pure-JAX ``first_triangle_hit_by_ray``
+    definition (``_utils.py:1775-1960``), like every other kernel here.  Returns
+    ``(path_candidates [num_tx, num_rays, order] i32, vertices [num_tx, num_rays, order, 3] f32,
+    masks [num_tx, num_rx, num_rays, order + 1] bool)`` — the quantities the reference assembles
+    into ``LaunchedPaths`` (``:446-491``).
+    """
+    tri = triangle_vertices(vertices, triangles)
+    nrm = triangle_normals(tri)
+    tx, rx = _f(tx).reshape(-1, 3), _f(rx).reshape(-1, 3)
+    d = _f(ray_directions).copy()
+    ntx, nrays = d.shape[0], d.shape[1]
+    o = np.broadcast_to(tx[:, None, :], d.shape).astype(np.float32).copy()
+    valid = np.ones((ntx, nrays), bool)
+    first_hit = first_hit or (lambda oo, dd: first_triangle_hit_by_ray(oo, dd, tri, mask, epsilon=epsilon))
+    cands, verts, masks = [], [], []
+    max_dist = F32(max_dist)
+    for _ in range(order + 1):
+        faces, t_hit = first_hit(o.reshape(-1, 3), d.reshape(-1, 3))
+        faces, t_hit = faces.reshape(ntx, nrays), t_hit.reshape(ntx, nrays).astype(np.float32)
+        # filter_rays
+        v = rx[None, :, None, :] - o[:, None, :, :]
+        c = cross3(d[:, None, :, :], v)
+        dist2 = (c[..., 0] * c[..., 0] + c[..., 1] * c[..., 1]) + c[..., 2] * c[..., 2]
+        t_rx = dot3(d[:, None, :, :], v)
+        with np.errstate(invalid="ignore"):
+            near = (t_rx > 0) & (t_rx < t_hit[:, None, :]) & valid[:, None, :] & (dist2 < max_dist)
+        masks.append(near)
+        # bounce_rays
+        inside = np.isfinite(t_hit)
+        valid = valid & inside
+        t = np.where(inside, t_hit, F32(0))
+        o = (o + t[..., None] * d).astype(np.float32)
+        n = nrm[faces]  # jnp.take wraps the -1 of a miss to the last triangle
+        k = F32(2.0) * dot3(d, n)
+        d = (d - k[..., None] * n).astype(np.float32)
+        cands.append(faces.astype(np.int32))
+        verts.append(o.copy())
+    path_candidates = np.moveaxis(np.stack(cands[:-1]), 0, -1) if order > 0 else np.zeros((ntx, nrays, 0), np.int32)
+    vertices_out = np.moveaxis(np.stack(verts[:-1]), 0, -2) if order > 0 else np.zeros((ntx, nrays, 0, 3), np.float32)
+    return path_candidates, vertices_out, np.moveaxis(np.stack(masks), 0, -1)
+
+
+MLM_MAGIC_1, MLM_MAGIC_2, MLM_MAGIC_3 = np.uint32(0x9E3779B9), np.uint32(0x045D9F3B), np.uint32(0x811C9DC5)
+
+
+def mlm_combine_hashes(h1, h2):
+    """``combine_hashes`` (``_scene.py:65-69``), uint32 wrap-around arithmetic."""
+    h1, h2 = np.asarray(h1, np.uint32), np.asarray(h2, np.uint32)
+    with np.errstate(over="ignore"):
+        return h1 ^ (h2 + MLM_MAGIC_1 + (h1 << np.uint32(6)) + (h1 >> np.uint32(2)))
+
+
+def mlm_hash_int(x):
+    """``hash_int`` (``_scene.py:72-78``)."""
+    x = np.asarray(x, np.uint32)
+    with np.errstate(over="ignore"):
+        x = ((x >> np.uint32(16)) ^ x) * MLM_MAGIC_2
+        x = ((x >> np.uint32(16)) ^ x) * MLM_MAGIC_2
+    return (x >> np.uint32(16)) ^ x
+
+
+def compute_tx_mlm(vertices, triangles, tx, ray_directions, *, max_order, min_order, assume_quads, dim_x,
+                   dim_y, receiver_height, min_x, max_x, min_y, max_y, mask=None, epsilon=1e-4, first_hit=None):
+    """The loop of ``_compute_tx_mlm_kernel`` (``_scene.py:81-171``) with the ray directions given and
+    the nearest hit taken from ``first_triangle_hit_by_ray`` (the reference asks Warp's BVH,
+    third-party arithmetic).  → ``[num_tx, dim_x, dim_y] uint32``."""
+    tri = triangle_vertices(vertices, triangles)
+    nrm = triangle_normals(tri)
+    tx = _f(tx).reshape(-1, 3)
+    d = _f(ray_directions).copy()
+    ntx, nrays = d.shape[0], d.shape[1]
+    qo = np.broadcast_to(tx[:, None, :], d.shape).astype(np.float32).copy()
+    first_hit = first_hit or (lambda oo, dd: first_triangle_hit_by_ray(oo, dd, tri, mask))
+    eps = F32(epsilon)
+    h = np.full((ntx, nrays), MLM_MAGIC_3, np.uint32)
+    alive = np.ones((ntx, nrays), bool)
+    out = np.zeros((ntx, dim_x, dim_y), np.uint32)
+    rh, x0, x1, y0, y1 = F32(receiver_height), F32(min_x), F32(max_x), F32(min_y), F32(max_y)
+    dx, dy = (x1 - x0) / F32(dim_x), (y1 - y0) / F32(dim_y)
+    itx = np.broadcast_to(np.arange(ntx)[:, None], (ntx, nrays))
+    for it in range(max_order + 1):
+        faces, res_t = first_hit(qo.reshape(-1, 3), d.reshape(-1, 3))
+        faces, res_t = faces.reshape(ntx, nrays), res_t.reshape(ntx, nrays).astype(np.float32)
+        hit = faces >= 0
+        t_hit = np.where(hit, res_t + eps if it > 0 else res_t, INF).astype(np.float32)
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            u = ((rh - qo[..., 2]) / d[..., 2]).astype(np.float32)
+            P = (qo + d * u[..., None]).astype(np.float32)
+            ok = alive & (np.abs(d[..., 2]) > F32(1e-6)) & (u > 0) & (u < t_hit) & (it >= min_order)
+            ok &= (P[..., 0] >= x0) & (P[..., 0] <= x1) & (P[..., 1] >= y0) & (P[..., 1] <= y1)
+            ix = np.clip(np.floor(((P[..., 0] - x0) / dx).astype(np.float32)), 0, dim_x - 1)
+            iy = np.clip(np.floor(((P[..., 1] - y0) / dy).astype(np.float32)), 0, dim_y - 1)
+        sel = np.nonzero(ok)
+        np.bitwise_or.at(out, (itx[sel], ix[sel].astype(np.int64), iy[sel].astype(np.int64)), h[sel])
+        alive = alive & hit
+        o = (qo + d * res_t[..., None]).astype(np.float32)
+        n = nrm[np.where(hit, faces, 0)]
+        k = F32(2.0) * dot3(d, n)
+        d_new = (d - k[..., None] * n).astype(np.float32)
+        h = np.where(alive, mlm_combine_hashes(h, mlm_hash_int((faces // 2 if assume_quads else faces).astype(np.uint32))), h)
+        qo = np.where(alive[..., None], (o + d_new * eps).astype(np.float32), qo)
+        d = np.where(alive[..., None], d_new, d)
+    return out

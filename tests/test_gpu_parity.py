@@ -788,3 +788,82 @@ def test_hybrid_trace_finds_the_golden_paths(drt, kats, two_buildings, order, as
     mh, me = hyb.masked(), exh.masked()
     assert torch.equal(mh.objects, me.objects) and torch.equal(mh.vertices, me.vertices)
     assert mh.vertices.shape[0] >= 1
+
+
+# ------------------------------------------------------------------------------------------------
+# N3: shooting-and-bouncing rays (SBRPathLauncher.launch_paths) and the multipath lifetime map
+# ------------------------------------------------------------------------------------------------
+
+
+def _c_first_hit(tri, mask=None):
+    return lambda o, d: co.first_triangle_hit_by_ray(o, d, tri, mask, batch_size=512)
+
+
+@pytest.mark.parametrize("order", [0, 1, 3])
+def test_sbr_launch_paths_bit_exact(drt, order):
+    v, t = scenes.street_canyon(4)
+    mesh = drt.Mesh.from_numpy(v, t)
+    tx = np.array([[15.0, 0.0, 25.0], [5.0, 2.0, 12.0]], np.float32)
+    rx = np.array([[x, y, 1.5] for x in (2.0, 11.0, 19.0, 33.0) for y in (-6.0, 5.0)], np.float32)
+    tri = orc.triangle_vertices(v, t)
+    _, dirs = orc.sbr_launch_rays(tri, tx, rx, 3000)
+    got = drt.launch_paths(mesh, tx, rx, order, ray_directions=dirs, max_dist=4.0)
+    cand, verts, masks = orc.sbr_launch_paths(v, t, tx, rx, dirs, order, max_dist=4.0, first_hit=_c_first_hit(tri))
+    np.testing.assert_array_equal(got.masks.cpu().numpy(), masks)
+    np.testing.assert_array_equal(got.ray_objects.cpu().numpy(), cand)
+    np.testing.assert_array_equal(bits(got.ray_vertices.cpu().numpy()), bits(verts))
+    assert masks.any(), "the scene must produce receivers in the vicinity of some rays"
+    # the dense views of the reference and the compacted per-order paths agree
+    assert got.vertices.shape == (2, 8, 3000, order + 2, 3) and got.objects.shape == (2, 8, 3000, order + 2)
+    for k in range(order + 1):
+        p = got.get_paths(k)
+        idx = np.argwhere(masks[..., k])
+        assert p.vertices.shape[0] == idx.shape[0]
+        if idx.shape[0]:
+            np.testing.assert_array_equal(p.objects[:, 0].cpu().numpy(), idx[:, 0])
+            np.testing.assert_array_equal(p.objects[:, -1].cpu().numpy(), idx[:, 1])
+            np.testing.assert_array_equal(p.objects[:, 1:-1].cpu().numpy(), cand[idx[:, 0], idx[:, 2], :k])
+
+
+def test_sbr_ray_generation_and_golden_scene(drt, kats, two_buildings):
+    """launch_rays matches the oracle's frustum + lattice, and on the reference's two_buildings scene
+    SBR finds the golden order-1 interaction (test_scene.py:116-160 with method="sbr", which the
+    reference itself only checks at rtol=1)."""
+    v, t = two_buildings
+    g = kats["two_buildings_scene"]
+    mesh = drt.Mesh.from_numpy(v, t)
+    tx, rx = np.array(g["tx"], np.float32).reshape(1, 3), np.array(g["rx"], np.float32).reshape(1, 3)
+    o, d = drt.launch_rays(mesh, tx, rx, 5000)
+    eo, ed = orc.sbr_launch_rays(orc.triangle_vertices(v, t), tx, rx, 5000)
+    np.testing.assert_allclose(d.cpu().numpy(), ed, rtol=0, atol=2e-6)  # libm vs CUDA sin/cos/acos
+    got = drt.launch_paths(mesh, tx, rx, 1, num_rays=200_000, max_dist=1e-1)
+    objs = got.get_paths(1).objects[:, 1].unique().cpu().numpy()
+    expected = np.array(g["orders"]["1"]["objects"]).reshape(-1, 3)[:, 1]  # [tx, triangle, rx] rows
+    assert np.isin(expected - expected % 2, objs - objs % 2).all()
+
+
+def test_mlm_matches_oracle_and_hash_constants(drt):
+    v, t = scenes.street_canyon(3)
+    mesh = drt.Mesh.from_numpy(v, t)
+    tx = np.array([[10.0, 0.0, 20.0], [14.0, 3.0, 8.0]], np.float32)
+    tri = orc.triangle_vertices(v, t)
+    rng = np.random.default_rng(5)
+    dirs = rng.normal(size=(2, 4000, 3)).astype(np.float32)
+    dirs /= np.linalg.norm(dirs, axis=-1, keepdims=True)
+    kw = dict(max_order=2, min_order=0, dim_x=9, dim_y=7, receiver_height=1.5, min_x=-10.0, max_x=30.0,
+              min_y=-25.0, max_y=25.0)
+    got = drt.compute_tx_mlm(mesh, tx, ray_directions=dirs, **kw).cpu().numpy().astype(np.uint32)
+    exp = orc.compute_tx_mlm(v, t, tx, dirs, assume_quads=False, first_hit=_c_first_hit(tri), **kw)
+    np.testing.assert_array_equal(got, exp)
+    assert (got != 0).sum() > 10
+    # line-of-sight cells carry the FNV offset basis 0x811C9DC5 = 2166136261 (test_scene.py:910)
+    los = drt.compute_tx_mlm(mesh, tx, ray_directions=dirs, **{**kw, "max_order": 0}).cpu().numpy()
+    assert set(np.unique(los)) <= {0, 2166136261} and (los == 2166136261).any()
+    # min_order filters the direct paths out
+    no_los = drt.compute_tx_mlm(mesh, tx, ray_directions=dirs, **{**kw, "min_order": 1}).cpu().numpy()
+    exp2 = orc.compute_tx_mlm(v, t, tx, dirs, assume_quads=False, first_hit=_c_first_hit(tri), **{**kw, "min_order": 1})
+    np.testing.assert_array_equal(no_los.astype(np.uint32), exp2)
+    # generated rays: runs end to end and is deterministic
+    a = drt.compute_tx_mlm(mesh, tx, num_rays=20000, **kw)
+    b = drt.compute_tx_mlm(mesh, tx, num_rays=20000, **kw)
+    assert torch.equal(a, b) and int((a != 0).sum()) > 0

@@ -333,3 +333,35 @@ def test_bench_valid_candidates_fixture_is_valid_per_oracle():
     # and the bench workload starts with them
     n3 = min(known["order3"].shape[0], wl["cand"].shape[0] // 4)
     np.testing.assert_array_equal(wl["cand"][:n3], known["order3"][:n3])
+
+
+def test_mlm_hash_functions_known_answers():
+    """combine_hashes / hash_int (reference differt/src/differt/geometry/_scene.py:60-78) evaluated by
+    hand with Python integers."""
+    M1, M2, M3 = 0x9E3779B9, 0x045D9F3B, 0x811C9DC5
+
+    def hash_int(x):
+        x = (((x >> 16) ^ x) * M2) & 0xFFFFFFFF
+        x = (((x >> 16) ^ x) * M2) & 0xFFFFFFFF
+        return (x >> 16) ^ x
+
+    def combine(h1, h2):
+        return h1 ^ ((h2 + M1 + ((h1 << 6) & 0xFFFFFFFF) + (h1 >> 2)) & 0xFFFFFFFF)
+
+    for x in (0, 1, 5, 12345, 0xFFFFFFFF):
+        assert int(orc.mlm_hash_int(x)) == hash_int(x)
+        assert int(orc.mlm_combine_hashes(M3, orc.mlm_hash_int(x))) == combine(M3, hash_int(x))
+    assert int(orc.MLM_MAGIC_3) == 2166136261  # the LOS value differt/tests/geometry/test_scene.py:910 expects
+
+
+def test_sbr_oracle_finds_the_order_one_reflection_of_a_wall():
+    """One vertical wall, TX and RX on the same side: the specular point of the image method
+    (x = 0 plane) is where SBR rays that pass near the RX bounce."""
+    v = np.array([[0, -50, 0], [0, 50, 0], [0, 50, 50], [0, -50, 50]], np.float32)
+    t = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    tx, rx = np.array([[10.0, -5.0, 10.0]], np.float32), np.array([[10.0, 5.0, 10.0]], np.float32)
+    _, dirs = orc.sbr_launch_rays(orc.triangle_vertices(v, t), tx, rx, 40_000)
+    cand, verts, masks = orc.sbr_launch_paths(v, t, tx, rx, dirs, 1, max_dist=1e-2)
+    assert masks[0, 0, :, 1].any()
+    hit = verts[0, masks[0, 0, :, 1], 0, :]
+    np.testing.assert_allclose(hit.mean(0), [0.0, 0.0, 10.0], atol=0.2)
