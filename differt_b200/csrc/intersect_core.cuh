@@ -49,7 +49,14 @@ constexpr int kStages = DRT_STAGES;
 constexpr int kWarps = DRT_WARPS;
 constexpr int kCtasPerSm = DRT_CTAS_PER_SM;
 constexpr int kUnroll = DRT_UNROLL;
-constexpr int kThreads = kWarps * 32;
+// first-hit units carry three running minima per ray: 12 warps x 2 CTAs leaves them 80 registers
+#ifndef DRT_WARPS_FIRST
+#define DRT_WARPS_FIRST 12
+#endif
+template <int MODE>
+struct WarpsFor {
+    static constexpr int value = MODE == 1 /*MODE_FIRST*/ ? DRT_WARPS_FIRST : kWarps;
+};
 constexpr int kHead = DRT_HEAD_TILES;
 constexpr size_t kHeadBytes = size_t(kHead) * kTile * sizeof(Tri48);
 constexpr size_t kRingBytes = size_t(kStages) * kTile * sizeof(Tri48);
@@ -137,8 +144,9 @@ __device__ __forceinline__ uint32_t scan_tile_any(const Tri48 *__restrict__ tile
 // is decided — after an early exit or after it has seen all NT tiles, wherever in the cycle that
 // happens.  No warp idles while another one of its CTA still works on a long unit.
 template <int RPW, int MODE, bool PATH, class Src, class Sink>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+__global__ void __launch_bounds__(WarpsFor<MODE>::value * 32, kCtasPerSm)
 intersect_kernel(const CoreParams p, const Src src, const Sink sink) {
+    constexpr int kWarpsK = WarpsFor<MODE>::value;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Tri48 *head = reinterpret_cast<Tri48 *>(smem_raw);
     Tri48 *ring = reinterpret_cast<Tri48 *>(smem_raw + kHeadBytes);
@@ -146,8 +154,8 @@ intersect_kernel(const CoreParams p, const Src src, const Sink sink) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t num_units = p.num_units_dev ? *p.num_units_dev : p.num_units;
-    const int64_t total_warps = int64_t(gridDim.x) * kWarps;
-    if (int64_t(blockIdx.x) * kWarps >= num_units) return;
+    const int64_t total_warps = int64_t(gridDim.x) * kWarpsK;
+    if (int64_t(blockIdx.x) * kWarpsK >= num_units) return;
 
     const int NT = p.num_tiles;
     const int NH = NT < kHead ? NT : kHead;  // resident head tiles
@@ -185,7 +193,7 @@ intersect_kernel(const CoreParams p, const Src src, const Sink sink) {
     if (NH > 0) mbar_wait(&bars[kStages], 0u);
 
     // per-warp state of the unit in flight
-    int64_t unit = int64_t(blockIdx.x) * kWarps + warp;
+    int64_t unit = int64_t(blockIdx.x) * kWarpsK + warp;
     bool live = unit < num_units;
     float3 o[RPW], d[RPW];
     uint32_t valid = 0, active = 0, hit_any = 0;
@@ -230,22 +238,49 @@ intersect_kernel(const CoreParams p, const Src src, const Sink sink) {
             if (MODE == MODE_ANY) {
                 lane_hits = scan_tile_any<RPW, PATH>(tile, lane, o, d, active, p.eps, p.thr, fast_ok, rows);
             } else {
+                // first-hit: fast reciprocal first; pairs whose |a| is out of its range are skipped and
+                // flagged, and the tile is then redone with the fully general test (idempotent)
+                bool weird = !fast_ok;
+                if (fast_ok) {
 #pragma unroll kUnroll
-                for (int j = lane; j < kTile; j += 32) {
-                    const float4 a = tile[j].a, b = tile[j].b, c = tile[j].c;
-                    const Tri tr = unpack(a, b, c);
+                    for (int j = lane; j < kTile; j += 32) {
+                        const float4 a = tile[j].a, b = tile[j].b, c = tile[j].c;
+                        const Tri tr = unpack(a, b, c);
 #pragma unroll
-                    for (int r = 0; r < RPW; ++r) {
-                        if (active & (1u << r)) {
+                        for (int r = 0; r < RPW; ++r) {
                             float t;
-                            const bool hit = mt_exact(o[r], d[r], tr, p.eps, t);
-                            if (hit && t <= best_t[r]) {
+                            const bool hit = mt_first_fast(o[r], d[r], tr, p.eps, t, weird);
+                            if (hit && t <= best_t[r] && (active & (1u << r))) {
                                 const int64_t gj = int64_t(tile_index) * kTile + j;
                                 const uint32_t key = tie_key(gj, p.batch_size, p.num_triangles);
                                 if (t < best_t[r] || key < best_key[r]) {
                                     best_t[r] = t;
                                     best_key[r] = key;
                                     best_idx[r] = static_cast<int32_t>(gj);
+                                }
+                            }
+                        }
+                    }
+                    weird = __any_sync(kFull, weird);
+                }
+                if (weird) {
+#pragma unroll kUnroll
+                    for (int j = lane; j < kTile; j += 32) {
+                        const float4 a = tile[j].a, b = tile[j].b, c = tile[j].c;
+                        const Tri tr = unpack(a, b, c);
+#pragma unroll
+                        for (int r = 0; r < RPW; ++r) {
+                            if (active & (1u << r)) {
+                                float t;
+                                const bool hit = mt_exact(o[r], d[r], tr, p.eps, t);
+                                if (hit && t <= best_t[r]) {
+                                    const int64_t gj = int64_t(tile_index) * kTile + j;
+                                    const uint32_t key = tie_key(gj, p.batch_size, p.num_triangles);
+                                    if (t < best_t[r] || key < best_key[r]) {
+                                        best_t[r] = t;
+                                        best_key[r] = key;
+                                        best_idx[r] = static_cast<int32_t>(gj);
+                                    }
                                 }
                             }
                         }
@@ -313,11 +348,12 @@ inline cudaError_t launch_intersect(cudaStream_t stream, const CoreParams &p, co
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t blocks = (max_units + kWarps - 1) / kWarps;
+    constexpr int kWarpsK = WarpsFor<MODE>::value;
+    const int64_t blocks = (max_units + kWarpsK - 1) / kWarpsK;
     if (blocks <= 0) return cudaSuccess;
     const int64_t resident_ctas = int64_t(sms) * kCtasPerSm;
     const int grid = static_cast<int>(blocks < resident_ctas ? blocks : resident_ctas);
-    kern<<<grid, kThreads, kSmemBytes, stream>>>(p, src, sink);
+    kern<<<grid, kWarpsK * 32, kSmemBytes, stream>>>(p, src, sink);
     return cudaGetLastError();
 }
 

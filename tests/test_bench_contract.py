@@ -1,0 +1,55 @@
+"""bench.py's reference arm runs on CPU: check the JSON contract of its line (the GPU arm prints the
+same keys plus roofline / clocks and is exercised on the GPU box)."""
+
+from __future__ import annotations
+
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    res = subprocess.run(
+        [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+         "--cpu-seconds", "0.3", "--workload", "urban10k_small"],
+        capture_output=True, text=True, timeout=600, cwd=ROOT,
+    )
+    assert res.returncode == 0, res.stderr
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "ray_triangle_tests_per_s" and d["unit"] == "tests/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["value"] > 1e6 and "workload" in d["config"]
+
+
+def test_non_zero_ranks_of_the_reference_arm_do_nothing():
+    import os
+
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    res = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+def test_workload_is_deterministic_and_sharded_per_rank():
+    sys.path.insert(0, str(ROOT))
+    import numpy as np
+
+    import bench
+
+    a = bench.build_workload("urban10k_small", 0, 2)
+    b = bench.build_workload("urban10k_small", 1, 2)
+    a2 = bench.build_workload("urban10k_small", 0, 2)
+    np.testing.assert_array_equal(a["cand"], a2["cand"])
+    assert a["cand_start"] == 0 and b["cand_start"] == a["cand"].shape[0] and a["cand_global"] == 2 * a["cand"].shape[0]
+    assert not np.array_equal(a["cand"], b["cand"])
+    assert (a["cand"][:, 1:] != a["cand"][:, :-1]).all()
