@@ -26,6 +26,7 @@ PROTOTYPES: dict[str, tuple] = {
     "drt_mesh_pack_triangle_vertices": (C.c_int, [ptr, i64, ptr, ptr, ptr]),
     "drt_mesh_pack_sort_workspace_bytes": (size_t, [i64]),
     "drt_mesh_pack_sort_by_area": (C.c_int, [ptr, i64, ptr, ptr, size_t, ptr]),
+    "drt_mesh_pack_sort_by_keys": (C.c_int, [ptr, i64, ptr, ptr, ptr, size_t, ptr]),
     "drt_ray_intersect_triangle": (
         C.c_int, [ptr, i32, p_i64, ptr, p_i64, ptr, p_i64, ptr, p_i64, f32, ptr, ptr]),
     "drt_ray_intersect_any_triangle": (C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, f32, ptr, ptr]),

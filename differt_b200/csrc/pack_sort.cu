@@ -28,6 +28,11 @@ __global__ void area_keys_kernel(int64_t n, const Tri48 *__restrict__ pack, uint
     idx[j] = static_cast<uint32_t>(j);
 }
 
+__global__ void iota_kernel(int64_t n, uint32_t *__restrict__ idx) {
+    const int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (j < n) idx[j] = static_cast<uint32_t>(j);
+}
+
 __global__ void gather_pack_kernel(int64_t n, const Tri48 *__restrict__ in, const uint32_t *__restrict__ idx,
                                    Tri48 *__restrict__ out) {
     const int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
@@ -90,6 +95,31 @@ int drt_mesh_pack_sort_by_area(drt_stream_t stream, int64_t num_triangles, const
     size_t cub_bytes = l.cub_bytes;
     if (cub::DeviceRadixSort::SortPairsDescending(ws + l.cub, cub_bytes, keys_in, keys_out, idx_in,
                                                   idx_out, static_cast<int>(n), 0, 32, s) != cudaSuccess)
+        return DRT_ERR_CUDA;
+    gather_pack_kernel<<<blocks, 256, 0, s>>>(n, static_cast<const Tri48 *>(pack_in), idx_out,
+                                              static_cast<Tri48 *>(pack_out));
+    return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
+}
+
+int drt_mesh_pack_sort_by_keys(drt_stream_t stream, int64_t num_triangles, const void *pack_in,
+                               const uint32_t *keys, void *workspace, size_t workspace_bytes,
+                               void *pack_out) {
+    if (num_triangles < 0 || num_triangles > (int64_t(1) << 30)) return DRT_ERR_BAD_EXTENT;
+    if (!pack_in || !pack_out || !workspace || !keys) return DRT_ERR_NULL_POINTER;
+    if (pack_in == pack_out) return DRT_ERR_UNSUPPORTED;
+    const int64_t n = int64_t(drt_mesh_pack_bytes(num_triangles) / sizeof(Tri48));
+    const SortLayout l = sort_layout(n);
+    if (workspace_bytes < l.total) return DRT_ERR_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    uint32_t *keys_out = reinterpret_cast<uint32_t *>(ws + l.keys_out);
+    uint32_t *idx_in = reinterpret_cast<uint32_t *>(ws + l.idx_in);
+    uint32_t *idx_out = reinterpret_cast<uint32_t *>(ws + l.idx_out);
+    const unsigned blocks = unsigned((n + 255) / 256);
+    iota_kernel<<<blocks, 256, 0, s>>>(n, idx_in);
+    size_t cub_bytes = l.cub_bytes;
+    if (cub::DeviceRadixSort::SortPairsDescending(ws + l.cub, cub_bytes, keys, keys_out, idx_in, idx_out,
+                                                  static_cast<int>(n), 0, 32, s) != cudaSuccess)
         return DRT_ERR_CUDA;
     gather_pack_kernel<<<blocks, 256, 0, s>>>(n, static_cast<const Tri48 *>(pack_in), idx_out,
                                               static_cast<Tri48 *>(pack_out));

@@ -319,6 +319,58 @@ path_head_kernel(const Tri48 *__restrict__ pack, const int num_head_tiles, const
         atomicAdd(reinterpret_cast<unsigned long long *>(tests_done), (unsigned long long)tests);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Blockage, ordering pass: which triangles block THIS batch?  A sample of the candidates (every
+// `stride`-th path) is tested against every triangle with no early exit, one thread per triangle, and
+// the number of sampled candidates each triangle blocks is counted.  The pack is then re-sorted by
+// that count (stable: ties keep the area order), so the head pass meets the triangles that block
+// most of this transmitter / receiver configuration first.  Any-hit results do not depend on the
+// order, so this is purely a work-reduction heuristic — which is also why the sample can use the
+// fast test without its exactness fallback.
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kCountBatch = 64;  // sampled candidates staged in shared memory at a time
+
+template <int NSEG>
+__global__ void __launch_bounds__(256)
+hit_count_kernel(const Tri48 *__restrict__ pack, const int64_t num_records,
+                 const float *__restrict__ vertices, const int64_t stride, const int64_t num_samples,
+                 const int64_t samples_per_chunk, const float eps, const float thr,
+                 uint32_t *__restrict__ counts) {
+    constexpr int NV3 = (NSEG + 1) * 3;
+    __shared__ float sv[kCountBatch][NV3];
+    const int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    Tri tr;
+    {
+        const int64_t jj = j < num_records ? j : num_records - 1;
+        tr = unpack(pack[jj].a, pack[jj].b, pack[jj].c);
+    }
+    const int64_t s0 = int64_t(blockIdx.y) * samples_per_chunk;
+    const int64_t s1 = s0 + samples_per_chunk < num_samples ? s0 + samples_per_chunk : num_samples;
+    uint32_t c = 0;
+    for (int64_t base = s0; base < s1; base += kCountBatch) {
+        const int nb = int(s1 - base < kCountBatch ? s1 - base : kCountBatch);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb * NV3; i += blockDim.x) {
+            const int u = i / NV3, k = i - u * NV3;
+            sv[u][k] = vertices[(base + u) * stride * NV3 + k];
+        }
+        __syncthreads();
+        for (int u = 0; u < nb; ++u) {
+            bool any = false, weird = false;
+            float3 prev = make_float3(sv[u][0], sv[u][1], sv[u][2]);
+#pragma unroll
+            for (int sgm = 0; sgm < NSEG; ++sgm) {
+                const float3 next = make_float3(sv[u][3 * sgm + 3], sv[u][3 * sgm + 4], sv[u][3 * sgm + 5]);
+                any = mt_any_fast(prev, sub3(next, prev), tr, eps, thr, weird) || any;
+                prev = next;
+            }
+            c += any ? 1u : 0u;
+        }
+    }
+    if (c != 0 && j < num_records) atomicAdd(&counts[j], c);
+}
+
 // generic order: flat (slot, segment) rays, RPW per warp, no path-level early exit
 template <int RPW>
 struct SegRays {
@@ -658,7 +710,7 @@ __global__ void complete_graph_candidates_kernel(int64_t n, int order, int64_t s
 }
 
 struct TraceWorkspace {
-    size_t pack_geom, pack_active, pack_sorted, sort_ws, sort_bytes, list, list2, counters, total;
+    size_t pack_geom, pack_active, pack_sorted, pack_sorted2, hit_counts, sort_ws, sort_bytes, list, list2, counters, total;
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -673,6 +725,10 @@ inline TraceWorkspace trace_workspace_layout(int64_t T, int64_t P) {
     off += align256(pack);
     w.pack_sorted = off;  // blockage pack: active triangles in descending area order (pack_sort.cu)
     off += align256(pack);
+    w.pack_sorted2 = off;  // ... re-sorted by the hit counts of a sample of this batch
+    off += align256(pack);
+    w.hit_counts = off;
+    off += align256(pack / sizeof(Tri48) * sizeof(uint32_t));
     w.sort_ws = off;
     w.sort_bytes = drt_mesh_pack_sort_workspace_bytes(T);
     off += align256(w.sort_bytes);
@@ -705,7 +761,8 @@ static thread_local ProfileRing g_profile;
 template <int K>
 int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, bool profile,
                  const Tri48 *pack_active, float hit_tol, int64_t *tests_done,
-                 int64_t *units_scratch, uint32_t *list2, int64_t *list2_count) {
+                 int64_t *units_scratch, uint32_t *list2, int64_t *list2_count, uint32_t *hit_counts,
+                 Tri48 *pack_sorted2, void *sort_ws, size_t sort_bytes) {
     // candidates along x, receiver chunks along y (enough of them to fill the GPU), transmitters along z
     const int threads = 128;
     const int64_t cblocks = (a.C + threads - 1) / threads;
@@ -738,7 +795,29 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
         cudaEventRecord(g_profile.start[slot], s);
     }
     if constexpr (NSEG <= 6) {
-        // head pass: every candidate against the largest triangles, resident, barrier free
+        // ordering pass (dense batches only: a pruned work list is too short to pay for it)
+        constexpr int64_t kSamples = 32768;
+        if (dense && a.P >= 8 * kSamples && p.eps >= 1.17549435e-38f) {
+            int64_t stride = (a.P / kSamples) | 1;
+            auto gcd = [](int64_t x, int64_t y) { while (y) { const int64_t r = x % y; x = y; y = r; } return x; };
+            while (gcd(stride, a.C) != 1) stride += 2;  // walk across candidates AND receivers
+            const int64_t num_samples = (a.P + stride - 1) / stride;
+            const int64_t records = int64_t(p.num_tiles) * kTile;
+            if (cudaMemsetAsync(hit_counts, 0, size_t(records) * sizeof(uint32_t), s) != cudaSuccess)
+                return DRT_ERR_CUDA;
+            const int chunks = 32;
+            const dim3 cgrid(unsigned((records + 255) / 256), chunks);
+            hit_count_kernel<NSEG><<<cgrid, 256, 0, s>>>(pack_active, records, a.out_vertices, stride,
+                                                         num_samples, (num_samples + chunks - 1) / chunks,
+                                                         a.eps, p.thr, hit_counts);
+            if (cudaGetLastError() != cudaSuccess) return DRT_ERR_CUDA;
+            const int rc = drt_mesh_pack_sort_by_keys(s, a.T, pack_active, hit_counts, sort_ws, sort_bytes,
+                                                      pack_sorted2);
+            if (rc != DRT_OK) return rc;
+            pack_active = pack_sorted2;
+            p.pack = pack_active;
+        }
+        // head pass: every candidate against the likeliest blockers, resident, barrier free
         const int NT = p.num_tiles;
         const int NH = NT < kPathHead ? NT : kPathHead;
         auto hk = path_head_kernel<NSEG>;
@@ -862,7 +941,10 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
 #define DRT_TRACE_CASE(K)                                                                         \
     case K:                                                                                       \
         rc = trace_launch<K>(s, a, quads, dense, profile, pack_active, hit_tol, tests_done,        \
-                             units_scratch, list2, counters + 2);                                 \
+                             units_scratch, list2, counters + 2,                                  \
+                             reinterpret_cast<uint32_t *>(ws + w.hit_counts),                      \
+                             reinterpret_cast<Tri48 *>(ws + w.pack_sorted2), ws + w.sort_ws,      \
+                             w.sort_bytes);                                                       \
         break;
     switch (order) {
         DRT_TRACE_CASE(0) DRT_TRACE_CASE(1) DRT_TRACE_CASE(2) DRT_TRACE_CASE(3) DRT_TRACE_CASE(4)

@@ -91,6 +91,12 @@ DRT_API int drt_mesh_pack_triangle_vertices(drt_stream_t stream, int64_t num_tri
 DRT_API size_t drt_mesh_pack_sort_workspace_bytes(int64_t num_triangles);
 DRT_API int drt_mesh_pack_sort_by_area(drt_stream_t stream, int64_t num_triangles, const void *pack_in,
                                void *workspace, size_t workspace_bytes, void *pack_out);
+/* Same, by caller-supplied keys (device uint32, one per record of the padded pack =
+ * drt_mesh_pack_bytes / 48 entries), descending and STABLE: records with equal keys keep their
+ * order.  The fused trace uses it with per-triangle hit counts of a sample of its own rays. */
+DRT_API int drt_mesh_pack_sort_by_keys(drt_stream_t stream, int64_t num_triangles, const void *pack_in,
+                               const uint32_t *keys, void *workspace, size_t workspace_bytes,
+                               void *pack_out);
 
 /* ---------------------------------------------------------------------------------------------
  * K1  ray_intersect_triangle — element-wise Möller–Trumbore over a broadcast batch
