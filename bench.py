@@ -213,7 +213,7 @@ def run_reference(args, rank: int) -> None:
         tests += n
     dt = time.perf_counter() - t0
     value = tests / dt
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -222,7 +222,7 @@ def run_reference(args, rank: int) -> None:
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def workload_config(wl: dict, world: int, **extra) -> dict:
@@ -433,12 +433,35 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             n, dt, _ = cpu_step(wl, cand, rx)
             line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": sample, "seconds": dt, "host_cpus": os.cpu_count()}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def claim_stdout() -> None:
+    """Keep stdout for the ONE JSON line: everything else that writes to file descriptor 1 (NCCL's
+    version / debug lines, library banners) is sent to stderr instead."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main() -> None:
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
