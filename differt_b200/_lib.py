@@ -61,6 +61,12 @@ PROTOTYPES: dict[str, tuple] = {
     "drt_compact_valid_paths": (
         C.c_int, [ptr, i64, i32, ptr, ptr, ptr, i64, ptr, size_t, ptr, ptr, ptr, ptr]),
     "drt_complete_graph_candidates": (C.c_int, [ptr, i64, i32, i64, i64, i32, ptr]),
+    "drt_bvh_bytes": (size_t, [i64]),
+    "drt_bvh_workspace_bytes": (size_t, [i64]),
+    "drt_bvh_build": (C.c_int, [ptr, i64, ptr, f32, ptr, size_t, ptr]),
+    "drt_bvh_ray_intersect_any_triangle": (C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, f32, ptr]),
+    "drt_bvh_first_triangle_hit_by_ray": (C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, i64, ptr, ptr]),
+    "drt_scatter_visible": (C.c_int, [ptr, i64, i64, i64, ptr, ptr]),
     "drt_sbr_bounce": (C.c_int, [ptr, i64, i64, i64, i64, ptr, ptr, ptr, ptr, ptr, ptr, ptr, f32, ptr, ptr]),
     "drt_mlm_step": (
         C.c_int,

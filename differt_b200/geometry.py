@@ -437,6 +437,16 @@ def fibonacci_lattice(n: int, dtype=None, *, frustum=None):
     return pl.out(torch.stack((sp * torch.cos(lon), sp * torch.sin(lon), torch.cos(lat)), dim=-1))
 
 
+def visibility_directions(vertices: torch.Tensor, tv: torch.Tensor, active, num_rays: int) -> torch.Tensor:
+    """Ray directions of the visibility query (reference ``_utils.py:1668-1700``): frustum over the
+    three vertices AND the centroid of every active triangle, Fibonacci lattice inside it."""
+    centers = tv.mean(dim=-2, keepdim=True)
+    world = torch.cat((tv, centers), dim=-2).reshape(-1, 3)
+    av = None if active is None else active.bool().repeat_interleave(4)
+    frustum = viewing_frustum(vertices, world, av)
+    return fibonacci_lattice(num_rays, frustum=frustum)
+
+
 def triangles_visible_from_vertex(
     vertex,
     triangle_vertices,
@@ -468,11 +478,7 @@ def triangles_visible_from_vertex(
         return pl.out(out.view(torch.bool))
     tv = tv.contiguous()
     if ray_directions is None:
-        centers = tv.mean(dim=-2, keepdim=True)
-        world = torch.cat((tv, centers), dim=-2).reshape(-1, 3)
-        av = None if act is None else act.bool().repeat_interleave(4)
-        frustum = viewing_frustum(vx.reshape(B, 3), world, av)
-        dirs = fibonacci_lattice(num_rays, frustum=frustum)
+        dirs = visibility_directions(vx.reshape(B, 3), tv, act, num_rays)
     else:
         dirs = pl.put(ray_directions, torch.float32)
         num_rays = int(dirs.shape[-2])

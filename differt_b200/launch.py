@@ -131,17 +131,17 @@ def launch_rays(mesh: Mesh, tx_vertices, rx_vertices, num_rays: int):
     return tx[:, None, :].expand(tx.shape[0], num_rays, 3).contiguous(), dirs.contiguous()
 
 
-def _first_hit(pack, T, o, d, eps, faces, t):
-    check(
-        lib.drt_first_triangle_hit_by_ray(
-            stream_ptr(), o.shape[0] * o.shape[1], ptr(o), ptr(d), ptr(pack), T, eps, 512, ptr(faces), ptr(t), None
-        )
-    )
+def _first_hit(pack, T, o, d, eps, faces, t, bvh=None):
+    n = o.shape[0] * o.shape[1]
+    if bvh is not None:  # opt-in accel="bvh"
+        check(lib.drt_bvh_first_triangle_hit_by_ray(stream_ptr(), n, ptr(o), ptr(d), ptr(bvh), T, eps, 512, ptr(faces), ptr(t)))
+    else:
+        check(lib.drt_first_triangle_hit_by_ray(stream_ptr(), n, ptr(o), ptr(d), ptr(pack), T, eps, 512, ptr(faces), ptr(t), None))
 
 
 def launch_paths(
     mesh: Mesh, tx_vertices, rx_vertices, order: int, *, num_rays: int = 1_000_000, epsilon=None,
-    max_dist: float = 1e-3, ray_directions=None,
+    max_dist: float = 1e-3, ray_directions=None, accel: str = "brute",
 ) -> LaunchedPaths:
     """``SBRPathLauncher.launch_paths`` (``_solvers.py:358-491``): ``order + 1`` bounces of nearest hit
     → receivers in the vicinity of the segment (``filter_rays``) → specular bounce (``bounce_rays``).
@@ -160,6 +160,7 @@ def launch_paths(
     ntx, nrays, nrx, T = d.shape[0], d.shape[1], rx.shape[0], mesh.num_triangles
     eps = 10.0 * F32_EPS if epsilon is None else float(epsilon)
     pack = geometry.pack_mesh(mesh.vertices.detach(), mesh.triangles, mesh._mask_u8())
+    bvh = mesh.build_bvh() if accel == "bvh" else None
     valid = torch.ones((ntx, nrays), dtype=torch.uint8, device=dev)
     # bounce-major storage (what the reference's scan stacks); the public views move that axis last
     masks = torch.empty((order + 1, ntx, nrx, nrays), dtype=torch.uint8, device=dev)
@@ -167,7 +168,7 @@ def launch_paths(
     faces = torch.empty((order + 1, ntx, nrays), dtype=torch.int32, device=dev)
     t_hit = torch.empty((ntx, nrays), dtype=torch.float32, device=dev)
     for b in range(order + 1):
-        _first_hit(pack, T, o, d, eps, faces[b], t_hit)
+        _first_hit(pack, T, o, d, eps, faces[b], t_hit, bvh)
         check(
             lib.drt_sbr_bounce(
                 stream_ptr(), ntx, nrays, nrx, T, ptr(pack), ptr(o), ptr(d), ptr(valid), ptr(faces[b]),
@@ -185,7 +186,7 @@ def launch_paths(
 def compute_tx_mlm(
     mesh: Mesh, tx_vertices, *, max_order: int, min_order: int = 0, dim_x: int, dim_y: int,
     num_rays: int = 1_000_000, receiver_height: float, min_x: float, max_x: float, min_y: float, max_y: float,
-    ray_directions=None, epsilon: float = 1e-4,
+    ray_directions=None, epsilon: float = 1e-4, accel: str = "brute",
 ) -> torch.Tensor:
     """Multipath lifetime map (reference ``_compute_tx_mlm``, ``_scene.py:226-302`` + kernel ``:81-171``):
     for every transmitter, every cell of the ``dim_x × dim_y`` receiver grid at ``z = receiver_height``
@@ -217,12 +218,13 @@ def compute_tx_mlm(
     alive = torch.ones((ntx, nrays), dtype=torch.uint8, device=dev)
     faces = torch.full((ntx, nrays), -1, dtype=torch.int32, device=dev)
     t_first = torch.full((ntx, nrays), float("inf"), dtype=torch.float32, device=dev)
-    pack = None
+    pack = bvh = None
     if T > 0:
         pack = geometry.pack_mesh(mesh.vertices.detach(), mesh.triangles, mesh._mask_u8())
+        bvh = mesh.build_bvh() if accel == "bvh" else None
     for it in range(max_order + 1):
         if T > 0:
-            _first_hit(pack, T, o, d, 10.0 * F32_EPS, faces, t_first)
+            _first_hit(pack, T, o, d, 10.0 * F32_EPS, faces, t_first, bvh)
         check(
             lib.drt_mlm_step(
                 stream_ptr(), ntx, nrays, T, ptr(pack), ptr(o), ptr(d), ptr(hashes), ptr(alive), ptr(faces),

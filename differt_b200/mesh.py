@@ -21,6 +21,12 @@ from ._tensor import F32_EPS, Placement, numel, ptr, require_cuda, stream_ptr
 __all__ = ["Mesh", "TracedPaths"]
 
 
+def _check_accel(accel: str) -> str:
+    if accel not in ("brute", "bvh"):
+        raise ValueError(f"accel must be 'brute' or 'bvh', got {accel!r}")
+    return accel
+
+
 @dataclasses.dataclass
 class Mesh:
     """Triangle mesh resident on the GPU: ``vertices [V,3] f32``, ``triangles [T,3] i32``,
@@ -91,9 +97,23 @@ class Mesh:
     def _mask_u8(self) -> torch.Tensor | None:
         return None if self.mask is None else self.mask.to(torch.uint8)
 
+    def build_bvh(self, relative_pad: float = 1e-4) -> torch.Tensor:
+        """Linear BVH over the (masked) triangles for the opt-in ``accel="bvh"`` queries
+        (``drt_bvh_build``): a caller-owned blob, rebuilt in ~0.1 ms — nothing is cached, so it can
+        never go stale the way the reference's ``_WARP_MESHES_CACHE`` can (``_mesh.py:48-55``)."""
+        T = self.num_triangles
+        dev = self.vertices.device
+        pack = geometry.pack_mesh(self.vertices.detach(), self.triangles, self._mask_u8())
+        bvh = torch.empty(max(lib.drt_bvh_bytes(T), 256), dtype=torch.uint8, device=dev)
+        ws = torch.empty(max(lib.drt_bvh_workspace_bytes(T), 256), dtype=torch.uint8, device=dev)
+        check(lib.drt_bvh_build(stream_ptr(), T, ptr(pack), float(relative_pad), ptr(ws), ws.numel(), ptr(bvh)))
+        return bvh
+
     # -- the three accelerated queries (reference: Warp launchers, _mesh.py:3018-3253) ------------
-    def ray_intersect_any_triangle(self, ray_origins, ray_directions, *, hit_tol=None, epsilon=None):
-        """Reference ``Mesh.ray_intersect_any_triangle`` (``_mesh.py:3018-3094``); no gradient."""
+    def ray_intersect_any_triangle(self, ray_origins, ray_directions, *, hit_tol=None, epsilon=None,
+                                   accel: str = "brute"):
+        """Reference ``Mesh.ray_intersect_any_triangle`` (``_mesh.py:3018-3094``); no gradient.
+        ``accel="bvh"`` opts into the BVH traversal (see ``csrc/bvh.cu`` for the exactness caveat)."""
         pl = Placement()
         pl.device = self.vertices.device
         o = pl.put(ray_origins, torch.float32)
@@ -105,6 +125,16 @@ class Mesh:
             return pl.out(out.view(torch.bool))
         o = o.detach().expand(*batch, 3).reshape(R, 3).contiguous()
         d = d.detach().expand(*batch, 3).reshape(R, 3).contiguous()
+        eps_ = 10.0 * F32_EPS if epsilon is None else float(epsilon)
+        tol_ = 100.0 * F32_EPS if hit_tol is None else float(hit_tol)
+        if _check_accel(accel) == "bvh":
+            bvh = self.build_bvh()
+            check(
+                lib.drt_bvh_ray_intersect_any_triangle(
+                    stream_ptr(), R, ptr(o), ptr(d), ptr(bvh), self.num_triangles, eps_, tol_, ptr(out)
+                )
+            )
+            return pl.out(out.view(torch.bool))
         pack = geometry.pack_mesh(self.vertices.detach(), self.triangles, self._mask_u8())
         if R >= geometry._SORT_MIN_RAYS:
             pack = geometry.sort_pack_by_area(pack, self.num_triangles)
@@ -117,7 +147,8 @@ class Mesh:
         )
         return pl.out(out.view(torch.bool))
 
-    def first_triangle_hit_by_ray(self, ray_origins, ray_directions, *, epsilon=None, batch_size=512):
+    def first_triangle_hit_by_ray(self, ray_origins, ray_directions, *, epsilon=None, batch_size=512,
+                                  accel: str = "brute"):
         """Reference ``Mesh.first_triangle_hit_by_ray`` (``_mesh.py:3096-3162``): ``(index, t)`` with
         ``t`` differentiable w.r.t. origins, directions and ``self.vertices`` (``custom_vjp``,
         ``_mesh.py:258-344``); the index carries no gradient."""
@@ -133,23 +164,60 @@ class Mesh:
             return pl.out(idx.view(batch)), pl.out(t.view(batch))
         of = o.expand(*batch, 3).reshape(R, 3).contiguous()
         df = d.expand(*batch, 3).reshape(R, 3).contiguous()
-        pack = geometry.pack_mesh(self.vertices.detach(), self.triangles, self._mask_u8())
-        check(
-            lib.drt_first_triangle_hit_by_ray(
-                stream_ptr(), R, ptr(of), ptr(df), ptr(pack), self.num_triangles,
-                10.0 * F32_EPS if epsilon is None else float(epsilon),
-                0 if batch_size is None else int(batch_size), ptr(idx), ptr(t), None,
+        eps_ = 10.0 * F32_EPS if epsilon is None else float(epsilon)
+        bs_ = 0 if batch_size is None else int(batch_size)
+        if _check_accel(accel) == "bvh":
+            bvh = self.build_bvh()
+            check(
+                lib.drt_bvh_first_triangle_hit_by_ray(
+                    stream_ptr(), R, ptr(of), ptr(df), ptr(bvh), self.num_triangles, eps_, bs_, ptr(idx), ptr(t)
+                )
             )
-        )
+        else:
+            pack = geometry.pack_mesh(self.vertices.detach(), self.triangles, self._mask_u8())
+            check(
+                lib.drt_first_triangle_hit_by_ray(
+                    stream_ptr(), R, ptr(of), ptr(df), ptr(pack), self.num_triangles, eps_, bs_, ptr(idx),
+                    ptr(t), None,
+                )
+            )
         if torch.is_grad_enabled() and any(x.requires_grad for x in (of, df, self.vertices)):
             t = geometry._FirstHitDistanceGrad.apply(t, self.vertices, self.triangles, of, df, idx)
         return pl.out(idx.view(batch)), pl.out(t.view(batch))
 
-    def triangles_visible_from_vertex(self, vertex, num_rays: int = 1_000_000, **kwargs: Any):
-        """Reference ``Mesh.triangles_visible_from_vertex`` (``_mesh.py:3164-3253``); no gradient."""
-        return geometry.triangles_visible_from_vertex(
-            vertex, self.triangle_vertices.detach(), self.mask, num_rays=num_rays, **kwargs
+    def triangles_visible_from_vertex(self, vertex, num_rays: int = 1_000_000, *, accel: str = "brute",
+                                      **kwargs: Any):
+        """Reference ``Mesh.triangles_visible_from_vertex`` (``_mesh.py:3164-3253``); no gradient.
+        ``accel="bvh"``: the same rays, nearest hits from the BVH, then the scatter."""
+        if _check_accel(accel) == "brute" or self.num_triangles == 0:
+            return geometry.triangles_visible_from_vertex(
+                vertex, self.triangle_vertices.detach(), self.mask, num_rays=num_rays, **kwargs
+            )
+        pl = Placement()
+        pl.device = self.vertices.device
+        vx = pl.put(vertex, torch.float32)
+        batch = tuple(vx.shape[:-1])
+        B, T = numel(batch), self.num_triangles
+        out = torch.zeros((*batch, T), dtype=torch.uint8, device=vx.device)
+        if B == 0:
+            return pl.out(out.view(torch.bool))
+        dirs = kwargs.get("ray_directions")
+        if dirs is None:
+            dirs = geometry.visibility_directions(vx.reshape(B, 3), self.triangle_vertices.detach(), self.mask, num_rays)
+        dirs = pl.put(dirs, torch.float32).reshape(B, -1, 3).contiguous()
+        n = int(dirs.shape[1])
+        origins = vx.reshape(B, 1, 3).expand(B, n, 3).contiguous()
+        idx = torch.empty(B * n, dtype=torch.int32, device=vx.device)
+        tt = torch.empty(B * n, dtype=torch.float32, device=vx.device)
+        bvh = self.build_bvh()
+        eps_ = 10.0 * F32_EPS if kwargs.get("epsilon") is None else float(kwargs["epsilon"])
+        check(
+            lib.drt_bvh_first_triangle_hit_by_ray(
+                stream_ptr(), B * n, ptr(origins), ptr(dirs), ptr(bvh), T, eps_, 0, ptr(idx), ptr(tt)
+            )
         )
+        check(lib.drt_scatter_visible(stream_ptr(), B, n, T, ptr(idx), ptr(out)))
+        return pl.out(out.view(torch.bool))
 
 
 @dataclasses.dataclass

@@ -216,7 +216,7 @@ class VisiblePathCandidates:
 
 
 def generate_visible_path_candidates(
-    mesh: Mesh, tx_vertices, rx_vertices, order: int, *, num_rays: int = 1_000_000
+    mesh: Mesh, tx_vertices, rx_vertices, order: int, *, num_rays: int = 1_000_000, accel: str = "brute"
 ) -> VisiblePathCandidates:
     """``HybridPathTracer.generate_path_candidates`` (reference ``_solvers.py:993-1058``): visibility
     of every triangle from the transmitters and from the receivers (K4), merged over quads and over
@@ -225,8 +225,8 @@ def generate_visible_path_candidates(
     pl.device = mesh.vertices.device
     tx = pl.put(tx_vertices, torch.float32).reshape(-1, 3)
     rx = pl.put(rx_vertices, torch.float32).reshape(-1, 3)
-    vis_tx = mesh.triangles_visible_from_vertex(tx, num_rays=num_rays).any(dim=0)
-    vis_rx = mesh.triangles_visible_from_vertex(rx, num_rays=num_rays).any(dim=0)
+    vis_tx = mesh.triangles_visible_from_vertex(tx, num_rays=num_rays, accel=accel).any(dim=0)
+    vis_rx = mesh.triangles_visible_from_vertex(rx, num_rays=num_rays, accel=accel).any(dim=0)
     active = mesh.mask
     if mesh.assume_quads:
         vis_tx = vis_tx.reshape(-1, 2).any(dim=-1)

@@ -271,6 +271,31 @@ DRT_API int drt_digraph_candidates(drt_stream_t stream, int64_t num_nodes, int32
                            int32_t stride_multiplier, int32_t *out);
 
 /* ---------------------------------------------------------------------------------------------
+ * N2  OPT-IN bounding-volume hierarchy (linear BVH over Morton-sorted triangles) for the queries the
+ *     reference answers with Warp's BVH (wp.mesh_query_ray[_anyhit], _mesh.py:142-223, 347-401).
+ *     Every triangle that is reached is tested with the same arithmetic as the brute-force kernels
+ *     (bit-identical t, same tie rule); node boxes are padded by relative_pad x scene size.  Results
+ *     equal the brute-force ones except for rays grazing a triangle's plane, where the reference's
+ *     fp32 test can accept hits no bounding volume contains — hence opt-in.
+ *     The BVH blob is caller-owned and stateless like the pack: build, query, discard.
+ * ------------------------------------------------------------------------------------------- */
+DRT_API size_t drt_bvh_bytes(int64_t num_triangles);
+DRT_API size_t drt_bvh_workspace_bytes(int64_t num_triangles);
+DRT_API int drt_bvh_build(drt_stream_t stream, int64_t num_triangles, const void *pack, float relative_pad,
+                  void *workspace, size_t workspace_bytes, void *bvh_out);
+DRT_API int drt_bvh_ray_intersect_any_triangle(drt_stream_t stream, int64_t num_rays,
+                                       const float *ray_origins, const float *ray_directions,
+                                       const void *bvh, int64_t num_triangles, float epsilon,
+                                       float hit_tol, uint8_t *out);
+DRT_API int drt_bvh_first_triangle_hit_by_ray(drt_stream_t stream, int64_t num_rays,
+                                      const float *ray_origins, const float *ray_directions,
+                                      const void *bvh, int64_t num_triangles, float epsilon,
+                                      int64_t batch_size, int32_t *out_index, float *out_t);
+/* out [B,T] u8 (zero-filled by the callee): out[b, first_hit_index[b, r]] = 1 for every hit */
+DRT_API int drt_scatter_visible(drt_stream_t stream, int64_t num_vertices_batch, int64_t num_rays,
+                        int64_t num_triangles, const int32_t *first_hit_index, uint8_t *out);
+
+/* ---------------------------------------------------------------------------------------------
  * N3  shooting-and-bouncing rays.  The nearest hit of every ray comes from
  *     drt_first_triangle_hit_by_ray between the steps; these entry points are the element-wise
  *     remainder of one bounce.

@@ -867,3 +867,64 @@ def test_mlm_matches_oracle_and_hash_constants(drt):
     a = drt.compute_tx_mlm(mesh, tx, num_rays=20000, **kw)
     b = drt.compute_tx_mlm(mesh, tx, num_rays=20000, **kw)
     assert torch.equal(a, b) and int((a != 0).sum()) > 0
+
+
+# ------------------------------------------------------------------------------------------------
+# N2: opt-in BVH — same answers as the brute-force kernels on the test scenes
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("scene", ["urban", "bruxelles", "box", "single"])
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_bvh_queries_equal_brute_force(drt, rng, bruxelles, scene, use_mask):
+    if scene == "urban":
+        v, t = scenes.urban_grid(29, 29)
+    elif scene == "bruxelles":
+        v, t = bruxelles
+    elif scene == "box":
+        v, t = scenes.box(2.0, 3.0, 4.0, with_top=True)
+    else:
+        v, t = scenes.box(2.0, 3.0, 4.0, with_top=True)
+        t = t[:1]
+    mask = (rng.uniform(size=t.shape[0]) < 0.6) if use_mask else None
+    mesh = drt.Mesh.from_numpy(v, t, mask=mask)
+    n = 200_000 if t.shape[0] > 100 else 20_000
+    lo, hi = v.min(0) - 1.0, v.max(0) + 1.0
+    o = rng.uniform(lo, hi, size=(n, 3)).astype(np.float32)
+    e = rng.uniform(lo, hi, size=(n, 3)).astype(np.float32)
+    oc, dc = torch.from_numpy(o).cuda(), torch.from_numpy(e - o).cuda()
+    a0 = mesh.ray_intersect_any_triangle(oc, dc)
+    a1 = mesh.ray_intersect_any_triangle(oc, dc, accel="bvh")
+    assert torch.equal(a0, a1) and (scene == "single" or bool(a0.any()))
+    for bs in (512, None):
+        i0, t0 = mesh.first_triangle_hit_by_ray(oc, dc, batch_size=bs)
+        i1, t1 = mesh.first_triangle_hit_by_ray(oc, dc, batch_size=bs, accel="bvh")
+        assert torch.equal(t0.view(torch.int32), t1.view(torch.int32))
+        assert torch.equal(i0, i1)
+    # and against the oracle on a sub-sample
+    tri = orc.triangle_vertices(v, t)
+    ei, et = co.first_triangle_hit_by_ray(o[:3000], dc[:3000].cpu().numpy(), tri, mask, batch_size=None)
+    np.testing.assert_array_equal(i1[:3000].cpu().numpy(), ei)  # i1: last loop iteration, batch_size=None
+    np.testing.assert_array_equal(bits(t1[:3000].cpu().numpy()), bits(et))
+
+
+def test_bvh_visibility_sbr_and_hybrid_match_brute_force(drt, kats, two_buildings):
+    v, t = scenes.urban_grid(7, 7)
+    mesh = drt.Mesh.from_numpy(v, t)
+    vx = np.array([[90.0, 95.0, 50.0], [15.0, 15.0, 1.5]], np.float32)
+    assert torch.equal(mesh.triangles_visible_from_vertex(vx, num_rays=50_000),
+                       mesh.triangles_visible_from_vertex(vx, num_rays=50_000, accel="bvh"))
+    tx, rx = vx[:1], np.array([[45.0, 15.0, 1.5], [105.0, 75.0, 1.5]], np.float32)
+    a = drt.launch_paths(mesh, tx, rx, 2, num_rays=30_000, max_dist=1.0)
+    b = drt.launch_paths(mesh, tx, rx, 2, num_rays=30_000, max_dist=1.0, accel="bvh")
+    assert torch.equal(a.masks, b.masks) and torch.equal(a.ray_objects, b.ray_objects)
+    assert torch.equal(a.ray_vertices.view(torch.int32), b.ray_vertices.view(torch.int32))
+    kw = dict(max_order=2, dim_x=8, dim_y=8, num_rays=30_000, receiver_height=1.5, min_x=-15.0, max_x=195.0,
+              min_y=-15.0, max_y=195.0)
+    assert torch.equal(drt.compute_tx_mlm(mesh, tx, **kw), drt.compute_tx_mlm(mesh, tx, accel="bvh", **kw))
+    # empty mesh and degenerate rays
+    empty = drt.Mesh(torch.zeros((0, 3)), torch.zeros((0, 3), dtype=torch.int32))
+    assert not bool(empty.ray_intersect_any_triangle(vx, vx, accel="bvh").any())
+    z = torch.zeros((5, 3)).cuda()
+    i1, t1 = mesh.first_triangle_hit_by_ray(z + 50.0, z, accel="bvh")
+    assert bool((i1 == -1).all()) and bool(torch.isinf(t1).all())

@@ -133,6 +133,18 @@ def main() -> None:
     row("K4 triangles_visible_from_vertex [1 vertex, 10^6 rays (reference default) x 10 094 tri]", ms, 1_000_000 * T, "tests",
         36 * 1_000_000 * T, "includes frustum + Fibonacci lattice generation")
 
+    # ---- N2: the opt-in BVH on the same queries ---------------------------------------------------------
+    ms = timed(lambda: mesh.build_bvh())
+    row("N2 drt_bvh_build [10 094 tri] incl. pack", ms, T, "triangles", None, "Morton keys, radix sort, Karras tree, refit")
+    ms = timed(lambda: mesh.ray_intersect_any_triangle(o1, d1, accel="bvh"))
+    row("N2 BVH any-hit [2^20 rays x 10 094 tri] incl. build", ms, R * T, "tests", None, "opt-in; brute-force-equivalent tests/s")
+    ms = timed(lambda: mesh.first_triangle_hit_by_ray(o1, d1, accel="bvh"))
+    row("N2 BVH first-hit [2^20 rays x 10 094 tri] incl. build", ms, R * T, "tests", None, "opt-in; brute-force-equivalent tests/s")
+    ms = timed(lambda: mesh.triangles_visible_from_vertex(txp, num_rays=1_000_000, accel="bvh"), iters=5)
+    row("N2 BVH visibility [1 vertex, 10^6 rays x 10 094 tri] incl. ray generation + build", ms, 1_000_000 * T, "tests", None, "opt-in")
+    ms = timed(lambda: bmesh.first_triangle_hit_by_ray(fo, fd, accel="bvh"))
+    row("N2 BVH first-hit, reference harness: 10 000 rays x bruxelles.obj incl. build", ms, 10_000 * 14_206, "tests", None, "opt-in")
+
     # ---- K5 image method, 36 k B / path ----------------------------------------------------------------
     for n5, k in ((1 << 22, 3), (10_000, 8)):
         f = torch.from_numpy(rng.uniform(-100, 100, (n5, 3)).astype(np.float32)).to(dev)
