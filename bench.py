@@ -48,6 +48,8 @@ WORKLOADS = {
     "urban10k_1tx_4096rx_order3": dict(scene=("urban", 29, 29), rx=(64, 64), order=3, cand=4096),
     # BASELINE.json configs[1], one chunk of the exhaustive candidate list
     "canyon1k_1tx_256rx_order2": dict(scene=("canyon", 41), rx=(16, 16), order=2, cand=65536),
+    # BASELINE.json configs[4] per GPU: 50k-triangle mesh, 1 TX x 16 384 RX, order 4, 2048 candidates
+    "urban50k_1tx_16384rx_order4": dict(scene=("urban", 64, 65), rx=(128, 128), order=4, cand=2048),
     # small variant for quick checks (not a bench line)
     "urban10k_small": dict(scene=("urban", 29, 29), rx=(16, 16), order=3, cand=1024),
 }
