@@ -301,7 +301,9 @@ intersect_kernel(const CoreParams p, const Src src, const Sink sink) {
                 } else {
 #pragma unroll
                     for (int r = 0; r < RPW; ++r) {
-                        const uint32_t tb = float_order_bits(best_t[r]);
+                        // -0 and +0 are the same distance (they tie and the index decides): + 0.0f
+                        // canonicalises the sign before the bit-pattern comparison
+                        const uint32_t tb = float_order_bits(best_t[r] + 0.0f);
                         const uint32_t tmin = __reduce_min_sync(kFull, tb);
                         const uint32_t key = (tb == tmin) ? best_key[r] : 0xffffffffu;
                         const uint32_t kmin = __reduce_min_sync(kFull, key);

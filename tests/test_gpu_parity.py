@@ -928,3 +928,67 @@ def test_bvh_visibility_sbr_and_hybrid_match_brute_force(drt, kats, two_building
     z = torch.zeros((5, 3)).cuda()
     i1, t1 = mesh.first_triangle_hit_by_ray(z + 50.0, z, accel="bvh")
     assert bool((i1 == -1).all()) and bool(torch.isinf(t1).all())
+
+
+# ------------------------------------------------------------------------------------------------
+# the exactness fallbacks of the inlined reciprocal (|a| >= 2^126, epsilon below FLT_MIN, inf / NaN)
+# ------------------------------------------------------------------------------------------------
+
+
+def _extreme_scene(rng, n_tri=700, n_rays=3000):
+    """Triangles and rays whose determinant `a` spans the whole float range: coordinates from 1e-12 to
+    1e14 (|a| up to ~1e38+, overflowing to inf), plus rays with inf / NaN components."""
+    scale_t = 10.0 ** rng.uniform(-12, 14, size=(n_tri, 1, 1))
+    tri = (rng.normal(size=(n_tri, 3, 3)) * scale_t).astype(np.float32)
+    scale_r = 10.0 ** rng.uniform(-12, 14, size=(n_rays, 1))
+    o = (rng.normal(size=(n_rays, 3)) * scale_r).astype(np.float32)
+    d = (rng.normal(size=(n_rays, 3)) * scale_r * 10.0).astype(np.float32)
+    # aim a third of the rays at a triangle centroid so that real hits exist at every magnitude
+    aim = rng.integers(0, n_tri, size=n_rays // 3)
+    c = tri[aim].mean(axis=1)
+    o[: aim.size] = (c - d[: aim.size] * np.float32(0.5)).astype(np.float32)
+    d[-5:, 0] = np.inf
+    o[-10:-5, 1] = np.nan
+    d[-15:-10] = 0.0
+    return tri, o, d
+
+
+@pytest.mark.parametrize("epsilon", [None, 1e-42, 0.0, -1.0])
+def test_any_and_first_hit_bit_exact_on_extreme_magnitudes(drt, rng, epsilon):
+    tri, o, d = _extreme_scene(rng)
+    with np.errstate(all="ignore"):
+        exp_any = co.ray_intersect_any_triangle(o, d, tri, epsilon=epsilon)
+        ei, et = co.first_triangle_hit_by_ray(o, d, tri, epsilon=epsilon)
+    kw = {} if epsilon is None else {"epsilon": epsilon}
+    got_any = drt.ray_intersect_any_triangle(o, d, tri, **kw)
+    np.testing.assert_array_equal(got_any.numpy(), exp_any)
+    gi, gt = drt.first_triangle_hit_by_ray(o, d, tri, **kw)
+    np.testing.assert_array_equal(gi.numpy(), ei)
+    np.testing.assert_array_equal(bits(gt.numpy()), bits(et))
+    assert exp_any.any() and (ei >= 0).sum() > 100
+    # the sorted-pack path (>= 4096 rays) as well
+    o2, d2 = np.tile(o, (2, 1)), np.tile(d, (2, 1))
+    np.testing.assert_array_equal(drt.ray_intersect_any_triangle(o2, d2, tri, **kw).numpy(), np.tile(exp_any, 2))
+
+
+def test_trace_bit_exact_on_extreme_magnitudes(drt, rng):
+    """Dense and pruned blockage on a mesh whose determinants overflow the fast reciprocal's range."""
+    n_tri = 600
+    # mostly small triangles scattered over +-1e3, a few astronomically large ones far away
+    scale = np.where(rng.uniform(size=(n_tri, 1, 1)) < 0.97, 10.0 ** rng.uniform(-3, 1.5, size=(n_tri, 1, 1)),
+                     10.0 ** rng.uniform(9, 13, size=(n_tri, 1, 1)))
+    centre = rng.normal(size=(n_tri, 1, 3)) * np.where(scale < 1e3, 1e3, 1e15)
+    tv = (centre + rng.normal(size=(n_tri, 3, 3)) * scale).astype(np.float32)
+    v = tv.reshape(-1, 3)
+    t = np.arange(3 * n_tri, dtype=np.int32).reshape(n_tri, 3)
+    tx = (rng.normal(size=(2, 3)) * 1e3).astype(np.float32)
+    rx = (rng.normal(size=(5, 3)) * 1e3).astype(np.float32)
+    cand = scenes.sampled_candidates(n_tri, 2, 700)
+    mesh = drt.Mesh.from_numpy(v, t)
+    with np.errstate(all="ignore"):
+        ev, eo, em, st = co.trace_path_candidates(v, t, tx, rx, cand, stages=True)
+    for dense in (True, False):
+        got = drt.trace_path_candidates(mesh, tx, rx, cand, dense_blockage=dense)
+        np.testing.assert_array_equal(got.mask.cpu().numpy(), em)
+        np.testing.assert_array_equal(bits(got.vertices.cpu().numpy()), bits(ev))
+    assert st["blocked"].any() and (~st["blocked"]).any()
