@@ -992,3 +992,41 @@ def test_trace_bit_exact_on_extreme_magnitudes(drt, rng):
         np.testing.assert_array_equal(got.mask.cpu().numpy(), em)
         np.testing.assert_array_equal(bits(got.vertices.cpu().numpy()), bits(ev))
     assert st["blocked"].any() and (~st["blocked"]).any()
+
+
+def test_exact_zero_and_tie_cases_on_a_lattice_scene(drt, rng):
+    """Integer-coordinate boxes and rays between lattice points: determinants, barycentrics and
+    distances hit exact zeros, ones and ties (rays through edges and corners, rays inside the plane
+    of a wall, zero-length rays), where signed zeros and the tie rule decide."""
+    parts = [scenes.box(4.0, 4.0, 6.0, with_top=True, center=(8.0 * i, 8.0 * j, 3.0)) for i in range(4) for j in range(4)]
+    v, t = scenes._merge(parts)
+    tri = orc.triangle_vertices(v, t)
+    g = np.arange(-4, 30, 2, dtype=np.float32)
+    pts = np.stack(np.meshgrid(g, g, np.array([0.0, 3.0, 6.0, 7.0], np.float32), indexing="ij"), -1).reshape(-1, 3)
+    a = pts[rng.integers(0, pts.shape[0], 6000)]
+    b = pts[rng.integers(0, pts.shape[0], 6000)]
+    o, d = a, (b - a).astype(np.float32)
+    for bs in (512, 7, None):
+        ei, et = co.first_triangle_hit_by_ray(o, d, tri, batch_size=bs)
+        gi, gt = drt.first_triangle_hit_by_ray(o, d, tri, batch_size=bs)
+        np.testing.assert_array_equal(gi.numpy(), ei)
+        np.testing.assert_array_equal(bits(gt.numpy()), bits(et))
+    np.testing.assert_array_equal(drt.ray_intersect_any_triangle(o, d, tri).numpy(),
+                                  co.ray_intersect_any_triangle(o, d, tri))
+    mesh = drt.Mesh.from_numpy(v, t)
+    gi2, gt2 = mesh.first_triangle_hit_by_ray(o, d, accel="bvh")
+    ei, et = co.first_triangle_hit_by_ray(o, d, tri, batch_size=512)
+    # the BVH reaches the same triangles on this scene too (ties resolved by the same key)
+    np.testing.assert_array_equal(gi2.cpu().numpy(), ei)
+    np.testing.assert_array_equal(bits(gt2.cpu().numpy()), bits(et))
+    # trace: lattice tx / rx, every order-2 candidate of a sub-mesh, with and without quads
+    tx, rx = pts[[5, 77]], pts[rng.integers(0, pts.shape[0], 40)]
+    sub_v, sub_t = scenes._merge(parts[:3])
+    for quads in (False, True):
+        cand = scenes.complete_graph_candidates(sub_t.shape[0] // (2 if quads else 1), 2) * (2 if quads else 1)
+        m = drt.Mesh.from_numpy(sub_v, sub_t, assume_quads=quads)
+        ev, eo, em = co.trace_path_candidates(sub_v, sub_t, tx, rx, cand, assume_quads=quads)
+        for dense in (True, False):
+            got = drt.trace_path_candidates(m, tx, rx, cand, dense_blockage=dense)
+            np.testing.assert_array_equal(got.mask.cpu().numpy(), em)
+            np.testing.assert_array_equal(bits(got.vertices.cpu().numpy()), bits(ev))
