@@ -27,6 +27,8 @@ from .solvers import (
     generate_visible_path_candidates,
     trace_path_candidates,
     trace_paths,
+    trace_paths_chunks_iter,
+    trace_valid_paths,
 )
 
 __version__ = "0.1.0"
@@ -55,6 +57,8 @@ __all__ = [
     "solvers",
     "trace_path_candidates",
     "trace_paths",
+    "trace_paths_chunks_iter",
+    "trace_valid_paths",
     "triangles_visible_from_vertex",
     "viewing_frustum",
 ]

@@ -25,6 +25,8 @@ __all__ = [
     "generate_all_path_candidates_chunks_iter",
     "trace_path_candidates",
     "trace_paths",
+    "trace_paths_chunks_iter",
+    "trace_valid_paths",
 ]
 
 
@@ -237,6 +239,65 @@ def generate_visible_path_candidates(
         mesh.num_primitives, order, vis_tx, vis_rx, active, assume_quads=mesh.assume_quads,
         device=mesh.vertices.device,
     )
+
+
+def _candidate_chunks(mesh: Mesh, tx_vertices, rx_vertices, order: int, chunk_size: int, solver: str,
+                      num_rays: int, accel: str):
+    """``(total, iterator of (start, candidates))`` for the exhaustive or the hybrid candidate set."""
+    if solver == "exhaustive":
+        total = num_complete_graph_candidates(mesh.num_primitives, order)
+        gen = lambda start: generate_all_path_candidates(  # noqa: E731
+            mesh.num_primitives, order, assume_quads=mesh.assume_quads, start=start, count=chunk_size,
+            device=mesh.vertices.device)
+    elif solver == "hybrid":
+        vis = generate_visible_path_candidates(mesh, tx_vertices, rx_vertices, order, num_rays=num_rays, accel=accel)
+        total = len(vis)
+        gen = lambda start: vis.chunk(start, chunk_size)  # noqa: E731
+    else:
+        raise ValueError(f"Unknown solver: {solver}")
+    return total, ((start, gen(start)) for start in range(0, total, chunk_size))
+
+
+def trace_paths_chunks_iter(mesh: Mesh, tx_vertices, rx_vertices, order: int, *, chunk_size: int,
+                            solver: str = "exhaustive", num_rays: int = 1_000_000, accel: str = "brute",
+                            **kwargs) -> Iterator[TracedPaths]:
+    """``Scene.trace_paths(order, chunk_size=...)`` (reference ``_scene.py:738-751``): one dense
+    ``TracedPaths`` per chunk of candidates; the candidates of every chunk are decoded on the device."""
+    _, chunks = _candidate_chunks(mesh, tx_vertices, rx_vertices, order, chunk_size, solver, num_rays, accel)
+    for _, cand in chunks:
+        yield trace_path_candidates(mesh, tx_vertices, rx_vertices, cand, **kwargs)
+
+
+def trace_valid_paths(mesh: Mesh, tx_vertices, rx_vertices, order: int, *, chunk_size: int = 1 << 16,
+                      solver: str = "exhaustive", num_rays: int = 1_000_000, accel: str = "brute",
+                      **kwargs):
+    """Every valid path of ``order`` — what ``Scene.trace_paths(order).masked()`` returns — without
+    ever holding more than one chunk of the dense arrays: chunks are traced and compacted on the
+    device and the survivors merged back into the reference's row-major ``(tx, rx, candidate)`` order.
+    Returns a :class:`differt_b200.distributed.ValidPaths`."""
+    from .distributed import GatherRecord, ValidPaths, fill_record, gather_valid_paths
+
+    total, chunks = _candidate_chunks(mesh, tx_vertices, rx_vertices, order, chunk_size, solver, num_rays, accel)
+    idx, verts, objs = [], [], []
+    for start, cand in chunks:
+        paths = trace_path_candidates(mesh, tx_vertices, rx_vertices, cand, **kwargs)
+        capacity = 1 << 12
+        while True:
+            record = GatherRecord(capacity, paths.order, paths.vertices.device)
+            fill_record(record, paths, total, start)
+            count, index, v, o = record.fields()
+            n = int(count.item())
+            if n <= capacity:
+                break
+            capacity = n
+        idx.append(index[:n].clone()), verts.append(v[:n].clone()), objs.append(o[:n].clone())
+    dev = mesh.vertices.device
+    if not idx:
+        return ValidPaths(torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros((0, order + 2, 3), device=dev),
+                          torch.zeros((0, order + 2), dtype=torch.int32, device=dev), [0])
+    index, vertices, objects = torch.cat(idx), torch.cat(verts), torch.cat(objs)
+    perm = torch.argsort(index, stable=True)
+    return ValidPaths(index[perm], vertices[perm], objects[perm], [int(index.numel())])
 
 
 def trace_paths(mesh: Mesh, tx_vertices, rx_vertices, order: int, *, solver: str = "exhaustive",

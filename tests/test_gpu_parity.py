@@ -1030,3 +1030,22 @@ def test_exact_zero_and_tie_cases_on_a_lattice_scene(drt, rng):
             got = drt.trace_path_candidates(m, tx, rx, cand, dense_blockage=dense)
             np.testing.assert_array_equal(got.mask.cpu().numpy(), em)
             np.testing.assert_array_equal(bits(got.vertices.cpu().numpy()), bits(ev))
+
+
+@pytest.mark.parametrize("solver", ["exhaustive", "hybrid"])
+def test_chunked_trace_equals_one_shot_masked(drt, two_buildings, kats, solver):
+    """Scene.trace_paths(chunk_size=...) semantics (_scene.py:738-751) and the merged valid paths:
+    identical to tracing every candidate at once and calling masked()."""
+    v, t = two_buildings
+    g = kats["two_buildings_scene"]
+    mesh = drt.Mesh.from_numpy(v, t)
+    tx = np.array([g["tx"], [1.0, 3.0, 20.0]], np.float32)
+    rx = np.array([g["rx"], [0.5, 9.0, 1.5], [-2.0, 12.0, 2.0]], np.float32)
+    kw = dict(solver=solver, num_rays=50_000)
+    one = drt.trace_paths(mesh, tx, rx, 2, **kw).masked()
+    valid = drt.trace_valid_paths(mesh, tx, rx, 2, chunk_size=37, **kw)
+    assert one.vertices.shape[0] > 0
+    assert torch.equal(valid.vertices, one.vertices) and torch.equal(valid.objects, one.objects)
+    chunks = list(drt.trace_paths_chunks_iter(mesh, tx, rx, 2, chunk_size=100, **kw))
+    assert sum(int(c.mask.sum()) for c in chunks) == one.vertices.shape[0]
+    assert all(c.mask.shape[:2] == (2, 3) and c.mask.shape[2] <= 100 for c in chunks)

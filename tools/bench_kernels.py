@@ -184,6 +184,21 @@ def main() -> None:
     row("K6b trace VJP of vertices.sum() wrt tx, rx, mesh.vertices [16.8 M paths]", ms, P, "candidate_pairs", 12 * (k + 2) * P,
         "reads the cotangent; float atomics into 3 small gradient arrays")
 
+    # ---- BASELINE config 2 end to end: exhaustive order 2 on the street canyon, chunked --------------------
+    cv, ct = scenes.street_canyon(41)
+    cmesh = drt.Mesh.from_numpy(cv, ct)
+    clo, chi = cv.min(0), cv.max(0)
+    ctx = torch.tensor([[0.5 * (clo[0] + chi[0]), 0.0, 1.2 * chi[2]]], device=dev)
+    crx = torch.from_numpy(scenes.receivers_grid(cv, 16, 16)).to(dev)
+    ncand = scenes.num_complete_graph_candidates(ct.shape[0], 2)
+    res = {}
+
+    def cfg2():
+        res["v"] = drt.trace_valid_paths(cmesh, ctx, crx, 2, chunk_size=1 << 16)
+    ms = timed(cfg2, warmup=1, iters=3)
+    row(f"config 2: exhaustive order 2, 986 tri, 1 x 256 RX, {ncand} candidates in 65 536-chunks → valid paths",
+        ms, ncand * 256, "candidate_pairs", None, f"{res['v'].num_valid_paths} valid paths; default (pruned) mode, candidates decoded on the device")
+
     # ---- N1 candidate generators ------------------------------------------------------------------------
     ms = timed(lambda: drt.generate_all_path_candidates(T, 2, start=0, count=1 << 24))
     row("N1 complete-graph candidates [2^24 x order 2 of 10 094 nodes]", ms, 1 << 24, "candidates", 8 * (1 << 24))
