@@ -173,7 +173,17 @@ __global__ void fill_first_miss_kernel(int64_t R, int32_t *idx, float *t) {
     }
 }
 
-constexpr int kRPW = 4;
+// Rays per warp: 4 amortises each triangle load over four tests and gives four independent chains,
+// but a small batch then yields too few warps to fill 148 SMs — fewer rays per warp below ~2^17 rays
+// (the reference's own benchmark harness launches 10 000).
+inline int rays_per_warp(int64_t R) { return R >= (int64_t(1) << 17) ? 4 : (R >= (int64_t(1) << 15) ? 2 : 1); }
+
+#define DRT_DISPATCH_RPW(R, ...)                                \
+    switch (rays_per_warp(R)) {                                  \
+        case 4: { constexpr int RPW = 4; __VA_ARGS__ } break;    \
+        case 2: { constexpr int RPW = 2; __VA_ARGS__ } break;    \
+        default: { constexpr int RPW = 1; __VA_ARGS__ } break;   \
+    }
 
 }  // namespace drt
 
@@ -280,16 +290,18 @@ int drt_ray_intersect_any_triangle(drt_stream_t stream, int64_t R, const float *
     CoreParams p{};
     p.pack = static_cast<const Tri48 *>(pack);
     p.num_tiles = int(padded_triangles(T) / kTile);
-    p.num_units = (R + kRPW - 1) / kRPW;
     p.num_units_dev = nullptr;
     p.eps = epsilon;
     p.thr = 1.0f - hit_tol;
     p.batch_size = 0;
     p.num_triangles = T;
     p.tests_done = tests_done;
-    FlatRays<kRPW> src{o, d, R};
-    AnySink<kRPW> sink{out};
-    DRT_CHECK_CUDA((launch_intersect<kRPW, MODE_ANY, false>(s, p, src, sink, p.num_units)));
+    DRT_DISPATCH_RPW(R, {
+        p.num_units = (R + RPW - 1) / RPW;
+        FlatRays<RPW> src{o, d, R};
+        AnySink<RPW> sink{out};
+        DRT_CHECK_CUDA((launch_intersect<RPW, MODE_ANY, false>(s, p, src, sink, p.num_units)));
+    })
     return DRT_OK;
 }
 
@@ -309,15 +321,17 @@ int drt_first_triangle_hit_by_ray(drt_stream_t stream, int64_t R, const float *o
     CoreParams p{};
     p.pack = static_cast<const Tri48 *>(pack);
     p.num_tiles = int(padded_triangles(T) / kTile);
-    p.num_units = (R + kRPW - 1) / kRPW;
     p.eps = epsilon;
     p.thr = 0.f;
     p.batch_size = batch_size;
     p.num_triangles = T;
     p.tests_done = tests_done;
-    FlatRays<kRPW> src{o, d, R};
-    FirstSink<kRPW> sink{out_index, out_t};
-    DRT_CHECK_CUDA((launch_intersect<kRPW, MODE_FIRST, false>(s, p, src, sink, p.num_units)));
+    DRT_DISPATCH_RPW(R, {
+        p.num_units = (R + RPW - 1) / RPW;
+        FlatRays<RPW> src{o, d, R};
+        FirstSink<RPW> sink{out_index, out_t};
+        DRT_CHECK_CUDA((launch_intersect<RPW, MODE_FIRST, false>(s, p, src, sink, p.num_units)));
+    })
     return DRT_OK;
 }
 
@@ -335,14 +349,16 @@ int drt_triangles_visible_from_vertex(drt_stream_t stream, int64_t B, int64_t n_
     CoreParams p{};
     p.pack = static_cast<const Tri48 *>(pack);
     p.num_tiles = int(padded_triangles(T) / kTile);
-    p.num_units = (R + kRPW - 1) / kRPW;
     p.eps = epsilon;
     p.batch_size = 0;  // the reference calls first-hit with batch_size=None here (_utils.py:1717)
     p.num_triangles = T;
     p.tests_done = tests_done;
-    VertexRays<kRPW> src{vertices, dirs, R, n_rays};
-    VisibleSink<kRPW> sink{out, n_rays, T};
-    DRT_CHECK_CUDA((launch_intersect<kRPW, MODE_FIRST, false>(s, p, src, sink, p.num_units)));
+    DRT_DISPATCH_RPW(R, {
+        p.num_units = (R + RPW - 1) / RPW;
+        VertexRays<RPW> src{vertices, dirs, R, n_rays};
+        VisibleSink<RPW> sink{out, n_rays, T};
+        DRT_CHECK_CUDA((launch_intersect<RPW, MODE_FIRST, false>(s, p, src, sink, p.num_units)));
+    })
     return DRT_OK;
 }
 
