@@ -424,9 +424,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                     "executed_tests_per_s": tests_e2e / (ms_e2e * 1e-3), "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                     "valid_paths_gathered": num_valid_global},
-            # pack, area keys + gather, stage A, head pass, ring pass, 3 compaction kernels per step
-            # (+ 4 CUB radix-sort kernels, not counted as ours)
-            "gpu_launches": args.steps * 9,
+            # per step: pack, area keys + gather, stage A, hit-count + iota + gather (ordering pass),
+            # head pass, ring pass, 3 compaction kernels (+ 8 CUB radix-sort kernels, not counted as ours)
+            "gpu_launches": args.steps * 12,
             "clocks": clocks, "roofline": roofline,
         }
         if world == 1 and not args.no_cpu:
