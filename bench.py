@@ -7,7 +7,8 @@
 A *step* is one pass of the hot path over one batch of synthetic input: trace-and-validate
 (`_trace_path_candidates`, reference differt/src/differt/geometry/_solvers.py:499-770) of every
 (tx, rx, candidate) of the workload, with the blockage test evaluated for every candidate like the
-reference does ("dense"), followed by the compaction of the valid paths (`TracedPaths.masked()`)
+reference does ("dense"), the reverse mode of `vertices.sum()` w.r.t. tx, rx and the mesh vertices
+(BASELINE config 3 is "with VJP"), followed by the compaction of the valid paths (`TracedPaths.masked()`)
 and — for N > 1, where every rank traces its own shard of the candidates — ONE all-gather of the
 survivors.  The metric is BASELINE.json's: ray–triangle tests per second, counted as SURVEY.md
 §8(d) defines it — every (ray, triangle) pair the step DECIDES, rays x triangles ("algorithmic",
@@ -276,10 +277,21 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     record = GatherRecord(capacity, k, dev)
     stats_acc = torch.zeros(4, dtype=torch.int64, device=dev)
 
+    # reverse mode every step (BASELINE config 3 is "with VJP"; SURVEY §8d: VJP of vertices.sum() w.r.t.
+    # tx, rx and mesh.vertices): an all-ones cotangent, resident like the other inputs
+    with_vjp = not args.no_vjp
+    if with_vjp:
+        mesh = drt.Mesh(mesh.vertices.requires_grad_(True), mesh.triangles)
+        tx_d.requires_grad_(True)
+        rx_d.requires_grad_(True)
+        cot = torch.ones((tx_d.shape[0], rx_d.shape[0], cand_d.shape[0], k + 2, 3), dtype=torch.float32, device=dev)
+
     def step_resident(profile: bool):
         paths = drt.trace_path_candidates(
             mesh, tx_d, rx_d, cand_d, dense_blockage=True, _stats_accumulate=stats_acc, _profile=profile
         )
+        if with_vjp:
+            torch.autograd.grad(paths.vertices, (mesh.vertices, tx_d, rx_d), cot)
         fill_record(record, paths, wl["cand_global"], wl["cand_start"])
         if world > 1:
             gathered = torch.empty(world * record.nbytes, dtype=torch.uint8, device=dev)
@@ -288,14 +300,20 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
 
     def step_e2e():
         """Host buffers in, host results out, through the public API."""
-        m = drt.Mesh(host["vertices"].to(dev, non_blocking=True), host["triangles"].to(dev, non_blocking=True))
+        m = drt.Mesh(host["vertices"].to(dev, non_blocking=True).requires_grad_(with_vjp),
+                     host["triangles"].to(dev, non_blocking=True))
+        tx_e = host["tx"].to(dev, non_blocking=True).requires_grad_(with_vjp)
+        rx_e = host["rx"].to(dev, non_blocking=True).requires_grad_(with_vjp)
         paths = drt.trace_path_candidates(
-            m, host["tx"], host["rx"], host["cand"], dense_blockage=True, _stats_accumulate=stats_acc
+            m, tx_e, rx_e, host["cand"], dense_blockage=True, _stats_accumulate=stats_acc
         )
+        grads = ()
+        if with_vjp:
+            grads = tuple(g.cpu() for g in torch.autograd.grad(paths.vertices, (m.vertices, tx_e, rx_e), cot))
         fill_record(record, paths, wl["cand_global"], wl["cand_start"])
         valid = gather_valid_paths(record)  # all-gather (N>1) + counts to host
         mask_h = paths.mask.cpu()
-        out = (valid.index.cpu(), valid.vertices.cpu(), valid.objects.cpu(), mask_h)
+        out = (valid.index.cpu(), valid.vertices.cpu(), valid.objects.cpu(), mask_h, *grads)
         return out
 
     def barrier():
@@ -407,7 +425,11 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             "metric": METRIC, "value": algo_step * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(wl, world),
+            "data": "synthetic",
+            "config": workload_config(
+                wl, world,
+                reverse_mode=("every step also runs the VJP of vertices.sum() w.r.t. tx, rx and mesh.vertices "
+                              "(all-ones cotangent, 1 ms); not counted in value's tests") if with_vjp else "off"),
             "candidate_pairs_per_s": world * wl["tx"].shape[0] * wl["rx"].shape[0] * wl["cand"].shape[0]
             * args.steps / (ms * 1e-3),
             "valid_paths_per_s": valid_total * args.steps / (ms * 1e-3),
@@ -426,7 +448,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                     "valid_paths_gathered": num_valid_global},
             # per step: pack, area keys + gather, stage A, hit-count + iota + gather (ordering pass),
             # head pass, ring pass, 3 compaction kernels (+ 8 CUB radix-sort kernels, not counted as ours)
-            "gpu_launches": args.steps * 12,
+            "gpu_launches": args.steps * (12 + (1 if with_vjp else 0)),
             "clocks": clocks, "roofline": roofline,
         }
         if world == 1 and not args.no_cpu:
@@ -473,6 +495,7 @@ def main() -> None:
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per bounded sample")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-vjp", action="store_true", help="forward only (default: forward + VJP every step)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
