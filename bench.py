@@ -298,6 +298,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             dist.all_gather_into_tensor(gathered, record.buffer)
         return paths
 
+    mask_host = torch.empty((tx_d.shape[0], rx_d.shape[0], cand_d.shape[0]), dtype=torch.bool, pin_memory=True)
+    grad_host: list = []
+
     def step_e2e():
         """Host buffers in, host results out, through the public API."""
         m = drt.Mesh(host["vertices"].to(dev, non_blocking=True).requires_grad_(with_vjp),
@@ -309,11 +312,20 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         )
         grads = ()
         if with_vjp:
-            grads = tuple(g.cpu() for g in torch.autograd.grad(paths.vertices, (m.vertices, tx_e, rx_e), cot))
+            grads = torch.autograd.grad(paths.vertices, (m.vertices, tx_e, rx_e), cot)
         fill_record(record, paths, wl["cand_global"], wl["cand_start"])
+        # device → host: the mask and the gradients into pinned buffers (asynchronous), then the gather,
+        # whose count read is the synchronisation point
+        mask_host.copy_(paths.mask, non_blocking=True)
+        grads_h = []
+        for i, g in enumerate(grads):
+            if i >= len(grad_host):
+                grad_host.append(torch.empty(g.shape, dtype=g.dtype, pin_memory=True))
+            grad_host[i].copy_(g, non_blocking=True)
+            grads_h.append(grad_host[i])
         valid = gather_valid_paths(record)  # all-gather (N>1) + counts to host
-        mask_h = paths.mask.cpu()
-        out = (valid.index.cpu(), valid.vertices.cpu(), valid.objects.cpu(), mask_h, *grads)
+        out = (valid.index.cpu(), valid.vertices.cpu(), valid.objects.cpu(), mask_host, *grads_h)
+        torch.cuda.current_stream().synchronize()
         return out
 
     def barrier():
@@ -322,6 +334,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         torch.cuda.synchronize()
 
     # ---- kernel-level leg: inputs resident in HBM ------------------------------------------------
+    for _ in range(2):  # set-up: let the caching allocator reach its steady state before the W warm-ups
+        step_resident(False)
     for _ in range(args.warmup):
         step_resident(False)
     barrier()

@@ -196,6 +196,9 @@ struct PathSink {
 // (32 at a time per warp) for the ring pass over the remaining tiles.
 // ------------------------------------------------------------------------------------------------
 
+#ifndef DRT_CASCADE
+#define DRT_CASCADE 1
+#endif
 #ifndef DRT_PATH_HEAD_TILES
 #define DRT_PATH_HEAD_TILES 8
 #endif
@@ -710,7 +713,7 @@ __global__ void complete_graph_candidates_kernel(int64_t n, int order, int64_t s
 }
 
 struct TraceWorkspace {
-    size_t pack_geom, pack_active, pack_sorted, pack_sorted2, hit_counts, sort_ws, sort_bytes, list, list2, counters, total;
+    size_t pack_geom, pack_active, pack_sorted, pack_sorted2, hit_counts, sort_ws, sort_bytes, list, list2, list3, counters, total;
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -736,7 +739,9 @@ inline TraceWorkspace trace_workspace_layout(int64_t T, int64_t P) {
     off += 256;
     w.list = off;  // candidates that reach the blockage test (stage A → head pass)
     off += align256(size_t(P > 0 ? P : 1) * sizeof(uint32_t));
-    w.list2 = off;  // candidates that survive the head pass (head pass → ring pass)
+    w.list2 = off;  // candidates that survive a blockage pass (ping-pong with list3)
+    off += align256(size_t(P > 0 ? P : 1) * sizeof(uint32_t));
+    w.list3 = off;
     off += align256(size_t(P > 0 ? P : 1) * sizeof(uint32_t));
     w.total = off;
     return w;
@@ -761,7 +766,8 @@ static thread_local ProfileRing g_profile;
 template <int K>
 int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, bool profile,
                  const Tri48 *pack_active, float hit_tol, int64_t *tests_done,
-                 int64_t *units_scratch, uint32_t *list2, int64_t *list2_count, uint32_t *hit_counts,
+                 int64_t *units_scratch, uint32_t *list2, uint32_t *list3, int64_t *list2_count,
+                 uint32_t *hit_counts,
                  Tri48 *pack_sorted2, void *sort_ws, size_t sort_bytes) {
     // candidates along x, receiver chunks along y (enough of them to fill the GPU), transmitters along z
     const int threads = 128;
@@ -833,10 +839,37 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int64_t hblocks = (a.P + kPathHeadWarps - 1) / kPathHeadWarps;
         const int64_t hres = int64_t(sms) * DRT_PATH_HEAD_CTAS;
+#if DRT_CASCADE
+        // cascade of resident passes: tiles [0,8) for everyone, [8,16) for the survivors, ... — every
+        // pass barrier-free, survivor lists ping-pong between list2 and list3
+        (void)NH;
+        const uint32_t *in_list = list;
+        const int64_t *in_count = dense ? nullptr : a.list_count;
+        uint32_t *out_list = list2;
+        int64_t *out_count = list2_count;  // counters[2]; counters[3] is list3's
+        e = cudaSuccess;
+        for (int t0 = 0; t0 < NT && e == cudaSuccess; t0 += kPathHead) {
+            const int nh = NT - t0 < kPathHead ? NT - t0 : kPathHead;
+            hk<<<unsigned(hblocks < hres ? hblocks : hres), kPathHeadWarps * 32, kPathHeadSmem, s>>>(
+                pack_active + size_t(t0) * kTile, nh, a.P, in_count, a.out_vertices, in_list, a.eps, p.thr,
+                a.out_mask, out_list, out_count, tests_done);
+            e = cudaGetLastError();
+            if (t0 == 0 && e == cudaSuccess)  // stats[2]: survivors of the first pass
+                e = cudaMemcpyAsync(list2_count + 3, list2_count, sizeof(int64_t), cudaMemcpyDeviceToDevice, s);
+            in_list = out_list;
+            in_count = out_count;
+            const bool to3 = out_list == list2;
+            out_list = to3 ? list3 : list2;
+            out_count = to3 ? list2_count + 1 : list2_count;
+            if (e == cudaSuccess && t0 + kPathHead < NT) e = cudaMemsetAsync(out_count, 0, sizeof(int64_t), s);
+        }
+#else
         hk<<<unsigned(hblocks < hres ? hblocks : hres), kPathHeadWarps * 32, kPathHeadSmem, s>>>(
             pack_active, NH, a.P, dense ? nullptr : a.list_count, a.out_vertices, list, a.eps, p.thr,
             a.out_mask, list2, list2_count, tests_done);
         e = cudaGetLastError();
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(list2_count + 3, list2_count, sizeof(int64_t), cudaMemcpyDeviceToDevice, s);
         if (e == cudaSuccess && NT > NH) {
             // ring pass: the survivors against the remaining tiles
             p.pack = pack_active + size_t(NH) * kTile;
@@ -847,6 +880,7 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
             PathSink<NSEG> sink{a.out_mask, list2};
             e = launch_intersect<NSEG, MODE_ANY, true>(s, p, src, sink, a.P);
         }
+#endif
     } else {
         constexpr int RPW = 3;
         p.num_units = (a.P * NSEG + RPW - 1) / RPW;
@@ -937,11 +971,12 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
     int64_t *tests_done = stats;  // stats[0]
     int64_t *units_scratch = counters + 1;
     uint32_t *list2 = reinterpret_cast<uint32_t *>(ws + w.list2);
+    uint32_t *list3 = reinterpret_cast<uint32_t *>(ws + w.list3);
     const bool quads = assume_quads != 0;
 #define DRT_TRACE_CASE(K)                                                                         \
     case K:                                                                                       \
         rc = trace_launch<K>(s, a, quads, dense, profile, pack_active, hit_tol, tests_done,        \
-                             units_scratch, list2, counters + 2,                                  \
+                             units_scratch, list2, list3, counters + 2,                           \
                              reinterpret_cast<uint32_t *>(ws + w.hit_counts),                      \
                              reinterpret_cast<Tri48 *>(ws + w.pack_sorted2), ws + w.sort_ws,      \
                              w.sort_bytes);                                                       \
@@ -954,7 +989,7 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
     if (rc != DRT_OK) return rc;
     if (stats != nullptr) {
         if (cudaMemcpyAsync(stats + 1, counters, sizeof(int64_t), cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
-            cudaMemcpyAsync(stats + 2, counters + 2, sizeof(int64_t), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+            cudaMemcpyAsync(stats + 2, counters + 5, sizeof(int64_t), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
             return DRT_ERR_CUDA;
     }
     return DRT_OK;
