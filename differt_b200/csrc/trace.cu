@@ -156,49 +156,14 @@ trace_stage_a_kernel(const TraceArgs a, const int64_t rx_per_chunk) {
     }
 }
 
-// Stage-B sources: the k+1 segments of candidate `p` read back from the dense vertices output.
-template <int NSEG>
-struct PathRays {
-    const float *vertices;  // [P, NSEG+1, 3]
-    const uint32_t *list;   // nullable → unit == path index
-    __device__ __forceinline__ int64_t path_of(int64_t unit) const {
-        return list != nullptr ? int64_t(list[unit]) : unit;
-    }
-    __device__ __forceinline__ uint32_t load(int64_t unit, float3 (&o)[NSEG], float3 (&d)[NSEG]) const {
-        const float *v = vertices + path_of(unit) * (NSEG + 1) * 3;
-        float3 prev = ld3(v);
-#pragma unroll
-        for (int s = 0; s < NSEG; ++s) {
-            const float3 next = ld3(v + 3 * (s + 1));
-            o[s] = prev;
-            d[s] = sub3(next, prev);  // jnp.diff (_solvers.py:593)
-            prev = next;
-        }
-        return (1u << NSEG) - 1u;
-    }
-};
-
-template <int NSEG>
-struct PathSink {
-    uint8_t *mask;
-    const uint32_t *list;
-    __device__ __forceinline__ void any(int64_t unit, uint32_t hit, uint32_t) const {
-        if (hit) mask[list != nullptr ? int64_t(list[unit]) : unit] = 0;
-    }
-    __device__ __forceinline__ void first(int64_t, int, int32_t, float) const {}
-};
-
 // ------------------------------------------------------------------------------------------------
-// Blockage, head pass: every candidate against the first tiles of the area-sorted pack, which stay
-// resident in shared memory.  No ring, no CTA barrier after the initial load: warps run free, one
-// candidate at a time, with the next candidate's vertices prefetched (one float per lane) while the
-// current one is tested.  A hit retires the candidate (mask = 0); survivors are appended to `out_list`
-// (32 at a time per warp) for the ring pass over the remaining tiles.
+// Blockage pass: a list of candidates against `num_head_tiles` consecutive tiles of the ordered pack,
+// which stay resident in shared memory.  No ring, no CTA barrier after the initial load: warps run
+// free, one candidate at a time, with the next candidate's vertices prefetched (one float per lane)
+// while the current one is tested.  A hit retires the candidate (mask = 0); survivors are appended to
+// `out_list` (32 at a time per warp) for the next pass of the cascade (tiles [8,16), [16,24), ...).
 // ------------------------------------------------------------------------------------------------
 
-#ifndef DRT_CASCADE
-#define DRT_CASCADE 1
-#endif
 #ifndef DRT_PATH_HEAD_TILES
 #define DRT_PATH_HEAD_TILES 8
 #endif
@@ -825,7 +790,6 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
         }
         // head pass: every candidate against the likeliest blockers, resident, barrier free
         const int NT = p.num_tiles;
-        const int NH = NT < kPathHead ? NT : kPathHead;
         auto hk = path_head_kernel<NSEG>;
         static bool configured = false;  // benign race: idempotent attribute set
         if (!configured) {
@@ -839,10 +803,8 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int64_t hblocks = (a.P + kPathHeadWarps - 1) / kPathHeadWarps;
         const int64_t hres = int64_t(sms) * DRT_PATH_HEAD_CTAS;
-#if DRT_CASCADE
         // cascade of resident passes: tiles [0,8) for everyone, [8,16) for the survivors, ... — every
         // pass barrier-free, survivor lists ping-pong between list2 and list3
-        (void)NH;
         const uint32_t *in_list = list;
         const int64_t *in_count = dense ? nullptr : a.list_count;
         uint32_t *out_list = list2;
@@ -863,24 +825,6 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
             out_count = to3 ? list2_count + 1 : list2_count;
             if (e == cudaSuccess && t0 + kPathHead < NT) e = cudaMemsetAsync(out_count, 0, sizeof(int64_t), s);
         }
-#else
-        hk<<<unsigned(hblocks < hres ? hblocks : hres), kPathHeadWarps * 32, kPathHeadSmem, s>>>(
-            pack_active, NH, a.P, dense ? nullptr : a.list_count, a.out_vertices, list, a.eps, p.thr,
-            a.out_mask, list2, list2_count, tests_done);
-        e = cudaGetLastError();
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(list2_count + 3, list2_count, sizeof(int64_t), cudaMemcpyDeviceToDevice, s);
-        if (e == cudaSuccess && NT > NH) {
-            // ring pass: the survivors against the remaining tiles
-            p.pack = pack_active + size_t(NH) * kTile;
-            p.num_tiles = NT - NH;
-            p.num_units = a.P;
-            p.num_units_dev = list2_count;
-            PathRays<NSEG> src{a.out_vertices, list2};
-            PathSink<NSEG> sink{a.out_mask, list2};
-            e = launch_intersect<NSEG, MODE_ANY, true>(s, p, src, sink, a.P);
-        }
-#endif
     } else {
         constexpr int RPW = 3;
         p.num_units = (a.P * NSEG + RPW - 1) / RPW;
