@@ -21,6 +21,7 @@ from .geometry import (
 )
 from .launch import LaunchedPaths, compute_tx_mlm, launch_paths, launch_rays
 from .mesh import Mesh, TracedPaths
+from .scene import Scene
 from .solvers import (
     VisiblePathCandidates,
     generate_all_path_candidates,
@@ -36,6 +37,7 @@ __version__ = "0.1.0"
 __all__ = [
     "LaunchedPaths",
     "Mesh",
+    "Scene",
     "compute_tx_mlm",
     "launch_paths",
     "launch_rays",

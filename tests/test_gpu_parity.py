@@ -1049,3 +1049,55 @@ def test_chunked_trace_equals_one_shot_masked(drt, two_buildings, kats, solver):
     chunks = list(drt.trace_paths_chunks_iter(mesh, tx, rx, 2, chunk_size=100, **kw))
     assert sum(int(c.mask.sum()) for c in chunks) == one.vertices.shape[0]
     assert all(c.mask.shape[:2] == (2, 3) and c.mask.shape[2] <= 100 for c in chunks)
+
+
+# ------------------------------------------------------------------------------------------------
+# Scene: the reference's caller-side signatures (test_scene.py:116-160, 334-364, 650-764 error cases)
+# ------------------------------------------------------------------------------------------------
+
+
+def test_scene_call_signatures_and_golden_paths(drt, kats, two_buildings):
+    v, t = two_buildings
+    g = kats["two_buildings_scene"]
+    mesh = drt.Mesh.from_numpy(v, t)
+    scene = drt.Scene(np.array(g["tx"], np.float32), np.array(g["rx"], np.float32), mesh)
+    assert scene.num_transmitters == 1 and scene.num_receivers == 1
+    for order in (0, 1, 2):
+        exp = g["orders"][str(order)]
+        got = scene.trace_paths(order)
+        assert tuple(got.mask.shape) == (scenes.num_complete_graph_candidates(t.shape[0], order),)
+        m = got.masked()
+        n_valid = int(m.vertices.shape[0])
+        exp_v = np.array(exp["vertices"], np.float32).reshape(n_valid, order, 3)
+        np.testing.assert_allclose(m.vertices[:, 1:-1].cpu().numpy(), exp_v, rtol=g["rtol"])
+        np.testing.assert_array_equal(m.objects.cpu().numpy(), np.array(exp["objects"]).reshape(n_valid, order + 2))
+    # explicit candidates == exhaustive (test_scene.py:334-364), quads round the indices down
+    cand = scenes.complete_graph_candidates(t.shape[0], 2)
+    a, b = scene.trace_paths(2), scene.trace_paths(path_candidates=cand)
+    assert torch.equal(a.mask, b.mask) and torch.equal(a.vertices, b.vertices)
+    q = scene.set_assume_quads()
+    bq = q.trace_paths(path_candidates=cand[:50] | 1)
+    assert bool((bq.objects[..., 1:-1] % 2 == 0).all())
+    # chunked iterator and hybrid
+    chunks = list(scene.trace_paths(2, chunk_size=100))
+    assert sum(int(c.mask.sum()) for c in chunks) == int(a.mask.sum()) and len(chunks) == 6
+    h = scene.trace_paths(1, solver="hybrid", num_rays=50_000)
+    assert torch.equal(h.masked().objects, scene.trace_paths(1).masked().objects)
+    # error behaviour of the reference (_scene.py:692-717)
+    with pytest.raises(ValueError, match="one of 'order' or `path_candidates`"):
+        scene.trace_paths()
+    with pytest.raises(ValueError, match="one of 'order' or `path_candidates`"):
+        scene.trace_paths(1, path_candidates=cand)
+    with pytest.raises(ValueError, match="Unknown solver"):
+        scene.trace_paths(1, solver="nope")
+    with pytest.raises(ValueError, match="required when using HybridPathTracer"):
+        scene.trace_paths(path_candidates=cand, solver="hybrid")
+    # batched transmitters / receivers, grids, SBR and MLM entry points
+    grid = scene.with_receivers_grid(3, 2).with_transmitters_grid(2, 1, height=30.0)
+    assert tuple(grid.receivers.shape) == (2, 3, 3) and tuple(grid.transmitters.shape) == (1, 2, 3)
+    p = grid.trace_paths(1)
+    assert tuple(p.mask.shape) == (1, 2, 2, 3, t.shape[0]) and tuple(p.vertices.shape[-2:]) == (3, 3)
+    lp = grid.launch_paths(1, num_rays=2000, max_dist=1.0)
+    assert tuple(lp.masks.shape) == (2, 6, 2000, 2)
+    mlm = grid.compute_tx_mlm(1, 4, 5, num_rays=5000)
+    assert tuple(mlm.shape) == (1, 2, 4, 5) and int((mlm != 0).sum()) > 0  # cells hold ORs of path hashes
