@@ -11,7 +11,8 @@ LIB = HERE / "liboracle.so"
 
 # -ffp-contract=off: never fuse a*b+c (the oracle's contract); no -ffast-math, no -march=native
 # (the library is built in the CPU container and travels to the GPU box).
-CFLAGS = ["-O3", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-Wall"]
+CFLAGS = ["-O3", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-Wall",
+          "-Wno-maybe-uninitialized"]
 
 
 def build_oracle(force: bool = False) -> Path:

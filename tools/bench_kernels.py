@@ -199,6 +199,20 @@ def main() -> None:
     row(f"config 2: exhaustive order 2, 986 tri, 1 x 256 RX, {ncand} candidates in 65 536-chunks → valid paths",
         ms, ncand * 256, "candidate_pairs", None, f"{res['v'].num_valid_paths} valid paths; default (pruned) mode, candidates decoded on the device")
 
+    # the reference's city-scale notebook scene: ALL 2.02e8 order-2 candidates of bruxelles.obj, 1 TX, 1 RX
+    # (docs/source/notebooks/ray_tracing_at_city_scale.ipynb cell 3: "You probably don't want to try
+    #  order > 1 (too slow if testing all paths)")
+    bc = bx["vertices"].mean(0)
+    btx = torch.tensor([[bc[0], bc[1], float(bx["vertices"][:, 2].max()) + 10.0]], device=dev)
+    brx = torch.tensor([[bc[0] + 60.0, bc[1] - 40.0, 1.5]], device=dev)
+    nb = scenes.num_complete_graph_candidates(14_206, 2)
+
+    def city():
+        res["c"] = drt.trace_valid_paths(bmesh, btx, brx, 2, chunk_size=1 << 23)
+    ms = timed(city, warmup=1, iters=3)
+    row(f"city scale: exhaustive order 2 on bruxelles.obj (14 206 tri), 1 TX x 1 RX, {nb} candidates → valid paths",
+        ms, nb, "candidate_pairs", None, f"{res['c'].num_valid_paths} valid paths; the reference's notebook calls this too slow to try")
+
     # ---- N1 candidate generators ------------------------------------------------------------------------
     ms = timed(lambda: drt.generate_all_path_candidates(T, 2, start=0, count=1 << 24))
     row("N1 complete-graph candidates [2^24 x order 2 of 10 094 nodes]", ms, 1 << 24, "candidates", 8 * (1 << 24))
