@@ -29,6 +29,7 @@ from .solvers import (
     trace_path_candidates,
     trace_paths,
     trace_paths_chunks_iter,
+    trace_valid_path_candidates,
     trace_valid_paths,
 )
 
@@ -60,6 +61,7 @@ __all__ = [
     "trace_path_candidates",
     "trace_paths",
     "trace_paths_chunks_iter",
+    "trace_valid_path_candidates",
     "trace_valid_paths",
     "triangles_visible_from_vertex",
     "viewing_frustum",

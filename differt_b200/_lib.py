@@ -52,6 +52,11 @@ PROTOTYPES: dict[str, tuple] = {
         C.c_int,
         [ptr, i64, i64, ptr, ptr, ptr, i32, i64, ptr, i64, ptr, i64, i32, ptr, f32, f32, f32, u32,
          ptr, size_t, ptr, ptr, ptr, ptr]),
+    "drt_trace_valid_workspace_bytes": (size_t, [i64, i64]),
+    "drt_trace_valid_path_candidates": (
+        C.c_int,
+        [ptr, i64, i64, ptr, ptr, ptr, i32, i64, ptr, i64, ptr, i64, i32, ptr, f32, f32, f32, i64, ptr, size_t,
+         ptr, ptr, ptr, ptr, ptr]),
     "drt_trace_path_candidates_vjp": (
         C.c_int, [ptr, i64, i64, ptr, ptr, i64, ptr, i64, ptr, i64, i32, ptr, ptr, ptr, ptr, ptr]),
     "drt_profile_reset": (C.c_int, []),

@@ -28,6 +28,10 @@ struct TraceArgs {
     uint8_t *out_mask;
     uint32_t *list;           // nullable (dense blockage): indices of candidates to test
     int64_t *list_count;
+    // compact mode (drt_trace_valid_path_candidates): no dense outputs; candidates that pass the cheap
+    // tests are appended to out_vertices / out_objects / out_mask / compact_index [capacity]
+    int64_t capacity;
+    int64_t *compact_index;
 };
 
 // Candidate-major decomposition: thread = (candidate c, transmitter, chunk of receivers).  The
@@ -36,7 +40,7 @@ struct TraceArgs {
 // uncoalesced part of this stage (ncu: L1TEX-bound when done per path).  Lanes of a warp hold 32
 // consecutive candidates of the same receiver, i.e. 32 consecutive paths: their dense outputs are
 // staged in shared memory and leave as contiguous 16-byte stores.
-template <int K, bool QUADS>
+template <int K, bool QUADS, bool COMPACT>
 __global__ void __launch_bounds__(128)
 trace_stage_a_kernel(const TraceArgs a, const int64_t rx_per_chunk) {
     constexpr int KK = K > 0 ? K : 1;
@@ -55,6 +59,7 @@ trace_stage_a_kernel(const TraceArgs a, const int64_t rx_per_chunk) {
     const int64_t rx0 = int64_t(blockIdx.y) * rx_per_chunk;
     const int64_t rx1 = rx0 + rx_per_chunk < a.nrx ? rx0 + rx_per_chunk : a.nrx;
     const bool have = c < a.C;
+    const unsigned have_mask = __ballot_sync(kFull, have);
     const int n_warp = int((a.C - c0) < 32 ? (a.C - c0) : 32);
 
     float3 mv[KK], mn[KK];
@@ -110,17 +115,45 @@ trace_stage_a_kernel(const TraceArgs a, const int64_t rx_per_chunk) {
 #pragma unroll
             for (int i = 0; i < K + 2; ++i) finite = finite && finite3(full[i]);
 
-            float *sv = stage_v + lane * NV3;
-#pragma unroll
-            for (int i = 0; i < K + 2; ++i) st3(sv + 3 * i, finite ? full[i] : make_float3(0.f, 0.f, 0.f));
-            int32_t *so = stage_o + lane * (K + 2);
-            so[0] = int32_t(itx);
-#pragma unroll
-            for (int i = 0; i < K; ++i) so[i + 1] = ci[i];
-            so[K + 1] = int32_t(irx);
             prevalid = inside && same && !small && finite && active;
-            a.out_mask[p] = prevalid ? 1 : 0;
+            if (!COMPACT) {
+                float *sv = stage_v + lane * NV3;
+#pragma unroll
+                for (int i = 0; i < K + 2; ++i)
+                    st3(sv + 3 * i, finite ? full[i] : make_float3(0.f, 0.f, 0.f));
+                int32_t *so = stage_o + lane * (K + 2);
+                so[0] = int32_t(itx);
+#pragma unroll
+                for (int i = 0; i < K; ++i) so[i + 1] = ci[i];
+                so[K + 1] = int32_t(irx);
+                a.out_mask[p] = prevalid ? 1 : 0;
+            } else {
+                // the few candidates that pass go straight to their compact slot
+                const unsigned m = __ballot_sync(have_mask, prevalid);
+                if (prevalid) {
+                    const int leader = __ffs(m) - 1;
+                    int64_t start = 0;
+                    if (lane == leader)
+                        start = (int64_t)atomicAdd(reinterpret_cast<unsigned long long *>(a.list_count),
+                                                   (unsigned long long)__popc(m));
+                    start = __shfl_sync(m, start, leader);
+                    const int64_t slot = start + __popc(m & ((1u << lane) - 1u));
+                    if (slot < a.capacity) {
+                        float *ov = a.out_vertices + slot * NV3;
+#pragma unroll
+                        for (int i = 0; i < K + 2; ++i) st3(ov + 3 * i, full[i]);
+                        int32_t *oo = a.out_objects + slot * (K + 2);
+                        oo[0] = int32_t(itx);
+#pragma unroll
+                        for (int i = 0; i < K; ++i) oo[i + 1] = ci[i];
+                        oo[K + 1] = int32_t(irx);
+                        a.out_mask[slot] = 1;
+                        a.compact_index[slot] = p;
+                    }
+                }
+            }
         }
+        if (COMPACT) continue;
         __syncwarp();
         {
             float *gv = a.out_vertices + p0 * NV3;
@@ -383,6 +416,10 @@ struct SegSink {
     }
     __device__ __forceinline__ void first(int64_t, int, int32_t, float) const {}
 };
+
+__global__ void clamp_count_kernel(const int64_t *count, int64_t capacity, int64_t *clamped) {
+    *clamped = *count < capacity ? *count : capacity;
+}
 
 __global__ void seg_units_kernel(const int64_t *count, int nseg, int rpw, int64_t *units) {
     *units = (*count * nseg + rpw - 1) / rpw;
@@ -743,10 +780,18 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
     if (chunks > 65535) chunks = 65535;
     const int64_t rx_per_chunk = (a.nrx + chunks - 1) / chunks;
     const dim3 grid(unsigned(cblocks), unsigned((a.nrx + rx_per_chunk - 1) / rx_per_chunk), unsigned(a.ntx));
-    if (quads)
-        trace_stage_a_kernel<K, true><<<grid, threads, 0, s>>>(a, rx_per_chunk);
-    else
-        trace_stage_a_kernel<K, false><<<grid, threads, 0, s>>>(a, rx_per_chunk);
+    const bool compact = a.compact_index != nullptr;
+    if (compact) {
+        if (quads)
+            trace_stage_a_kernel<K, true, true><<<grid, threads, 0, s>>>(a, rx_per_chunk);
+        else
+            trace_stage_a_kernel<K, false, true><<<grid, threads, 0, s>>>(a, rx_per_chunk);
+    } else {
+        if (quads)
+            trace_stage_a_kernel<K, true, false><<<grid, threads, 0, s>>>(a, rx_per_chunk);
+        else
+            trace_stage_a_kernel<K, false, false><<<grid, threads, 0, s>>>(a, rx_per_chunk);
+    }
     if (cudaGetLastError() != cudaSuccess) return DRT_ERR_CUDA;
     if (a.T == 0) return DRT_OK;  // empty mesh: nothing can block (_mesh.py:3053-3057)
 
@@ -768,7 +813,7 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
     if constexpr (NSEG <= 6) {
         // ordering pass (dense batches only: a pruned work list is too short to pay for it)
         constexpr int64_t kSamples = 32768;
-        if (dense && a.P >= 8 * kSamples && p.eps >= 1.17549435e-38f) {
+        if (dense && !compact && a.P >= 8 * kSamples && p.eps >= 1.17549435e-38f) {
             int64_t stride = (a.P / kSamples) | 1;
             auto gcd = [](int64_t x, int64_t y) { while (y) { const int64_t r = x % y; x = y; y = r; } return x; };
             while (gcd(stride, a.C) != 1) stride += 2;  // walk across candidates AND receivers
@@ -801,19 +846,22 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int64_t hblocks = (a.P + kPathHeadWarps - 1) / kPathHeadWarps;
+        // compact mode: the units are the compact slots 0 .. min(count, capacity) - 1
+        const int64_t bound = compact ? a.capacity : a.P;
+        if (compact) clamp_count_kernel<<<1, 1, 0, s>>>(a.list_count, a.capacity, units_scratch);
+        const int64_t hblocks = (bound + kPathHeadWarps - 1) / kPathHeadWarps;
         const int64_t hres = int64_t(sms) * DRT_PATH_HEAD_CTAS;
         // cascade of resident passes: tiles [0,8) for everyone, [8,16) for the survivors, ... — every
         // pass barrier-free, survivor lists ping-pong between list2 and list3
-        const uint32_t *in_list = list;
-        const int64_t *in_count = dense ? nullptr : a.list_count;
+        const uint32_t *in_list = compact ? nullptr : list;
+        const int64_t *in_count = compact ? units_scratch : (dense ? nullptr : a.list_count);
         uint32_t *out_list = list2;
         int64_t *out_count = list2_count;  // counters[2]; counters[3] is list3's
         e = cudaSuccess;
         for (int t0 = 0; t0 < NT && e == cudaSuccess; t0 += kPathHead) {
             const int nh = NT - t0 < kPathHead ? NT - t0 : kPathHead;
             hk<<<unsigned(hblocks < hres ? hblocks : hres), kPathHeadWarps * 32, kPathHeadSmem, s>>>(
-                pack_active + size_t(t0) * kTile, nh, a.P, in_count, a.out_vertices, in_list, a.eps, p.thr,
+                pack_active + size_t(t0) * kTile, nh, bound, in_count, a.out_vertices, in_list, a.eps, p.thr,
                 a.out_mask, out_list, out_count, tests_done);
             e = cudaGetLastError();
             if (t0 == 0 && e == cudaSuccess)  // stats[2]: survivors of the first pass
@@ -826,6 +874,7 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
             if (e == cudaSuccess && t0 + kPathHead < NT) e = cudaMemsetAsync(out_count, 0, sizeof(int64_t), s);
         }
     } else {
+        if (compact) return DRT_ERR_UNSUPPORTED;  // compact mode is built for orders <= 5
         constexpr int RPW = 3;
         p.num_units = (a.P * NSEG + RPW - 1) / RPW;
         p.num_units_dev = nullptr;
@@ -937,6 +986,90 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
             return DRT_ERR_CUDA;
     }
     return DRT_OK;
+}
+
+size_t drt_trace_valid_workspace_bytes(int64_t T, int64_t capacity) {
+    if (T < 0 || capacity < 0) return 0;
+    return trace_workspace_layout(T, capacity).total;
+}
+
+int drt_trace_valid_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const float *vertices,
+                                    const int32_t *triangles, const uint8_t *triangle_mask,
+                                    int32_t assume_quads, int64_t ntx, const float *tx, int64_t nrx,
+                                    const float *rx, int64_t C, int32_t order, const int32_t *cand,
+                                    float epsilon, float hit_tol, float min_len, int64_t capacity,
+                                    void *workspace, size_t workspace_bytes, int64_t *out_count,
+                                    int64_t *out_index, float *out_vertices, int32_t *out_objects,
+                                    uint8_t *out_valid) {
+    if (V < 0 || T < 0 || ntx < 0 || nrx < 0 || C < 0 || order < 0 || capacity <= 0) return DRT_ERR_BAD_EXTENT;
+    if (order > 5) return DRT_ERR_UNSUPPORTED;
+    if (capacity >= (int64_t(1) << 32)) return DRT_ERR_BAD_EXTENT;
+    if (!out_count) return DRT_ERR_NULL_POINTER;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(out_count, 0, sizeof(int64_t), s) != cudaSuccess) return DRT_ERR_CUDA;
+    const int64_t P = ntx * nrx * C;
+    if (P == 0) return DRT_OK;
+    if (!tx || !rx || !out_vertices || !out_objects || !out_valid || !out_index || !workspace)
+        return DRT_ERR_NULL_POINTER;
+    if (order > 0 && cand == nullptr) return DRT_ERR_NULL_POINTER;
+    if (order > 0 && T < (assume_quads ? 2 : 1)) return DRT_ERR_BAD_EXTENT;
+    const TraceWorkspace w = trace_workspace_layout(T, capacity);
+    if (workspace_bytes < w.total) return DRT_ERR_WORKSPACE;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    Tri48 *pack_geom = reinterpret_cast<Tri48 *>(ws + w.pack_geom);
+    const Tri48 *pack_active = pack_geom;
+    int rc = drt_mesh_pack(stream, V, T, vertices, triangles, nullptr, pack_geom);
+    if (rc != DRT_OK) return rc;
+    if (triangle_mask != nullptr) {
+        Tri48 *pm = reinterpret_cast<Tri48 *>(ws + w.pack_active);
+        rc = drt_mesh_pack(stream, V, T, vertices, triangles, triangle_mask, pm);
+        if (rc != DRT_OK) return rc;
+        pack_active = pm;
+    }
+    if (T > 0) {
+        Tri48 *pack_sorted = reinterpret_cast<Tri48 *>(ws + w.pack_sorted);
+        rc = drt_mesh_pack_sort_by_area(stream, T, pack_active, ws + w.sort_ws, w.sort_bytes, pack_sorted);
+        if (rc != DRT_OK) return rc;
+        pack_active = pack_sorted;
+    }
+    int64_t *counters = reinterpret_cast<int64_t *>(ws + w.counters);
+    if (cudaMemsetAsync(counters, 0, 256, s) != cudaSuccess) return DRT_ERR_CUDA;
+    TraceArgs a{};
+    a.pack = pack_geom;
+    a.tri_mask = triangle_mask;
+    a.tx = tx;
+    a.rx = rx;
+    a.cand = cand;
+    a.T = T;
+    a.ntx = ntx;
+    a.nrx = nrx;
+    a.C = C;
+    a.P = P;
+    a.eps = epsilon;
+    a.min_len = min_len;
+    a.out_vertices = out_vertices;
+    a.out_objects = out_objects;
+    a.out_mask = out_valid;
+    a.list = nullptr;
+    a.list_count = out_count;
+    a.capacity = capacity;
+    a.compact_index = out_index;
+    const bool quads = assume_quads != 0;
+#define DRT_TRACE_CASE(K)                                                                               \
+    case K:                                                                                             \
+        rc = trace_launch<K>(s, a, quads, false, false, pack_active, hit_tol, nullptr, counters + 1,    \
+                             reinterpret_cast<uint32_t *>(ws + w.list2),                                 \
+                             reinterpret_cast<uint32_t *>(ws + w.list3), counters + 2,                   \
+                             reinterpret_cast<uint32_t *>(ws + w.hit_counts),                            \
+                             reinterpret_cast<Tri48 *>(ws + w.pack_sorted2), ws + w.sort_ws,            \
+                             w.sort_bytes);                                                             \
+        break;
+    switch (order) {
+        DRT_TRACE_CASE(0) DRT_TRACE_CASE(1) DRT_TRACE_CASE(2) DRT_TRACE_CASE(3) DRT_TRACE_CASE(4)
+        DRT_TRACE_CASE(5)
+    }
+#undef DRT_TRACE_CASE
+    return rc;
 }
 
 int drt_trace_path_candidates_vjp(drt_stream_t stream, int64_t V, int64_t T, const float *vertices,

@@ -24,6 +24,7 @@ __all__ = [
     "generate_all_path_candidates",
     "generate_all_path_candidates_chunks_iter",
     "trace_path_candidates",
+    "trace_valid_path_candidates",
     "trace_paths",
     "trace_paths_chunks_iter",
     "trace_valid_paths",
@@ -138,6 +139,58 @@ def trace_path_candidates(
         s = stats.cpu().tolist()
         paths.stats = {"tests_done": s[0], "candidates_blockage_tested": s[1], "head_pass_survivors": s[2]}
     return paths
+
+
+def trace_valid_path_candidates(
+    mesh: Mesh, tx_vertices, rx_vertices, path_candidates, *, epsilon=None, hit_tol=None, min_len=None,
+    capacity: int = 1 << 16, index_offset: tuple[int, int] | None = None,
+):
+    """Compact form of :func:`trace_path_candidates` for exhaustive searches
+    (``drt_trace_valid_path_candidates``): same validation, but only the valid paths are produced —
+    no dense ``[Ntx, Nrx, C, …]`` arrays.  Returns a :class:`differt_b200.distributed.ValidPaths` in
+    the reference's row-major ``masked()`` order.  ``index_offset = (num_global, start)`` maps the
+    indices of a chunk of candidates into the global candidate list."""
+    from .distributed import ValidPaths, global_path_index
+
+    pl = Placement()
+    dev = pl.device = mesh.vertices.device
+    tx = pl.put(tx_vertices, torch.float32).reshape(-1, 3).contiguous()
+    rx = pl.put(rx_vertices, torch.float32).reshape(-1, 3).contiguous()
+    cand = pl.put(path_candidates, torch.int32).contiguous()
+    if cand.ndim != 2:
+        raise TypeError("path_candidates must have shape [num_path_candidates, order]")
+    ntx, nrx, (C, k) = tx.shape[0], rx.shape[0], cand.shape
+    if k > 5:
+        raise NotImplementedError("the compact trace supports orders up to 5; use trace_path_candidates")
+    T = mesh.num_triangles
+    mask_u8 = mesh._mask_u8()
+    while True:
+        out_i = torch.empty(capacity, dtype=torch.int64, device=dev)
+        out_v = torch.empty((capacity, k + 2, 3), dtype=torch.float32, device=dev)
+        out_o = torch.empty((capacity, k + 2), dtype=torch.int32, device=dev)
+        out_ok = torch.empty(capacity, dtype=torch.uint8, device=dev)
+        count = torch.zeros(1, dtype=torch.int64, device=dev)
+        ws = torch.empty(max(lib.drt_trace_valid_workspace_bytes(T, capacity), 1), dtype=torch.uint8, device=dev)
+        check(
+            lib.drt_trace_valid_path_candidates(
+                stream_ptr(), mesh.vertices.shape[0], T, ptr(mesh.vertices.detach()), ptr(mesh.triangles),
+                ptr(mask_u8), int(mesh.assume_quads), ntx, ptr(tx), nrx, ptr(rx), C, k, ptr(cand),
+                10.0 * F32_EPS if epsilon is None else float(epsilon),
+                100.0 * F32_EPS if hit_tol is None else float(hit_tol),
+                10.0 * F32_EPS if min_len is None else float(min_len),
+                capacity, ptr(ws), ws.numel(), ptr(count), ptr(out_i), ptr(out_v), ptr(out_o), ptr(out_ok),
+            )
+        )
+        n = int(count.item())  # the one host read
+        if n <= capacity:
+            break
+        capacity = n
+    keep = out_ok[:n].view(torch.bool)
+    index = out_i[:n][keep]
+    if index_offset is not None:
+        index = global_path_index(index, C, index_offset[0], index_offset[1])
+    perm = torch.argsort(index, stable=True)  # slots are filled in no particular order
+    return ValidPaths(index[perm], out_v[:n][keep][perm], out_o[:n][keep][perm], [int(index.numel())])
 
 
 def generate_all_path_candidates(
@@ -268,18 +321,25 @@ def trace_paths_chunks_iter(mesh: Mesh, tx_vertices, rx_vertices, order: int, *,
         yield trace_path_candidates(mesh, tx_vertices, rx_vertices, cand, **kwargs)
 
 
-def trace_valid_paths(mesh: Mesh, tx_vertices, rx_vertices, order: int, *, chunk_size: int = 1 << 16,
+def trace_valid_paths(mesh: Mesh, tx_vertices, rx_vertices, order: int, *, chunk_size: int = 1 << 20,
                       solver: str = "exhaustive", num_rays: int = 1_000_000, accel: str = "brute",
                       **kwargs):
     """Every valid path of ``order`` — what ``Scene.trace_paths(order).masked()`` returns — without
-    ever holding more than one chunk of the dense arrays: chunks are traced and compacted on the
-    device and the survivors merged back into the reference's row-major ``(tx, rx, candidate)`` order.
+    the dense arrays: chunks of candidates are decoded, traced and validated on the device by the
+    compact kernel (``trace_valid_path_candidates``; the dense kernel + compaction for orders > 5) and
+    the survivors merged back into the reference's row-major ``(tx, rx, candidate)`` order.
+    ``num_tx * num_rx * chunk_size`` must stay below 2**32.
     Returns a :class:`differt_b200.distributed.ValidPaths`."""
     from .distributed import GatherRecord, ValidPaths, fill_record, gather_valid_paths
 
     total, chunks = _candidate_chunks(mesh, tx_vertices, rx_vertices, order, chunk_size, solver, num_rays, accel)
     idx, verts, objs = [], [], []
     for start, cand in chunks:
+        if order <= 5 and not kwargs.get("dense_blockage", False):
+            part = trace_valid_path_candidates(mesh, tx_vertices, rx_vertices, cand, index_offset=(total, start),
+                                               **{k: v for k, v in kwargs.items() if k in ("epsilon", "hit_tol", "min_len")})
+            idx.append(part.index), verts.append(part.vertices), objs.append(part.objects)
+            continue
         paths = trace_path_candidates(mesh, tx_vertices, rx_vertices, cand, **kwargs)
         capacity = 1 << 12
         while True:

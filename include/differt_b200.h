@@ -211,6 +211,23 @@ DRT_API int drt_trace_path_candidates(drt_stream_t stream, int64_t num_vertices,
                               void *workspace, size_t workspace_bytes, float *out_vertices,
                               int32_t *out_objects, uint8_t *out_mask,
                               int64_t *stats /*nullable*/);
+/* K6c compact form of K6 for exhaustive searches: no dense outputs.  Every candidate is traced and
+ *     validated like in drt_trace_path_candidates; the ones that pass the cheap tests are appended (in
+ *     no particular order) to out_index (flat (tx, rx, candidate) index) / out_vertices / out_objects
+ *     [capacity], then blockage-tested: out_valid[slot] = 1 iff the path is valid.  *out_count
+ *     (device) = candidates that passed the cheap tests; if it exceeds `capacity` the excess was
+ *     dropped and the caller retries with a larger capacity.  Orders 0..5.
+ *     workspace: drt_trace_valid_workspace_bytes(num_triangles, capacity). */
+DRT_API size_t drt_trace_valid_workspace_bytes(int64_t num_triangles, int64_t capacity);
+DRT_API int drt_trace_valid_path_candidates(drt_stream_t stream, int64_t num_vertices, int64_t num_triangles,
+                                    const float *vertices, const int32_t *triangles,
+                                    const uint8_t *triangle_mask /*nullable*/, int32_t assume_quads,
+                                    int64_t num_tx, const float *tx, int64_t num_rx, const float *rx,
+                                    int64_t num_candidates, int32_t order,
+                                    const int32_t *path_candidates, float epsilon, float hit_tol,
+                                    float min_len, int64_t capacity, void *workspace,
+                                    size_t workspace_bytes, int64_t *out_count, int64_t *out_index,
+                                    float *out_vertices, int32_t *out_objects, uint8_t *out_valid);
 DRT_API int drt_trace_path_candidates_vjp(drt_stream_t stream, int64_t num_vertices, int64_t num_triangles,
                                   const float *vertices, const int32_t *triangles,
                                   int64_t num_tx, const float *tx, int64_t num_rx, const float *rx,

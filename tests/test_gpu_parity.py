@@ -1101,3 +1101,26 @@ def test_scene_call_signatures_and_golden_paths(drt, kats, two_buildings):
     assert tuple(lp.masks.shape) == (2, 6, 2000, 2)
     mlm = grid.compute_tx_mlm(1, 4, 5, num_rays=5000)
     assert tuple(mlm.shape) == (1, 2, 4, 5) and int((mlm != 0).sum()) > 0  # cells hold ORs of path hashes
+
+
+@pytest.mark.parametrize("order", [0, 1, 2, 3, 5])
+@pytest.mark.parametrize("assume_quads,use_mask", [(False, False), (True, False), (False, True)])
+def test_compact_trace_equals_dense_masked(drt, rng, order, assume_quads, use_mask):
+    """drt_trace_valid_path_candidates (no dense outputs) returns exactly masked() of the dense trace,
+    including the capacity-overflow retry."""
+    v, t = scenes.street_canyon(4)
+    mask = (rng.uniform(size=t.shape[0]) < 0.8) if use_mask else None
+    if use_mask and assume_quads is False:
+        mask[-2:] = True  # keep the ground
+    mesh = drt.Mesh.from_numpy(v, t, mask=mask, assume_quads=assume_quads)
+    tx = np.array([[15.0, 0.0, 25.0], [5.0, 2.0, 12.0]], np.float32)
+    rx = np.array([[x, y, 1.5] for x in (2.0, 11.0, 19.0, 33.0) for y in (-6.0, 5.0)], np.float32)
+    n = mesh.num_primitives
+    cand = (scenes.complete_graph_candidates(n, order) if order <= 2 else scenes.sampled_candidates(n, order, 20000))
+    cand = cand * (2 if assume_quads else 1)
+    dense = drt.trace_path_candidates(mesh, tx, rx, cand).masked()
+    for capacity in (1 << 16, 3):
+        got = drt.trace_valid_path_candidates(mesh, tx, rx, cand, capacity=capacity)
+        assert torch.equal(got.vertices, dense.vertices) and torch.equal(got.objects, dense.objects)
+    if order in (1, 2):
+        assert dense.vertices.shape[0] > 0

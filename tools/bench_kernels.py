@@ -194,9 +194,9 @@ def main() -> None:
     res = {}
 
     def cfg2():
-        res["v"] = drt.trace_valid_paths(cmesh, ctx, crx, 2, chunk_size=1 << 16)
+        res["v"] = drt.trace_valid_paths(cmesh, ctx, crx, 2)  # one chunk: 971 210 x 256 < 2^32 paths
     ms = timed(cfg2, warmup=1, iters=3)
-    row(f"config 2: exhaustive order 2, 986 tri, 1 x 256 RX, {ncand} candidates in 65 536-chunks → valid paths",
+    row(f"config 2: exhaustive order 2, 986 tri, 1 x 256 RX, {ncand} candidates → valid paths (compact kernel)",
         ms, ncand * 256, "candidate_pairs", None, f"{res['v'].num_valid_paths} valid paths; default (pruned) mode, candidates decoded on the device")
 
     # the reference's city-scale notebook scene: ALL 2.02e8 order-2 candidates of bruxelles.obj, 1 TX, 1 RX
@@ -208,7 +208,7 @@ def main() -> None:
     nb = scenes.num_complete_graph_candidates(14_206, 2)
 
     def city():
-        res["c"] = drt.trace_valid_paths(bmesh, btx, brx, 2, chunk_size=1 << 23)
+        res["c"] = drt.trace_valid_paths(bmesh, btx, brx, 2, chunk_size=1 << 26)
     ms = timed(city, warmup=1, iters=3)
     row(f"city scale: exhaustive order 2 on bruxelles.obj (14 206 tri), 1 TX x 1 RX, {nb} candidates → valid paths",
         ms, nb, "candidate_pairs", None, f"{res['c'].num_valid_paths} valid paths; the reference's notebook calls this too slow to try")
