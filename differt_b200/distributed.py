@@ -22,6 +22,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = [
+    "trace_valid_paths_sharded",
     "GatherRecord",
     "ValidPaths",
     "gather_valid_paths",
@@ -182,3 +183,49 @@ def trace_path_candidates_sharded(
         if valid is not None:
             return paths, valid
         capacity *= 4
+
+
+def trace_valid_paths_sharded(mesh, tx_vertices, rx_vertices, order: int, *, group=None,
+                              chunk_size: int = 1 << 20, solver: str = "exhaustive", **kwargs) -> ValidPaths:
+    """Exhaustive (or hybrid) search of ``order`` sharded over the ranks: the candidate list is never
+    materialised anywhere — every rank decodes and traces its own contiguous range of candidate
+    indices with the compact kernel — and the valid paths of all ranks are exchanged with ONE
+    all-gather and merged into the reference's ``masked()`` order on every rank."""
+    from .solvers import _candidate_chunks, trace_valid_path_candidates
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    total, _ = _candidate_chunks(mesh, tx_vertices, rx_vertices, order, chunk_size, solver,
+                                 kwargs.pop("num_rays", 1_000_000), kwargs.pop("accel", "brute"))
+    start, stop = shard_bounds(total, world, rank)
+    dev = mesh.vertices.device
+    idx, verts, objs = [], [], []
+    if solver == "exhaustive":
+        from .solvers import generate_all_path_candidates
+
+        decode = lambda s0, n: generate_all_path_candidates(  # noqa: E731
+            mesh.num_primitives, order, assume_quads=mesh.assume_quads, start=s0, count=n, device=dev)
+    else:
+        from .solvers import generate_visible_path_candidates
+
+        vis = generate_visible_path_candidates(mesh, tx_vertices, rx_vertices, order)
+        decode = vis.chunk
+    for s0 in range(start, stop, chunk_size):
+        cand = decode(s0, min(chunk_size, stop - s0))
+        part = trace_valid_path_candidates(mesh, tx_vertices, rx_vertices, cand, index_offset=(total, s0), **kwargs)
+        idx.append(part.index), verts.append(part.vertices), objs.append(part.objects)
+    k2 = order + 2
+    index = torch.cat(idx) if idx else torch.zeros(0, dtype=torch.int64, device=dev)
+    vertices = torch.cat(verts) if verts else torch.zeros((0, k2, 3), device=dev)
+    objects = torch.cat(objs) if objs else torch.zeros((0, k2), dtype=torch.int32, device=dev)
+    capacity = max(int(index.numel()), 1)
+    if world > 1:  # agree on one record size: the largest local count
+        cap = torch.tensor([capacity], dtype=torch.int64, device=dev)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)
+        capacity = int(cap.item())
+    record = GatherRecord(capacity, order, dev)
+    count, r_index, r_vertices, r_objects = record.fields()
+    n = int(index.numel())
+    count[0] = n
+    r_index[:n], r_vertices[:n], r_objects[:n] = index, vertices, objects
+    return gather_valid_paths(record, group=group)

@@ -1124,3 +1124,17 @@ def test_compact_trace_equals_dense_masked(drt, rng, order, assume_quads, use_ma
         assert torch.equal(got.vertices, dense.vertices) and torch.equal(got.objects, dense.objects)
     if order in (1, 2):
         assert dense.vertices.shape[0] > 0
+
+
+def test_sharded_exhaustive_search_world_size_one(drt, two_buildings, kats):
+    from differt_b200.distributed import trace_valid_paths_sharded
+
+    v, t = two_buildings
+    g = kats["two_buildings_scene"]
+    mesh = drt.Mesh.from_numpy(v, t)
+    tx, rx = np.array([g["tx"]], np.float32), np.array([g["rx"], [0.5, 9.0, 1.5]], np.float32)
+    for order in (1, 2, 3):
+        got = trace_valid_paths_sharded(mesh, tx, rx, order, chunk_size=1000)
+        exp = drt.trace_paths(mesh, tx, rx, order).masked()
+        assert torch.equal(got.vertices, exp.vertices) and torch.equal(got.objects, exp.objects)
+        assert got.num_valid_paths >= 1
