@@ -91,3 +91,33 @@ def test_paths_are_sorted_and_respect_adjacency():  # graph.rs:1539-1552, 1442-1
         grid = np.stack(np.meshgrid(*[np.arange(n)] * order, indexing="ij"), -1).reshape(-1, order)
         ok = a[grid[:, 0]] & b[grid[:, -1]] & m[grid].all(-1) & (grid[:, 1:] != grid[:, :-1]).all(-1)
         np.testing.assert_array_equal(c, grid[ok].astype(np.int32))
+
+
+# reference known-answer table: differt/tests/geometry/test_utils.py:448-490
+_ENUMERATION_KATS = [
+    (0, 0, np.empty((1, 0), int)),
+    (8, 0, np.empty((1, 0), int)),
+    (0, 5, np.empty((0, 5), int)),
+    (3, 1, np.array([[0], [1], [2]])),
+    (3, 2, np.array([[0, 1], [0, 2], [1, 0], [1, 2], [2, 0], [2, 1]])),
+    (3, 3, np.array([[0, 1, 0], [0, 1, 2], [0, 2, 0], [0, 2, 1], [1, 0, 1], [1, 0, 2],
+                     [1, 2, 0], [1, 2, 1], [2, 0, 1], [2, 0, 2], [2, 1, 0], [2, 1, 2]])),
+]
+
+
+@pytest.mark.parametrize("num_primitives,order,expected", _ENUMERATION_KATS)
+def test_complete_graph_enumeration_known_answers(num_primitives, order, expected):
+    got = scenes.complete_graph_candidates(num_primitives, order)
+    assert got.shape == expected.shape and got.dtype == np.int32
+    np.testing.assert_array_equal(got, expected)  # our decode is already in the sorted order
+    assert scenes.num_complete_graph_candidates(num_primitives, order) == expected.shape[0]
+    # chunks of the linear index reproduce the same rows (reference idiom: chunk_size, graph.rs:64-116)
+    parts = [scenes.complete_graph_candidates(num_primitives, order, s, 5) for s in range(0, expected.shape[0], 5)]
+    if parts:
+        np.testing.assert_array_equal(np.concatenate(parts), expected)
+
+
+@pytest.mark.parametrize("n,depth,count", [(10, 3, 10), (10, 4, 90), (5, 5, 80), (1, 3, 1), (1, 4, 0), (0, 4, 0)])
+def test_complete_graph_counts(n, depth, count):  # n (n-1)^(k-1), graph.rs:356-362 / tests :1338-1378
+    assert scenes.num_complete_graph_candidates(n, depth - 2) == count
+    assert scenes.complete_graph_candidates(n, depth - 2).shape[0] == count
