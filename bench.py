@@ -206,7 +206,9 @@ def run_reference(args, rank: int) -> None:
 
     wl = build_workload(args.workload, 0, 1)
     cores = cpu_threads()
-    cand, rx, sample = cpu_calibrate(wl, args.cpu_seconds)
+    # bounded sample per step, sized so that the whole --steps K --warmup W run stays near two minutes
+    per_step = max(0.5, min(args.cpu_seconds, 120.0 / max(args.steps + args.warmup, 1)))
+    cand, rx, sample = cpu_calibrate(wl, per_step)
     for _ in range(args.warmup):
         cpu_step(wl, cand, rx)
     tests = 0
