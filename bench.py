@@ -91,7 +91,7 @@ def build_workload(name: str, rank: int, world: int):
 # ------------------------------------------------------------------------------------------------
 
 _SMI_FIELDS = (
-    "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
     "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
     "clocks_event_reasons.sw_power_cap"
 )
@@ -99,7 +99,9 @@ _REASONS = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_pow
 
 
 class ClockSampler:
-    """`nvidia-smi -lms 200` on this rank's GPU for the duration of the timed region."""
+    """`nvidia-smi -lms 200` on this rank's GPU.  It is started BEFORE the warm-up steps (its NVML
+    start-up contends with kernel launches for a few hundred ms) and keeps polling through the timed
+    region; only the samples stamped inside [mark_start(), stop()] are reported."""
 
     def __init__(self, device_index: int) -> None:
         import torch
@@ -116,10 +118,15 @@ class ClockSampler:
             )
         except Exception:  # nvidia-smi missing: report no clocks rather than fail the bench
             self.proc = None
+        self.t0 = time.time()
+
+    def mark_start(self) -> None:
+        self.t0 = time.time()
 
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        t1 = time.time()
         time.sleep(0.25)
         self.proc.terminate()
         try:
@@ -129,10 +136,19 @@ class ClockSampler:
         self.file.flush()
         self.file.seek(0)
         sm, smax, power, reasons = [], [], [], set()
+        import datetime
+
         for line in self.file.read().splitlines():
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
+            try:
+                stamp = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if not (self.t0 - 0.2 <= stamp <= t1 + 0.2):
+                    continue
+            except ValueError:
+                pass  # unknown timestamp format: keep the sample
+            parts = parts[1:]
             try:
                 sm.append(float(parts[0]))
                 smax.append(float(parts[1]))
@@ -336,6 +352,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         torch.cuda.synchronize()
 
     # ---- kernel-level leg: inputs resident in HBM ------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(2):  # set-up: let the caching allocator reach its steady state before the W warm-ups
         step_resident(False)
     for _ in range(args.warmup):
@@ -343,9 +360,10 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     barrier()
     stats_acc.zero_()
     _lib.check(_lib.lib.drt_profile_reset())
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.mark_start()
     ev0.record()
     for i in range(args.steps):
         paths = step_resident(i < 64)

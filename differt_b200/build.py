@@ -87,7 +87,8 @@ def build(force: bool = False, verbose: bool = False, extra_flags: list[str] | N
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, sources()))
     tmp = LIB.with_suffix(".so.tmp")
-    cmd = [exe, "-shared", "-o", str(tmp), *map(str, objs), "-cudart", "static"]
+    # --no-undefined: an unresolved internal symbol must fail the build, not the first dlopen
+    cmd = [exe, "-shared", "-o", str(tmp), *map(str, objs), "-cudart", "static", "-Xlinker", "--no-undefined"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

@@ -101,13 +101,31 @@ int drt_mesh_pack_sort_by_area(drt_stream_t stream, int64_t num_triangles, const
     return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
 }
 
+}  // extern "C"
+
+// internal: the same for an explicit number of records (a sub-range of a pack)
+namespace drt {
+int drt_sort_records_by_keys(drt_stream_t stream, int64_t n, const void *pack_in, const uint32_t *keys,
+                             void *workspace, size_t workspace_bytes, void *pack_out);
+}
+
+extern "C" {
+
 int drt_mesh_pack_sort_by_keys(drt_stream_t stream, int64_t num_triangles, const void *pack_in,
                                const uint32_t *keys, void *workspace, size_t workspace_bytes,
                                void *pack_out) {
     if (num_triangles < 0 || num_triangles > (int64_t(1) << 30)) return DRT_ERR_BAD_EXTENT;
+    return drt_sort_records_by_keys(stream, int64_t(drt_mesh_pack_bytes(num_triangles) / sizeof(Tri48)), pack_in,
+                                    keys, workspace, workspace_bytes, pack_out);
+}
+
+}  // extern "C"
+
+int drt::drt_sort_records_by_keys(drt_stream_t stream, int64_t n, const void *pack_in, const uint32_t *keys,
+                                  void *workspace, size_t workspace_bytes, void *pack_out) {
+    if (n <= 0) return DRT_ERR_BAD_EXTENT;
     if (!pack_in || !pack_out || !workspace || !keys) return DRT_ERR_NULL_POINTER;
     if (pack_in == pack_out) return DRT_ERR_UNSUPPORTED;
-    const int64_t n = int64_t(drt_mesh_pack_bytes(num_triangles) / sizeof(Tri48));
     const SortLayout l = sort_layout(n);
     if (workspace_bytes < l.total) return DRT_ERR_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -125,5 +143,3 @@ int drt_mesh_pack_sort_by_keys(drt_stream_t stream, int64_t num_triangles, const
                                               static_cast<Tri48 *>(pack_out));
     return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
 }
-
-}  // extern "C"

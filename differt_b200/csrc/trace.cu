@@ -197,6 +197,11 @@ trace_stage_a_kernel(const TraceArgs a, const int64_t rx_per_chunk) {
 // `out_list` (32 at a time per warp) for the next pass of the cascade (tiles [8,16), [16,24), ...).
 // ------------------------------------------------------------------------------------------------
 
+#ifndef DRT_GREEDY_TILES
+#define DRT_GREEDY_TILES 8
+#endif
+int drt_sort_records_by_keys(drt_stream_t stream, int64_t n, const void *pack_in, const uint32_t *keys,
+                             void *workspace, size_t workspace_bytes, void *pack_out);  // pack_sort.cu
 #ifndef DRT_PATH_HEAD_TILES
 #define DRT_PATH_HEAD_TILES 8
 #endif
@@ -330,12 +335,19 @@ path_head_kernel(const Tri48 *__restrict__ pack, const int num_head_tiles, const
 // fast test without its exactness fallback.
 // ------------------------------------------------------------------------------------------------
 
+__global__ void sample_list_kernel(int64_t n, int64_t stride, uint32_t *__restrict__ list) {
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i < n) list[i] = uint32_t(i * stride);
+}
+
 constexpr int kCountBatch = 64;  // sampled candidates staged in shared memory at a time
 
 template <int NSEG>
 __global__ void __launch_bounds__(256)
 hit_count_kernel(const Tri48 *__restrict__ pack, const int64_t num_records,
-                 const float *__restrict__ vertices, const int64_t stride, const int64_t num_samples,
+                 const float *__restrict__ vertices, const int64_t stride,
+                 const uint32_t *__restrict__ sample_list /* nullable: sample s = path s * stride */,
+                 const int64_t num_samples_host, const int64_t *__restrict__ num_samples_dev,
                  const int64_t samples_per_chunk, const float eps, const float thr,
                  uint32_t *__restrict__ counts) {
     constexpr int NV3 = (NSEG + 1) * 3;
@@ -346,6 +358,7 @@ hit_count_kernel(const Tri48 *__restrict__ pack, const int64_t num_records,
         const int64_t jj = j < num_records ? j : num_records - 1;
         tr = unpack(pack[jj].a, pack[jj].b, pack[jj].c);
     }
+    const int64_t num_samples = num_samples_dev != nullptr ? *num_samples_dev : num_samples_host;
     const int64_t s0 = int64_t(blockIdx.y) * samples_per_chunk;
     const int64_t s1 = s0 + samples_per_chunk < num_samples ? s0 + samples_per_chunk : num_samples;
     uint32_t c = 0;
@@ -354,7 +367,8 @@ hit_count_kernel(const Tri48 *__restrict__ pack, const int64_t num_records,
         __syncthreads();
         for (int i = threadIdx.x; i < nb * NV3; i += blockDim.x) {
             const int u = i / NV3, k = i - u * NV3;
-            sv[u][k] = vertices[(base + u) * stride * NV3 + k];
+            const int64_t path = sample_list != nullptr ? int64_t(sample_list[base + u]) : (base + u) * stride;
+            sv[u][k] = vertices[path * NV3 + k];
         }
         __syncthreads();
         for (int u = 0; u < nb; ++u) {
@@ -822,15 +836,63 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
             if (cudaMemsetAsync(hit_counts, 0, size_t(records) * sizeof(uint32_t), s) != cudaSuccess)
                 return DRT_ERR_CUDA;
             const int chunks = 32;
+            const int64_t spc = (num_samples + chunks - 1) / chunks;
             const dim3 cgrid(unsigned((records + 255) / 256), chunks);
-            hit_count_kernel<NSEG><<<cgrid, 256, 0, s>>>(pack_active, records, a.out_vertices, stride,
-                                                         num_samples, (num_samples + chunks - 1) / chunks,
-                                                         a.eps, p.thr, hit_counts);
+            hit_count_kernel<NSEG><<<cgrid, 256, 0, s>>>(pack_active, records, a.out_vertices, stride, nullptr,
+                                                         num_samples, nullptr, spc, a.eps, p.thr, hit_counts);
             if (cudaGetLastError() != cudaSuccess) return DRT_ERR_CUDA;
-            const int rc = drt_mesh_pack_sort_by_keys(s, a.T, pack_active, hit_counts, sort_ws, sort_bytes,
-                                                      pack_sorted2);
+            int rc = drt_mesh_pack_sort_by_keys(s, a.T, pack_active, hit_counts, sort_ws, sort_bytes, pack_sorted2);
             if (rc != DRT_OK) return rc;
-            pack_active = pack_sorted2;
+            Tri48 *cur = pack_sorted2;
+            Tri48 *other = const_cast<Tri48 *>(pack_active);  // the area-sorted copy is no longer needed
+#if DRT_GREEDY_TILES > 0
+            // Greedy refinement (set-cover heuristic): raw hit counts are redundant — the triangles
+            // that block the most samples tend to block the SAME samples.  Tile by tile: keep the
+            // samples the tiles chosen so far do not block (one resident pass of the cascade kernel on
+            // the sample list), recount the remaining triangles on those samples only, re-sort the
+            // remaining records.  Sample lists ping-pong between list2 and list3 (free at this point).
+            {
+                auto hk0 = path_head_kernel<NSEG>;
+                if (cudaFuncSetAttribute(hk0, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPathHeadSmem)) !=
+                    cudaSuccess)
+                    return DRT_ERR_CUDA;
+                uint32_t *sl_in = list2, *sl_out = list3;
+                int64_t *cnt_in = list2_count, *cnt_out = list2_count + 1;
+                sample_list_kernel<<<unsigned((num_samples + 255) / 256), 256, 0, s>>>(num_samples, stride, sl_in);
+                if (cudaMemcpyAsync(cnt_in, &num_samples, sizeof(int64_t), cudaMemcpyHostToDevice, s) != cudaSuccess)
+                    return DRT_ERR_CUDA;
+                const int rounds = p.num_tiles - 1 < DRT_GREEDY_TILES ? p.num_tiles - 1 : DRT_GREEDY_TILES;
+                for (int r = 0; r < rounds; ++r) {
+                    if (cudaMemsetAsync(cnt_out, 0, sizeof(int64_t), s) != cudaSuccess) return DRT_ERR_CUDA;
+                    // samples that tile r does not block
+                    const int64_t sb = (num_samples + kPathHeadWarps - 1) / kPathHeadWarps;
+                    hk0<<<unsigned(sb < 148 ? sb : 148), kPathHeadWarps * 32, kPathHeadSmem, s>>>(
+                        cur + size_t(r) * kTile, 1, num_samples, cnt_in, a.out_vertices, sl_in, a.eps, p.thr,
+                        a.out_mask, sl_out, cnt_out, nullptr);
+                    // recount the records after tile r on the surviving samples, re-sort them
+                    const int64_t rest = records - int64_t(r + 1) * kTile;
+                    if (cudaMemsetAsync(hit_counts, 0, size_t(rest) * sizeof(uint32_t), s) != cudaSuccess)
+                        return DRT_ERR_CUDA;
+                    const dim3 rgrid(unsigned((rest + 255) / 256), chunks);
+                    hit_count_kernel<NSEG><<<rgrid, 256, 0, s>>>(cur + size_t(r + 1) * kTile, rest, a.out_vertices,
+                                                                 stride, sl_out, num_samples, cnt_out, spc, a.eps,
+                                                                 p.thr, hit_counts);
+                    if (cudaGetLastError() != cudaSuccess) return DRT_ERR_CUDA;
+                    rc = drt_sort_records_by_keys(s, rest, cur + size_t(r + 1) * kTile, hit_counts, sort_ws,
+                                                  sort_bytes, other + size_t(r + 1) * kTile);
+                    if (rc != DRT_OK) return rc;
+                    if (cudaMemcpyAsync(other, cur, size_t(r + 1) * kTile * sizeof(Tri48), cudaMemcpyDeviceToDevice,
+                                        s) != cudaSuccess)
+                        return DRT_ERR_CUDA;
+                    Tri48 *tp = cur; cur = other; other = tp;
+                    uint32_t *tl = sl_in; sl_in = sl_out; sl_out = tl;
+                    int64_t *tc = cnt_in; cnt_in = cnt_out; cnt_out = tc;
+                }
+                // the cascade below starts from clean survivor counters
+                if (cudaMemsetAsync(list2_count, 0, 2 * sizeof(int64_t), s) != cudaSuccess) return DRT_ERR_CUDA;
+            }
+#endif
+            pack_active = cur;
             p.pack = pack_active;
         }
         // head pass: every candidate against the likeliest blockers, resident, barrier free
