@@ -246,6 +246,12 @@ def run_reference(args, rank: int) -> None:
     })
 
 
+def launches_per_step(wl: dict, with_vjp: bool) -> int:
+    tiles = -(-int(wl["triangles"].shape[0]) // 512)
+    rounds = min(8, tiles - 1)
+    return 1 + 2 + 1 + (3 + 1 + 4 * rounds) + -(-tiles // 8) + 3 + (1 if with_vjp else 0)
+
+
 def workload_config(wl: dict, world: int, **extra) -> dict:
     T = int(wl["triangles"].shape[0])
     pairs = int(wl["tx"].shape[0] * wl["rx"].shape[0] * wl["cand"].shape[0])
@@ -480,9 +486,11 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                     "executed_tests_per_s": tests_e2e / (ms_e2e * 1e-3), "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                     "valid_paths_gathered": num_valid_global},
-            # per step: pack, area keys + gather, stage A, hit-count + iota + gather (ordering pass),
-            # head pass, ring pass, 3 compaction kernels (+ 8 CUB radix-sort kernels, not counted as ours)
-            "gpu_launches": args.steps * (12 + (1 if with_vjp else 0)),
+            # our kernels per step: pack, area keys + gather, stage A, ordering pass (hit count, iota,
+            # gather, sample list, then per greedy round: resident pass on the samples, hit count, iota,
+            # gather), ceil(tiles / 8) resident passes of the cascade, 3 compaction kernels, the VJP
+            # (CUB's radix-sort kernels are not counted as ours)
+            "gpu_launches": args.steps * launches_per_step(wl, with_vjp),
             "clocks": clocks, "roofline": roofline,
         }
         if world == 1 and not args.no_cpu:
