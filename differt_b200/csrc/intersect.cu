@@ -300,7 +300,7 @@ int drt_ray_intersect_any_triangle(drt_stream_t stream, int64_t R, const float *
         p.num_units = (R + RPW - 1) / RPW;
         FlatRays<RPW> src{o, d, R};
         AnySink<RPW> sink{out};
-        DRT_CHECK_CUDA((launch_intersect<RPW, MODE_ANY, false>(s, p, src, sink, p.num_units)));
+        DRT_CHECK_CUDA((launch_intersect<RPW, MODE_ANY>(s, p, src, sink, p.num_units)));
     })
     return DRT_OK;
 }
@@ -330,7 +330,7 @@ int drt_first_triangle_hit_by_ray(drt_stream_t stream, int64_t R, const float *o
         p.num_units = (R + RPW - 1) / RPW;
         FlatRays<RPW> src{o, d, R};
         FirstSink<RPW> sink{out_index, out_t};
-        DRT_CHECK_CUDA((launch_intersect<RPW, MODE_FIRST, false>(s, p, src, sink, p.num_units)));
+        DRT_CHECK_CUDA((launch_intersect<RPW, MODE_FIRST>(s, p, src, sink, p.num_units)));
     })
     return DRT_OK;
 }
@@ -357,7 +357,7 @@ int drt_triangles_visible_from_vertex(drt_stream_t stream, int64_t B, int64_t n_
         p.num_units = (R + RPW - 1) / RPW;
         VertexRays<RPW> src{vertices, dirs, R, n_rays};
         VisibleSink<RPW> sink{out, n_rays, T};
-        DRT_CHECK_CUDA((launch_intersect<RPW, MODE_FIRST, false>(s, p, src, sink, p.num_units)));
+        DRT_CHECK_CUDA((launch_intersect<RPW, MODE_FIRST>(s, p, src, sink, p.num_units)));
     })
     return DRT_OK;
 }

@@ -136,14 +136,13 @@ __device__ __forceinline__ uint32_t scan_tile_any(const Tri48 *__restrict__ tile
 // Src:  __device__ uint32_t load(int64_t unit, float3 (&o)[RPW], float3 (&d)[RPW])  → active mask
 // Sink: __device__ void any(int64_t unit, uint32_t hit_mask, uint32_t valid_mask)           (ANY)
 //       __device__ void first(int64_t unit, int r, int32_t idx, float t)                    (FIRST)
-// PATH = true: the unit is finished as soon as any of its rays hits (K6 blockage).
 //
 // Scheduling: the CTA walks the tile ring in lockstep (one barrier per tile, which also hands the
 // consumed slot back to the TMA producer), but every WARP owns its own sequence of work units
 // (unit = global warp id + n * total warps) and moves on to its next unit the moment the current one
 // is decided — after an early exit or after it has seen all NT tiles, wherever in the cycle that
 // happens.  No warp idles while another one of its CTA still works on a long unit.
-template <int RPW, int MODE, bool PATH, class Src, class Sink>
+template <int RPW, int MODE, class Src, class Sink>
 __global__ void __launch_bounds__(WarpsFor<MODE>::value * 32, kCtasPerSm)
 intersect_kernel(const CoreParams p, const Src src, const Sink sink) {
     constexpr int kWarpsK = WarpsFor<MODE>::value;
@@ -236,7 +235,7 @@ intersect_kernel(const CoreParams p, const Src src, const Sink sink) {
             uint32_t lane_hits = 0;
             int rows = 0;
             if (MODE == MODE_ANY) {
-                lane_hits = scan_tile_any<RPW, PATH>(tile, lane, o, d, active, p.eps, p.thr, fast_ok, rows);
+                lane_hits = scan_tile_any<RPW, false>(tile, lane, o, d, active, p.eps, p.thr, fast_ok, rows);
             } else {
                 // first-hit: fast reciprocal first; pairs whose |a| is out of its range are skipped and
                 // flagged, and the tile is then redone with the fully general test (idempotent)
@@ -293,7 +292,7 @@ intersect_kernel(const CoreParams p, const Src src, const Sink sink) {
             if (MODE == MODE_ANY) {
                 const uint32_t m = __reduce_or_sync(kFull, lane_hits) & active;
                 hit_any |= m;
-                active = (PATH && m) ? 0u : (active & ~m);
+                active &= ~m;
             }
             if (pos == NT || active == 0) {  // unit decided: emit, move on to this warp's next unit
                 if (MODE == MODE_ANY) {
@@ -336,10 +335,10 @@ intersect_kernel(const CoreParams p, const Src src, const Sink sink) {
     }
 }
 
-template <int RPW, int MODE, bool PATH, class Src, class Sink>
+template <int RPW, int MODE, class Src, class Sink>
 inline cudaError_t launch_intersect(cudaStream_t stream, const CoreParams &p, const Src &src,
                                     const Sink &sink, int64_t max_units) {
-    auto kern = intersect_kernel<RPW, MODE, PATH, Src, Sink>;
+    auto kern = intersect_kernel<RPW, MODE, Src, Sink>;
     static bool configured = false;  // benign race: idempotent attribute set
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,

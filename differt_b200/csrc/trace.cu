@@ -946,7 +946,7 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
         }
         SegRays<RPW> src{a.out_vertices, list, dense ? nullptr : a.list_count, a.P, NSEG};
         SegSink<RPW> sink{a.out_mask, list, NSEG};
-        e = launch_intersect<RPW, MODE_ANY, false>(s, p, src, sink, p.num_units);
+        e = launch_intersect<RPW, MODE_ANY>(s, p, src, sink, p.num_units);
     }
     if (slot >= 0) cudaEventRecord(g_profile.stop[slot], s);
     return e == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
