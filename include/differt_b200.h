@@ -194,8 +194,8 @@ DRT_API int drt_consecutive_vertices_are_on_same_side_of_mirror(
  *     Outputs = the fields of TracedPaths (_paths.py:77-116), dense and contiguous:
  *       vertices [Ntx,Nrx,C,k+2,3] f32, objects [Ntx,Nrx,C,k+2] i32, mask [Ntx,Nrx,C] u8.
  *     `stats` (nullable, device int64[4]): [0] ray–triangle tests evaluated, [1] candidates that
- *     passed the cheap tests (0 in dense mode, where every candidate is blockage-tested),
- *     [2] candidates still unblocked after the resident head tiles, [3] reserved.
+ *     passed the cheap tests (the only ones blockage-tested unless DRT_TRACE_DENSE_BLOCKAGE),
+ *     [2] candidates still unblocked after the first resident pass (8 tiles), [3] reserved.
  *     The callee zero-fills it.
  * K6b reverse mode of `vertices` w.r.t. tx, rx and Mesh.vertices (mask carries no cotangent,
  *     reference: _mesh.py:3087-3094).  g_* outputs are zero-filled by the callee.
