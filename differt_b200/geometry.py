@@ -15,7 +15,6 @@ reference itself bypasses its accelerated path (``_solvers.py:675-680``).
 
 from __future__ import annotations
 
-import ctypes as C
 import math
 from typing import Any
 

@@ -330,7 +330,7 @@ def trace_valid_paths(mesh: Mesh, tx_vertices, rx_vertices, order: int, *, chunk
     the survivors merged back into the reference's row-major ``(tx, rx, candidate)`` order.
     ``num_tx * num_rx * chunk_size`` must stay below 2**32.
     Returns a :class:`differt_b200.distributed.ValidPaths`."""
-    from .distributed import GatherRecord, ValidPaths, fill_record, gather_valid_paths
+    from .distributed import GatherRecord, ValidPaths, fill_record
 
     total, chunks = _candidate_chunks(mesh, tx_vertices, rx_vertices, order, chunk_size, solver, num_rays, accel)
     idx, verts, objs = [], [], []

@@ -1,7 +1,6 @@
 """Stage statistics of the bench workload (how many candidates each blockage pass sees)."""
 import sys, json
 sys.path.insert(0, ".")
-import numpy as np, torch
 import differt_b200 as drt
 import bench
 wl = bench.build_workload(sys.argv[1] if len(sys.argv) > 1 else bench.DEFAULT_WORKLOAD, 0, 1)
