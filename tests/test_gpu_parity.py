@@ -1138,3 +1138,43 @@ def test_sharded_exhaustive_search_world_size_one(drt, two_buildings, kats):
         exp = drt.trace_paths(mesh, tx, rx, order).masked()
         assert torch.equal(got.vertices, exp.vertices) and torch.equal(got.objects, exp.objects)
         assert got.num_valid_paths >= 1
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_fuzz_degenerate_meshes_and_candidates(drt, seed):
+    """Zero-area and duplicated triangles, shared vertices, candidates that repeat a triangle or use a
+    degenerate one, tx / rx lying on mesh vertices and in triangle planes: every output of the fused
+    trace (dense and pruned), any-hit and first-hit still equals the oracle bit for bit."""
+    rng = np.random.default_rng(seed)
+    nv, nt = 40, 90
+    v = rng.integers(-4, 5, size=(nv, 3)).astype(np.float32)  # lattice vertices: many coincidences
+    t = rng.integers(0, nv, size=(nt, 3)).astype(np.int32)
+    t[:8, 1] = t[:8, 0]                      # zero-area (two identical vertices)
+    t[8:12] = t[12:16]                       # duplicated triangles
+    v[5] = v[6]                              # coincident vertices
+    tx = np.concatenate([v[[0, 3]], rng.uniform(-5, 5, (2, 3)).astype(np.float32)])
+    rx = np.concatenate([v[[7]], rng.integers(-5, 6, (6, 3)).astype(np.float32)])
+    tri = orc.triangle_vertices(v, t)
+    for order in (1, 2, 3):
+        cand = rng.integers(0, nt, size=(1500, order)).astype(np.int32)  # repeats allowed on purpose
+        mesh = drt.Mesh.from_numpy(v, t)
+        with np.errstate(all="ignore"):
+            ev, eo, em = co.trace_path_candidates(v, t, tx, rx, cand)
+        for dense in (True, False):
+            got = drt.trace_path_candidates(mesh, tx, rx, cand, dense_blockage=dense)
+            np.testing.assert_array_equal(got.mask.cpu().numpy(), em)
+            np.testing.assert_array_equal(bits(got.vertices.cpu().numpy()), bits(ev))
+            np.testing.assert_array_equal(got.objects.cpu().numpy(), eo)
+        comp = drt.trace_valid_path_candidates(mesh, tx, rx, cand)
+        idx = np.flatnonzero(em.reshape(-1))
+        np.testing.assert_array_equal(comp.index.cpu().numpy(), idx)
+        np.testing.assert_array_equal(bits(comp.vertices.cpu().numpy()), bits(ev.reshape(-1, order + 2, 3)[idx]))
+    o = np.concatenate([v[rng.integers(0, nv, 2000)], rng.integers(-5, 6, (2000, 3)).astype(np.float32)])
+    d = (np.concatenate([v[rng.integers(0, nv, 2000)], rng.integers(-5, 6, (2000, 3)).astype(np.float32)]) - o).astype(np.float32)
+    with np.errstate(all="ignore"):
+        np.testing.assert_array_equal(drt.ray_intersect_any_triangle(o, d, tri).numpy(),
+                                      co.ray_intersect_any_triangle(o, d, tri))
+        ei, et = co.first_triangle_hit_by_ray(o, d, tri)
+    gi, gt = drt.first_triangle_hit_by_ray(o, d, tri)
+    np.testing.assert_array_equal(gi.numpy(), ei)
+    np.testing.assert_array_equal(bits(gt.numpy()), bits(et))
