@@ -49,6 +49,8 @@ WORKLOADS = {
     "urban10k_1tx_4096rx_order3": dict(scene=("urban", 29, 29), rx=(64, 64), order=3, cand=4096),
     # BASELINE.json configs[1], one chunk of the exhaustive candidate list
     "canyon1k_1tx_256rx_order2": dict(scene=("canyon", 41), rx=(16, 16), order=2, cand=65536),
+    # BASELINE.json configs[3] per GPU: 16 TX x 4096 RX, order 3, the 4096 candidates sharded over 8 GPUs
+    "urban10k_16tx_4096rx_order3": dict(scene=("urban", 29, 29), rx=(64, 64), order=3, cand=512, ntx=16),
     # BASELINE.json configs[4] per GPU: 50k-triangle mesh, 1 TX x 16 384 RX, order 4, 2048 candidates
     "urban50k_1tx_16384rx_order4": dict(scene=("urban", 64, 65), rx=(128, 128), order=4, cand=2048),
     # small variant for quick checks (not a bench line)
@@ -69,6 +71,12 @@ def build_workload(name: str, rank: int, world: int):
         v, t = scenes.street_canyon(w["scene"][1])
     lo, hi = v.min(0), v.max(0)
     tx = np.array([[0.5 * (lo[0] + hi[0]) + 15.0, 0.5 * (lo[1] + hi[1]) + 15.0, 1.2 * hi[2]]], np.float32)
+    if w.get("ntx", 1) > 1:  # 4 x 4 grid of transmitters at the same height
+        n = int(round(w["ntx"] ** 0.5))
+        gx = np.linspace(lo[0] + 100.0, hi[0] - 100.0, n, dtype=np.float32) + 15.0
+        gy = np.linspace(lo[1] + 100.0, hi[1] - 100.0, n, dtype=np.float32) + 15.0
+        xx, yy = np.meshgrid(gx, gy, indexing="ij")
+        tx = np.stack((xx, yy, np.full_like(xx, 1.2 * hi[2])), -1).reshape(-1, 3).astype(np.float32)
     rx = scenes.receivers_grid(v, *w["rx"])
     cand_all = scenes.sampled_candidates(t.shape[0], w["order"], w["cand"] * world, seed=1234)
     start = rank * w["cand"]
