@@ -1,3 +1,5 @@
+"""Regenerate BASELINE.md sections 5-6 and profiles/traffic.json from the JSON artefacts under profiles/
+(round-1 bookkeeping script; paths are relative to /root/repo)."""
 import json,re
 json.dump({
  "source": "profiles/r1_ncu_dram_traffic_bench_workload.csv (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum; bench workload urban10k_1tx_4096rx_order3; 30 consecutive launches of the blockage kernels = a little more than one step)",
