@@ -66,6 +66,11 @@ PROTOTYPES: dict[str, tuple] = {
     "drt_compact_valid_paths": (
         C.c_int, [ptr, i64, i32, ptr, ptr, ptr, i64, ptr, size_t, ptr, ptr, ptr, ptr]),
     "drt_complete_graph_candidates": (C.c_int, [ptr, i64, i32, i64, i64, i32, ptr]),
+    "drt_ray_intersect_triangle_smooth": (
+        C.c_int, [ptr, i32, p_i64, ptr, p_i64, ptr, p_i64, ptr, p_i64, f32, f32, ptr, ptr]),
+    "drt_ray_intersect_any_triangle_smooth": (C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, f32, f32, ptr]),
+    "drt_consecutive_vertices_are_on_same_side_of_mirror_smooth": (
+        C.c_int, [ptr, i32, p_i64, i32, ptr, p_i64, ptr, p_i64, ptr, p_i64, f32, ptr]),
     "drt_bvh_bytes": (size_t, [i64]),
     "drt_bvh_workspace_bytes": (size_t, [i64]),
     "drt_bvh_build": (C.c_int, [ptr, i64, ptr, f32, ptr, size_t, ptr]),

@@ -335,6 +335,8 @@ path_head_kernel(const Tri48 *__restrict__ pack, const int num_head_tiles, const
 // fast test without its exactness fallback.
 // ------------------------------------------------------------------------------------------------
 
+__global__ void set_i64_kernel(int64_t *p, int64_t v) { *p = v; }
+
 __global__ void sample_list_kernel(int64_t n, int64_t stride, uint32_t *__restrict__ list) {
     const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     if (i < n) list[i] = uint32_t(i * stride);
@@ -859,8 +861,8 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
                 uint32_t *sl_in = list2, *sl_out = list3;
                 int64_t *cnt_in = list2_count, *cnt_out = list2_count + 1;
                 sample_list_kernel<<<unsigned((num_samples + 255) / 256), 256, 0, s>>>(num_samples, stride, sl_in);
-                if (cudaMemcpyAsync(cnt_in, &num_samples, sizeof(int64_t), cudaMemcpyHostToDevice, s) != cudaSuccess)
-                    return DRT_ERR_CUDA;
+                set_i64_kernel<<<1, 1, 0, s>>>(cnt_in, num_samples);  // (a kernel, not a pageable H2D copy: stays
+                                                                      //  capturable in a CUDA graph)
                 const int rounds = p.num_tiles - 1 < DRT_GREEDY_TILES ? p.num_tiles - 1 : DRT_GREEDY_TILES;
                 for (int r = 0; r < rounds; ++r) {
                     if (cudaMemsetAsync(cnt_out, 0, sizeof(int64_t), s) != cudaSuccess) return DRT_ERR_CUDA;

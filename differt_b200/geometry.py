@@ -8,9 +8,11 @@ done by the CUDA library behind the C ABI (``include/differt_b200.h``) — there
 
 Differentiation surface (the reference's ``custom_vjp`` surface): ``image_method`` and
 the hit distance ``t`` of ``first_triangle_hit_by_ray`` / ``ray_intersect_triangle`` carry gradients
-(``torch.autograd``); boolean / index outputs never do.  ``smoothing_factor`` is not supported
-(SURVEY.md §8a): passing a value raises ``NotImplementedError`` — exactly the case in which the
-reference itself bypasses its accelerated path (``_solvers.py:675-680``).
+(``torch.autograd``); boolean / index outputs never do.  ``smoothing_factor`` is supported, forward
+only, by ``ray_intersect_triangle``, ``ray_intersect_any_triangle`` and
+``consecutive_vertices_are_on_same_side_of_mirror`` (float outputs); the fused trace raises
+``NotImplementedError`` — exactly the case in which the reference itself bypasses its accelerated
+path (``_solvers.py:675-680``).
 """
 
 from __future__ import annotations
@@ -52,7 +54,7 @@ _SORT_MIN_RAYS = 4096
 def _no_smoothing(smoothing_factor: Any) -> None:
     if smoothing_factor is not None:
         raise NotImplementedError(
-            "smoothing_factor is not supported by the CUDA path (SURVEY.md §8a); "
+            "smoothing_factor is not supported here (SURVEY.md §8a); "
             "the reference falls back to pure JAX in this case (_solvers.py:665-674)"
         )
 
@@ -178,8 +180,9 @@ def ray_intersect_triangle(
     """Möller–Trumbore ``(t, hit)`` — reference ``_utils.py:1157-1322``.
 
     ``t`` is returned even where ``hit`` is false; ``epsilon`` defaults to ``10 * eps(float32)``.
+    With ``smoothing_factor`` the hit is a float in [0, 1] (sigmoid relaxation, reference
+    ``_utils.py:1279-1318``); that variant is forward-only (no gradient).
     """
-    _no_smoothing(smoothing_factor)
     pl = Placement()
     o = pl.put(ray_origins, torch.float32)
     d = pl.put(ray_directions, torch.float32)
@@ -187,6 +190,17 @@ def ray_intersect_triangle(
     batch = torch.broadcast_shapes(o.shape[:-1], d.shape[:-1], tv.shape[:-2])
     n = numel(batch)
     t = torch.empty(batch, dtype=torch.float32, device=o.device)
+    if smoothing_factor is not None:
+        hit_f = torch.empty(batch, dtype=torch.float32, device=o.device)
+        if n > 0:
+            ndim, shape, (so, sd, st), keep = batch_strides(batch, [(o.detach(), 1), (d.detach(), 1), (tv.detach(), 2)])
+            check(
+                lib.drt_ray_intersect_triangle_smooth(
+                    stream_ptr(), ndim, shape, ptr(keep[0]), so, ptr(keep[1]), sd, ptr(keep[2]), st,
+                    _default(epsilon, 10.0), float(smoothing_factor), ptr(t), ptr(hit_f),
+                )
+            )
+        return pl.out(t), pl.out(hit_f)
     hit = torch.empty(batch, dtype=torch.uint8, device=o.device)
     needs_grad = torch.is_grad_enabled() and any(x.requires_grad for x in (o, d, tv))
     if n > 0:
@@ -250,7 +264,6 @@ def ray_intersect_any_triangle(
     ``batch_size`` is accepted for signature compatibility and ignored (it only bounds the
     reference's memory use); ``epsilon`` may be passed through ``**kwargs`` like in the reference.
     """
-    _no_smoothing(smoothing_factor)
     del batch_size
     pl = Placement()
     o = pl.put(ray_origins, torch.float32)
@@ -260,8 +273,25 @@ def ray_intersect_any_triangle(
     batch = torch.broadcast_shapes(
         o.shape[:-1], d.shape[:-1], tv.shape[:-3], () if act is None else act.shape[:-1]
     )
-    out = torch.zeros(batch, dtype=torch.uint8, device=o.device)
     T = int(tv.shape[-3])
+    if smoothing_factor is not None:  # forward-only sigmoid relaxation (_utils.py:1465-1476) → float
+        outf = torch.zeros(batch, dtype=torch.float32, device=o.device)
+        if T == 0 or numel(batch) == 0:
+            return pl.out(outf)
+        ob, db = o.expand(*batch, 3), d.expand(*batch, 3)
+        eps, tol = _default(kwargs.get("epsilon"), 10.0), _default(hit_tol, 100.0)
+        for sel, tvi, acti in _mesh_batches(batch, tv, act):
+            oi, di = ob[sel].reshape(-1, 3).contiguous(), db[sel].reshape(-1, 3).contiguous()
+            pack = pack_triangle_vertices(tvi.contiguous(), None if acti is None else acti.contiguous())
+            res = torch.empty(oi.shape[0], dtype=torch.float32, device=o.device)
+            check(
+                lib.drt_ray_intersect_any_triangle_smooth(
+                    stream_ptr(), oi.shape[0], ptr(oi), ptr(di), ptr(pack), T, eps, tol, float(smoothing_factor), ptr(res)
+                )
+            )
+            outf[sel] = res.view(outf[sel].shape)
+        return pl.out(outf)
+    out = torch.zeros(batch, dtype=torch.uint8, device=o.device)
     if T == 0 or numel(batch) == 0:
         return pl.out(out.view(torch.bool))
     ob, db = o.expand(*batch, 3), d.expand(*batch, 3)
@@ -604,8 +634,8 @@ def image_method(from_vertex, to_vertex, mirror_vertices, mirror_normals):
 def consecutive_vertices_are_on_same_side_of_mirror(
     vertices, mirror_vertices, mirror_normals, *, smoothing_factor=None
 ):
-    """Reference ``_solver_image_method.py:386-454`` → bool ``[*batch, k]``."""
-    _no_smoothing(smoothing_factor)
+    """Reference ``_solver_image_method.py:386-454`` → bool ``[*batch, k]`` (float in [0, 1] with
+    ``smoothing_factor``, forward only)."""
     pl = Placement()
     v = pl.put(vertices, torch.float32)
     mv = pl.put(mirror_vertices, torch.float32)
@@ -614,6 +644,17 @@ def consecutive_vertices_are_on_same_side_of_mirror(
     if v.shape[-2] != k + 2:
         raise TypeError(f"vertices must hold num_mirrors + 2 = {k + 2} points, got {v.shape[-2]}")
     batch = torch.broadcast_shapes(v.shape[:-2], mv.shape[:-2], mn.shape[:-2])
+    if smoothing_factor is not None:
+        outf = torch.empty((*batch, k), dtype=torch.float32, device=v.device)
+        if numel(batch) > 0 and k > 0:
+            ndim, shape, (sv, sm, sn), keep = batch_strides(batch, [(v, 2), (mv, 2), (mn, 2)])
+            check(
+                lib.drt_consecutive_vertices_are_on_same_side_of_mirror_smooth(
+                    stream_ptr(), ndim, shape, k, ptr(keep[0]), sv, ptr(keep[1]), sm, ptr(keep[2]), sn,
+                    float(smoothing_factor), ptr(outf),
+                )
+            )
+        return pl.out(outf)
     out = torch.empty((*batch, k), dtype=torch.uint8, device=v.device)
     if numel(batch) > 0 and k > 0:
         ndim, shape, (sv, sm, sn), keep = batch_strides(batch, [(v, 2), (mv, 2), (mn, 2)])

@@ -288,6 +288,28 @@ DRT_API int drt_digraph_candidates(drt_stream_t stream, int64_t num_nodes, int32
                            int32_t stride_multiplier, int32_t *out);
 
 /* ---------------------------------------------------------------------------------------------
+ * N4  (forward only) smoothed variants of the primitives: comparisons → sigmoid(x * smoothing_factor)
+ *     (reference: differt/src/differt/utils.py:70-89), AND → min, OR over triangles → sum clipped at 1
+ *     (_utils.py:1279-1318, 1465-1476; _solver_image_method.py:448-454).  Float outputs in [0,1];
+ *     parity to 1e-5 (transcendental), not bit-exact.  Masked-out triangles of a pack contribute 0.
+ * ------------------------------------------------------------------------------------------- */
+DRT_API int drt_ray_intersect_triangle_smooth(drt_stream_t stream, int32_t ndim, const int64_t *shape_host,
+                                      const float *ray_origins, const int64_t *o_strides_host,
+                                      const float *ray_directions, const int64_t *d_strides_host,
+                                      const float *triangle_vertices, const int64_t *tri_strides_host,
+                                      float epsilon, float smoothing_factor, float *t_out,
+                                      float *hit_out);
+DRT_API int drt_ray_intersect_any_triangle_smooth(drt_stream_t stream, int64_t num_rays,
+                                          const float *ray_origins, const float *ray_directions,
+                                          const void *pack, int64_t num_triangles, float epsilon,
+                                          float hit_tol, float smoothing_factor, float *out);
+DRT_API int drt_consecutive_vertices_are_on_same_side_of_mirror_smooth(
+    drt_stream_t stream, int32_t ndim, const int64_t *shape_host, int32_t order,
+    const float *vertices, const int64_t *v_strides_host, const float *mirror_vertices,
+    const int64_t *mv_strides_host, const float *mirror_normals, const int64_t *mn_strides_host,
+    float smoothing_factor, float *out);
+
+/* ---------------------------------------------------------------------------------------------
  * N2  OPT-IN bounding-volume hierarchy (linear BVH over Morton-sorted triangles) for the queries the
  *     reference answers with Warp's BVH (wp.mesh_query_ray[_anyhit], _mesh.py:142-223, 347-401).
  *     Every triangle that is reached is tested with the same arithmetic as the brute-force kernels

@@ -788,3 +788,65 @@ def compute_tx_mlm(vertices, triangles, tx, ray_directions, *, max_order, min_or
         qo = np.where(alive[..., None], (o + d_new * eps).astype(np.float32), qo)
         d = np.where(alive[..., None], d_new, d)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# N4 (forward): smoothed primitives
+# ------------------------------------------------------------------------------------------------
+
+
+def smoothing_function(x, smoothing_factor=1.0):
+    """``jax.nn.sigmoid(x * alpha)`` (``differt/src/differt/utils.py:70-89``), float32."""
+    with np.errstate(over="ignore", invalid="ignore"):
+        z = (_f(x) * F32(smoothing_factor)).astype(np.float32)
+        return (F32(1.0) / (F32(1.0) + np.exp(-z).astype(np.float32))).astype(np.float32)
+
+
+def ray_intersect_triangle_smooth(ray_origins, ray_directions, tri, *, epsilon=None, smoothing_factor=1.0):
+    """``ray_intersect_triangle(..., smoothing_factor=alpha)`` (``_utils.py:1263-1322``) → ``(t, hit)``
+    with ``hit`` a float in [0, 1]."""
+    eps = F32(10 * EPS if epsilon is None else epsilon)
+    o, d, tri = _f(ray_origins), _f(ray_directions), _f(tri)
+    with np.errstate(all="ignore"):
+        v0, v1, v2 = tri[..., 0, :], tri[..., 1, :], tri[..., 2, :]
+        e1, e2 = v1 - v0, v2 - v0
+        h = cross3(d, e2)
+        a = dot3(h, e1)
+        a = np.where(a == 0, INF, a).astype(np.float32)
+        hit = smoothing_function(np.abs(a) - eps, smoothing_factor)
+        f = (F32(1.0) / a).astype(np.float32)
+        s = o - v0
+        u = f * dot3(s, h)
+        one = np.ones_like(hit)
+        hit = np.minimum.reduce([hit, smoothing_function(u - F32(0), smoothing_factor),
+                                 smoothing_function(F32(1) - u, smoothing_factor), one])
+        q = cross3(s, e1)
+        v = f * dot3(q, d)
+        hit = np.minimum.reduce([hit, smoothing_function(v - F32(0), smoothing_factor),
+                                 smoothing_function(F32(1) - (u + v), smoothing_factor), one])
+        t = f * dot3(q, e2)
+        hit = np.minimum(hit, smoothing_function(t - eps, smoothing_factor))
+    return t.astype(np.float32), hit.astype(np.float32)
+
+
+def ray_intersect_any_triangle_smooth(ray_origins, ray_directions, tri, active=None, *, epsilon=None,
+                                      hit_tol=None, smoothing_factor=1.0):
+    """``ray_intersect_any_triangle(..., smoothing_factor=alpha)`` (``_utils.py:1452-1476``): sum over the
+    active triangles of ``min(hit, sigmoid((1 - hit_tol - t) alpha))``, clipped at 1."""
+    thr = F32(1.0) - F32(100 * EPS if hit_tol is None else hit_tol)
+    o, d, tri = _f(ray_origins), _f(ray_directions), _f(tri)
+    t, hit = ray_intersect_triangle_smooth(o[..., None, :], d[..., None, :], tri, epsilon=epsilon,
+                                           smoothing_factor=smoothing_factor)
+    term = np.minimum(hit, smoothing_function(thr - t, smoothing_factor))
+    if active is not None:
+        term = np.where(np.asarray(active, bool), term, F32(0))
+    return np.minimum(term.sum(axis=-1, dtype=np.float32), F32(1.0)).astype(np.float32)
+
+
+def consecutive_vertices_are_on_same_side_of_mirror_smooth(vertices, mirror_vertices, mirror_normals,
+                                                           smoothing_factor=1.0):
+    """``_solver_image_method.py:440-454`` with smoothing: ``sigmoid(sign(dot_prev) sign(dot_next) alpha)``."""
+    v, mv, mn = _f(vertices), _f(mirror_vertices), _f(mirror_normals)
+    dp = dot3(v[..., :-2, :] - mv, mn)
+    dn = dot3(v[..., 2:, :] - mv, mn)
+    return smoothing_function(np.sign(dp) * np.sign(dn), smoothing_factor)

@@ -1178,3 +1178,39 @@ def test_fuzz_degenerate_meshes_and_candidates(drt, seed):
     gi, gt = drt.first_triangle_hit_by_ray(o, d, tri)
     np.testing.assert_array_equal(gi.numpy(), ei)
     np.testing.assert_array_equal(bits(gt.numpy()), bits(et))
+
+
+# ------------------------------------------------------------------------------------------------
+# N4 (forward): smoothed primitives, parity to tolerance (the sigmoid is a transcendental)
+# ------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("alpha", [1.0, 10.0, 1e8])
+def test_smoothed_primitives_match_oracle(drt, rng, alpha):
+    tri = rng.normal(size=(300, 3, 3)).astype(np.float32)
+    o = rng.normal(size=(500, 3)).astype(np.float32)
+    d = (rng.normal(size=(500, 3)) * 3).astype(np.float32)
+    t, hit = drt.ray_intersect_triangle(o[:, None], d[:, None], tri, smoothing_factor=alpha)
+    et, eh = orc.ray_intersect_triangle_smooth(o[:, None], d[:, None], tri, smoothing_factor=alpha)
+    assert hit.dtype == torch.float32 and tuple(hit.shape) == (500, 300)
+    np.testing.assert_array_equal(bits(t.numpy()), bits(et))
+    np.testing.assert_allclose(hit.numpy(), eh, rtol=1e-5, atol=1e-6)
+    mask = rng.uniform(size=300) < 0.6
+    for act in (None, mask):
+        got = drt.ray_intersect_any_triangle(o, d, tri, act, smoothing_factor=alpha)
+        exp = orc.ray_intersect_any_triangle_smooth(o, d, tri, act, smoothing_factor=alpha)
+        np.testing.assert_allclose(got.numpy(), exp, rtol=2e-5, atol=1e-6)
+    v = rng.normal(size=(64, 5, 3)).astype(np.float32)
+    mv, mn = rng.normal(size=(64, 3, 3)).astype(np.float32), rng.normal(size=(64, 3, 3)).astype(np.float32)
+    got = drt.consecutive_vertices_are_on_same_side_of_mirror(v, mv, mn, smoothing_factor=alpha)
+    exp = orc.consecutive_vertices_are_on_same_side_of_mirror_smooth(v, mv, mn, alpha)
+    np.testing.assert_allclose(got.numpy(), exp, rtol=1e-5, atol=1e-6)
+    if alpha == 1e8:  # the reference's own test: a huge slope reproduces the hard decisions
+        _, hard = drt.ray_intersect_triangle(o[:, None], d[:, None], tri)
+        np.testing.assert_array_equal((hit > 0.5).numpy(), hard.numpy())
+        np.testing.assert_array_equal(
+            (drt.ray_intersect_any_triangle(o, d, tri, smoothing_factor=alpha) > 0.5).numpy(),
+            drt.ray_intersect_any_triangle(o, d, tri).numpy())
+    with pytest.raises(NotImplementedError):
+        m = drt.Mesh.from_numpy(tri.reshape(-1, 3), np.arange(900, dtype=np.int32).reshape(300, 3))
+        drt.trace_path_candidates(m, o[:1], o[1:2], np.zeros((1, 1), np.int32), smoothing_factor=alpha)

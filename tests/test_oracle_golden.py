@@ -365,3 +365,31 @@ def test_sbr_oracle_finds_the_order_one_reflection_of_a_wall():
     assert masks[0, 0, :, 1].any()
     hit = verts[0, masks[0, 0, :, 1], 0, :]
     np.testing.assert_allclose(hit.mean(0), [0.0, 0.0, 10.0], atol=0.2)
+
+
+def test_smoothing_oracle_matches_hard_decisions_for_large_alpha():
+    """Reference property (differt/tests/geometry/test_utils.py:636-646, 701-714 and
+    test_image_method.py:225-255): with smoothing_factor = 1e8 the relaxed outputs, thresholded at 0.5,
+    equal the hard ones; and sigmoid(0) = 0.5, smoothing_function is monotone."""
+    rng = np.random.default_rng(3)
+    tri = rng.normal(size=(40, 3, 3)).astype(np.float32)
+    o = rng.normal(size=(300, 3)).astype(np.float32)
+    d = (rng.normal(size=(300, 3)) * 3).astype(np.float32)
+    t, hit = orc.ray_intersect_triangle(o[:, None], d[:, None], tri)
+    ts, hs = orc.ray_intersect_triangle_smooth(o[:, None], d[:, None], tri, smoothing_factor=1e8)
+    np.testing.assert_array_equal(hs > 0.5, hit)
+    np.testing.assert_array_equal(ts.view(np.uint32), t.view(np.uint32))
+    mask = rng.uniform(size=40) < 0.5
+    for act in (None, mask):
+        a = orc.ray_intersect_any_triangle(o, d, tri, act)
+        a_s = orc.ray_intersect_any_triangle_smooth(o, d, tri, act, smoothing_factor=1e8)
+        np.testing.assert_array_equal(a_s > 0.5, a)
+        assert a_s.min() >= 0.0 and a_s.max() <= 1.0
+    v = rng.normal(size=(50, 5, 3)).astype(np.float32)
+    mv, mn = rng.normal(size=(50, 3, 3)).astype(np.float32), rng.normal(size=(50, 3, 3)).astype(np.float32)
+    hard = orc.consecutive_vertices_are_on_same_side_of_mirror(v, mv, mn)
+    soft = orc.consecutive_vertices_are_on_same_side_of_mirror_smooth(v, mv, mn, 1e8)
+    np.testing.assert_array_equal(soft > 0.5, hard)
+    assert float(orc.smoothing_function(0.0, 7.0)) == 0.5
+    x = np.linspace(-3, 3, 50, dtype=np.float32)
+    assert (np.diff(orc.smoothing_function(x, 2.0)) > 0).all()
