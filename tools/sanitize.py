@@ -29,6 +29,16 @@ for order, n in ((1, 1454), (2, 3000), (3, 3000), (6, 500)):
     for dense in (False, True):
         p = drt.trace_path_candidates(mesh, tx, rx, cand, dense_blockage=dense, with_stats=True)
         print("trace", order, dense, p.num_valid_paths, p.stats)
+# a dense batch large enough (>= 8 * 32768 paths) to run the ordering pass with its greedy rounds
+rx_big = scenes.receivers_grid(v, 16, 8)
+big = drt.trace_path_candidates(mesh, tx, rx_big, scenes.sampled_candidates(t.shape[0], 2, 2048), dense_blockage=True, with_stats=True)
+print("dense with ordering pass", big.num_valid_paths, big.stats)
+comp = drt.trace_valid_path_candidates(mesh, tx, rx, scenes.complete_graph_candidates(t.shape[0], 1), capacity=7)
+print("compact", comp.num_valid_paths)
+print("bvh", int(mesh.ray_intersect_any_triangle(o, d, accel="bvh").sum()), int((mesh.first_triangle_hit_by_ray(o, d, accel="bvh")[0] >= 0).sum()))
+print("smooth", float(drt.ray_intersect_any_triangle(o[:500], d[:500], tri, smoothing_factor=5.0).sum()))
+lp = drt.launch_paths(mesh, tx, rx[:8], 1, num_rays=2000, max_dist=1.0)
+print("sbr", int(lp.masks.sum()), "mlm", int((drt.compute_tx_mlm(mesh, tx, max_order=1, dim_x=4, dim_y=4, num_rays=2000, receiver_height=1.5, min_x=0.0, max_x=300.0, min_y=0.0, max_y=300.0) != 0).sum()))
 paths, valid = trace_path_candidates_sharded(mesh, tx, rx, torch.from_numpy(scenes.complete_graph_candidates(t.shape[0], 1)).cuda())
 print("sharded", valid.num_valid_paths)
 mg = drt.Mesh(mesh.vertices.clone().requires_grad_(True), mesh.triangles)
