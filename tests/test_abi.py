@@ -117,3 +117,36 @@ def test_deprecated_plural_names(lib):
     with pytest.warns(DeprecationWarning):
         assert drt.rt.first_triangles_hit_by_rays is drt.geometry.first_triangle_hit_by_ray
     assert drt.rt.image_method is drt.geometry.image_method
+
+
+def _compile_c_example(tmp_path, lib):
+    """gcc -std=c99 on integration/c_abi_example.c: the header must be valid C and every entry point
+    the example uses must link against the shared library."""
+    import shutil
+    import subprocess
+
+    cuda = Path("/usr/local/cuda")
+    if shutil.which("gcc") is None or not (cuda / "include" / "cuda_runtime_api.h").exists():
+        pytest.skip("needs gcc and the CUDA runtime headers")
+    exe = tmp_path / "c_abi_example"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}", f"-I{cuda / 'include'}",
+           str(ROOT / "integration" / "c_abi_example.c"), f"-L{lib.LIB_PATH.parent}", "-ldiffert_b200",
+           f"-L{cuda / 'lib64'}", "-lcudart", f"-Wl,-rpath,{lib.LIB_PATH.parent}", "-o", str(exe)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_header_is_valid_c_and_a_pure_c_consumer_links(lib, tmp_path):
+    assert _compile_c_example(tmp_path, lib).exists()
+
+
+@pytest.mark.gpu
+def test_pure_c_consumer_runs_on_the_gpu(lib, tmp_path):
+    import subprocess
+
+    exe = _compile_c_example(tmp_path, lib)
+    res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "OK: 6 valid order-1 paths" in res.stdout
+    assert res.stdout.count("blocked=1") == 6 and res.stdout.count("t=0.500") == 6
