@@ -256,7 +256,7 @@ def run_reference(args, rank: int) -> None:
 
 def launches_per_step(wl: dict, with_vjp: bool) -> int:
     tiles = -(-int(wl["triangles"].shape[0]) // 512)
-    rounds = min(8, tiles - 1)
+    rounds = min(4, tiles - 1)
     return 1 + 2 + 1 + (3 + 1 + 4 * rounds) + -(-tiles // 8) + 3 + (1 if with_vjp else 0)
 
 
@@ -367,8 +367,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
 
     # ---- kernel-level leg: inputs resident in HBM ------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    for _ in range(2):  # set-up: let the caching allocator reach its steady state before the W warm-ups
-        step_resident(False)
+    for _ in range(6):  # set-up: allocator steady state and cold-start effects of a fresh box, before the
+        step_resident(False)  # W warm-ups
     for _ in range(args.warmup):
         step_resident(False)
     barrier()

@@ -198,7 +198,7 @@ trace_stage_a_kernel(const TraceArgs a, const int64_t rx_per_chunk) {
 // ------------------------------------------------------------------------------------------------
 
 #ifndef DRT_GREEDY_TILES
-#define DRT_GREEDY_TILES 8
+#define DRT_GREEDY_TILES 4
 #endif
 int drt_sort_records_by_keys(drt_stream_t stream, int64_t n, const void *pack_in, const uint32_t *keys,
                              void *workspace, size_t workspace_bytes, void *pack_out);  // pack_sort.cu
