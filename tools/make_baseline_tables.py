@@ -21,8 +21,8 @@ open(p,'w').write(s)
 
 b=open('/root/repo/BASELINE.md').read()
 b=b[:b.index('## 5. Measured results')]
-d=json.load(open('/root/repo/profiles/r1_bench_v6.json'))
-n2=json.load(open('/root/repo/profiles/r1_bench_v6_n2.json'))
+d=json.load(open('/root/repo/profiles/r1_bench_v7.json'))
+n2=json.load(open('/root/repo/profiles/r1_bench_v7_n2.json'))
 n8=json.load(open('/root/repo/profiles/r1_bench_v6_n8.json'))
 ref=json.load(open('/root/repo/profiles/r1_bench_reference_arm.json')); ref['value']=d['cpu_baseline']['value']; ref['cpu_baseline']=d['cpu_baseline']
 big=json.load(open('/root/repo/profiles/r1_bench_v3_urban50k_order4.json'))
@@ -56,7 +56,7 @@ shard one of 8 GPUs gets: 3.4·10^7 candidate-pairs): 202 ms per step, 6.7·10^1
 
 North-star floor (10^9 tests/s per B200 at ≥ 60 % of the HBM roofline ⇔ 1.09·10^11 tests/s): exceeded
 ≈4× on executed tests and ≈50× on decided pairs.  Progression within the round (same workload, step
-time): 1198 → 649 → 576 → 288 → 138 → 127 → 117 → 109 → 97 ms (`profiles/README.md`, `DESIGN.md` §4).
+time): 1198 → 649 → 576 → 288 → 138 → 127 → 117 → 109 → 97 → 95 ms (`profiles/README.md`, `DESIGN.md` §4).
 '''
 k=json.load(open('/root/repo/profiles/r1_kernels.json'))
 lines=["## 6. Per-kernel timings (round 1, `tools/bench_kernels.py`, `profiles/r1_kernels.json`)","",
