@@ -184,3 +184,68 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(DrtTracePathCandidates, TraceImpl,
                                   .Ret<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::S32>>()
                                   .Ret<ffi::Buffer<ffi::PRED>>());
+
+// compact trace for exhaustive searches: static capacity (an attribute), → count [1] s64,
+// index [capacity] s64, vertices [capacity,k+2,3], objects [capacity,k+2], valid [capacity] pred.
+// The caller compares count with capacity and re-traces with a larger one on overflow.
+static ffi::Error TraceValidImpl(cudaStream_t stream, ffi::ScratchAllocator scratch,
+                                 ffi::Buffer<ffi::F32> vertices, ffi::Buffer<ffi::S32> triangles,
+                                 ffi::Buffer<ffi::U8> mask, ffi::Buffer<ffi::F32> tx,
+                                 ffi::Buffer<ffi::F32> rx, ffi::Buffer<ffi::S32> candidates,
+                                 bool assume_quads, float epsilon, float hit_tol, float min_len,
+                                 int64_t capacity, ffi::ResultBuffer<ffi::S64> out_count,
+                                 ffi::ResultBuffer<ffi::S64> out_index,
+                                 ffi::ResultBuffer<ffi::F32> out_vertices,
+                                 ffi::ResultBuffer<ffi::S32> out_objects,
+                                 ffi::ResultBuffer<ffi::PRED> out_valid) {
+    const int64_t V = vertices.dimensions()[0], T = triangles.dimensions()[0];
+    const size_t ws_bytes = drt_trace_valid_workspace_bytes(T, capacity);
+    auto ws = scratch.Allocate(ws_bytes);
+    if (!ws.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "trace workspace");
+    const uint8_t *m = mask.element_count() ? mask.typed_data() : nullptr;
+    return Check(drt_trace_valid_path_candidates(
+        stream, V, T, vertices.typed_data(), triangles.typed_data(), m, assume_quads ? 1 : 0,
+        tx.dimensions()[0], tx.typed_data(), rx.dimensions()[0], rx.typed_data(), candidates.dimensions()[0],
+        static_cast<int32_t>(candidates.dimensions()[1]), candidates.typed_data(), epsilon, hit_tol, min_len,
+        capacity, *ws, ws_bytes, out_count->typed_data(), out_index->typed_data(), out_vertices->typed_data(),
+        out_objects->typed_data(), reinterpret_cast<uint8_t *>(out_valid->typed_data())));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DrtTraceValidPathCandidates, TraceValidImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Ctx<ffi::ScratchAllocator>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Attr<bool>("assume_quads")
+                                  .Attr<float>("epsilon")
+                                  .Attr<float>("hit_tol")
+                                  .Attr<float>("min_len")
+                                  .Attr<int64_t>("capacity")
+                                  .Ret<ffi::Buffer<ffi::S64>>()
+                                  .Ret<ffi::Buffer<ffi::S64>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::S32>>()
+                                  .Ret<ffi::Buffer<ffi::PRED>>());
+
+// candidates start .. start+count-1 of the complete graph, decoded on the device: replaces the host
+// DFS + host→device copy of ExhaustivePathTracer.generate_path_candidates (_solvers.py:803-848)
+static ffi::Error CompleteGraphCandidatesImpl(cudaStream_t stream, int64_t num_nodes, int64_t start,
+                                              int64_t stride_multiplier,
+                                              ffi::ResultBuffer<ffi::S32> out) {
+    return Check(drt_complete_graph_candidates(stream, num_nodes, static_cast<int32_t>(out->dimensions()[1]),
+                                               start, out->dimensions()[0],
+                                               static_cast<int32_t>(stride_multiplier), out->typed_data()));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DrtCompleteGraphCandidates, CompleteGraphCandidatesImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Attr<int64_t>("num_nodes")
+                                  .Attr<int64_t>("start")
+                                  .Attr<int64_t>("stride_multiplier")
+                                  .Ret<ffi::Buffer<ffi::S32>>());
