@@ -71,6 +71,11 @@ PROTOTYPES: dict[str, tuple] = {
     "drt_ray_intersect_any_triangle_smooth": (C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, f32, f32, ptr]),
     "drt_consecutive_vertices_are_on_same_side_of_mirror_smooth": (
         C.c_int, [ptr, i32, p_i64, i32, ptr, p_i64, ptr, p_i64, ptr, p_i64, f32, ptr]),
+    "drt_trace_smooth_workspace_bytes": (size_t, [i64, i64, i64, i64]),
+    "drt_trace_path_candidates_smooth": (
+        C.c_int,
+        [ptr, i64, i64, ptr, ptr, ptr, i32, i64, ptr, i64, ptr, i64, i32, ptr, f32, f32, f32, f32, ptr, size_t,
+         ptr, ptr, ptr]),
     "drt_bvh_bytes": (size_t, [i64]),
     "drt_bvh_workspace_bytes": (size_t, [i64]),
     "drt_bvh_build": (C.c_int, [ptr, i64, ptr, f32, ptr, size_t, ptr]),

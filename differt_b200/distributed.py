@@ -143,6 +143,8 @@ def fill_record(record: GatherRecord, paths, num_global: int, start: int) -> Non
     v = paths.vertices.detach().reshape(P, k + 2, 3)
     o = paths.objects.reshape(P, k + 2)
     m = paths.mask.reshape(P)
+    if m.dtype.is_floating_point:  # relaxed trace: confidence >= threshold
+        m = m >= paths.confidence_threshold
     m = m.view(torch.uint8) if m.dtype == torch.bool else m
     dev = v.device
     ws = torch.empty(max(lib.drt_compact_workspace_bytes(P), 1), dtype=torch.uint8, device=dev)

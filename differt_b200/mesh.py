@@ -226,7 +226,7 @@ class TracedPaths:
 
     vertices: torch.Tensor           # [*batch, k+2, 3] f32
     objects: torch.Tensor            # [*batch, k+2] i32
-    mask: torch.Tensor               # [*batch] bool
+    mask: torch.Tensor               # [*batch] bool (float confidence with smoothing_factor)
     interaction_types: torch.Tensor  # [*batch, k] i32
     confidence_threshold: float = 0.5
     stats: dict | None = None
@@ -245,9 +245,16 @@ class TracedPaths:
             interaction_types=self.interaction_types.reshape(*batch, k),
         )
 
+    def _valid(self) -> torch.Tensor:
+        """Boolean validity: a float mask (relaxed trace) is a confidence, valid when
+        ``>= confidence_threshold`` (``_paths.py:101-103, 270-283``); NaN is never valid."""
+        if self.mask.dtype == torch.bool:
+            return self.mask
+        return self.mask >= self.confidence_threshold
+
     @property
     def num_valid_paths(self) -> int:
-        return int(self.mask.sum().item())
+        return int(self._valid().sum().item())
 
     def masked(self) -> "TracedPaths":
         """Keep the valid paths only, flattened in row-major order (reference ``_paths.py:299-328``).
@@ -260,7 +267,7 @@ class TracedPaths:
         dev = self.vertices.device
         v = self.vertices.detach().reshape(P, k + 2, 3).contiguous()
         o = self.objects.reshape(P, k + 2).contiguous()
-        m = self.mask.reshape(P).to(torch.uint8).contiguous()
+        m = self._valid().reshape(P).to(torch.uint8).contiguous()
         count = torch.zeros(1, dtype=torch.int64, device=dev)
         ws = torch.empty(max(lib.drt_compact_workspace_bytes(P), 1), dtype=torch.uint8, device=dev)
         index = torch.empty(P, dtype=torch.int64, device=dev)

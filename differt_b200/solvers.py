@@ -86,8 +86,6 @@ def trace_path_candidates(
     on the device (no host read), and an event pair is recorded around the blockage kernel
     (``DRT_TRACE_PROFILE``).
     """
-    if smoothing_factor is not None:
-        raise NotImplementedError("smoothing_factor is not supported by the CUDA path (SURVEY.md §8a)")
     del batch_size
     pl = Placement()
     pl.device = mesh.vertices.device
@@ -103,6 +101,30 @@ def trace_path_candidates(
     T = mesh.num_triangles
     out_v = torch.empty((ntx, nrx, C, k + 2, 3), dtype=torch.float32, device=dev)
     out_o = torch.empty((ntx, nrx, C, k + 2), dtype=torch.int32, device=dev)
+    if interaction_types is not None:
+        it = pl.put(interaction_types, torch.int32).expand(ntx, nrx, C, k)
+    else:
+        it = torch.zeros((1, 1, 1, 1), dtype=torch.int32, device=dev).expand(ntx, nrx, C, k)
+    if smoothing_factor is not None:
+        # relaxed validation (_solvers.py:599-713): float mask in [0, 1], forward only
+        if torch.is_grad_enabled() and any(x.requires_grad for x in (mesh.vertices, tx, rx)):
+            raise NotImplementedError("gradients through the relaxed trace are not built (DESIGN.md §6b)")
+        out_f = torch.empty((ntx, nrx, C), dtype=torch.float32, device=dev)
+        ws = torch.empty(max(lib.drt_trace_smooth_workspace_bytes(T, ntx, nrx, C), 1), dtype=torch.uint8, device=dev)
+        mask_u8 = mesh._mask_u8()  # named: must outlive the call
+        check(
+            lib.drt_trace_path_candidates_smooth(
+                stream_ptr(), mesh.vertices.shape[0], T, ptr(mesh.vertices.detach()), ptr(mesh.triangles),
+                ptr(mask_u8), int(mesh.assume_quads), ntx, ptr(tx.detach()), nrx, ptr(rx.detach()),
+                C, k, ptr(cand),
+                10.0 * F32_EPS if epsilon is None else float(epsilon),
+                100.0 * F32_EPS if hit_tol is None else float(hit_tol),
+                10.0 * F32_EPS if min_len is None else float(min_len),
+                float(smoothing_factor), ptr(ws), ws.numel(), ptr(out_v), ptr(out_o), ptr(out_f),
+            )
+        )
+        return TracedPaths(vertices=out_v, objects=out_o, mask=out_f, interaction_types=it,
+                           confidence_threshold=confidence_threshold)
     out_m = torch.empty((ntx, nrx, C), dtype=torch.uint8, device=dev)
     want_stats = with_stats or _stats_accumulate is not None
     stats = torch.zeros(4, dtype=torch.int64, device=dev) if want_stats else None
@@ -122,10 +144,6 @@ def trace_path_candidates(
     )
     if torch.is_grad_enabled() and any(x.requires_grad for x in (mesh.vertices, tx, rx)):
         out_v = _TraceVertices.apply(mesh.vertices, tx, rx, mesh.triangles, cand, out_v)
-    if interaction_types is not None:
-        it = pl.put(interaction_types, torch.int32).expand(ntx, nrx, C, k)
-    else:
-        it = torch.zeros((1, 1, 1, 1), dtype=torch.int32, device=dev).expand(ntx, nrx, C, k)
     paths = TracedPaths(
         vertices=out_v,
         objects=out_o,

@@ -399,8 +399,10 @@ def trace_path_candidates(
     hit_tol=None,
     min_len=None,
     stages=False,
+    smoothing_factor=None,
 ):
-    """``_solvers.py:514-770`` (non-smoothing branch), blockage with the pure-JAX any-hit.
+    """``_solvers.py:514-770``, blockage with the pure-JAX any-hit.  With ``smoothing_factor`` the
+    relaxed branch (``:599-713``): ``mask`` is a float in [0, 1] (NaN where the reference's is).
 
     Returns ``(vertices [Ntx,Nrx,C,k+2,3] f32, objects [Ntx,Nrx,C,k+2] i32, mask [Ntx,Nrx,C] bool)``;
     with ``stages=True`` also a dict of the five intermediate masks.
@@ -432,6 +434,9 @@ def trace_path_candidates(
         paths = image_method(tx[:, None, None, :], rx[None, :, None, :], mirror_v, mirror_n)
         full = assemble_path(tx[:, None, None, :], paths, rx[None, :, None, :])
 
+    if smoothing_factor is not None:
+        return _trace_smooth_tail(full, tv, mirror_v, mirror_n, tri_all, mask, active_rays, cand, assume_quads,
+                                  epsilon, hit_tol, ml, smoothing_factor)
     with np.errstate(all="ignore"):
         ro = full[..., :-1, :]
         rd = np.diff(full, axis=-2)
@@ -841,6 +846,42 @@ def ray_intersect_any_triangle_smooth(ray_origins, ray_directions, tri, active=N
     if active is not None:
         term = np.where(np.asarray(active, bool), term, F32(0))
     return np.minimum(term.sum(axis=-1, dtype=np.float32), F32(1.0)).astype(np.float32)
+
+
+def _trace_smooth_tail(full, tv, mirror_v, mirror_n, tri_all, mask, active_rays, cand, assume_quads, epsilon,
+                       hit_tol, ml, alpha):
+    """Steps 3.1-3.5 of ``_trace_path_candidates`` with smoothing (``_solvers.py:599-713``): AND → min,
+    OR → max, NOT x → 1 - x; the hard ``is_finite`` enters the min as 0 / 1."""
+    ntx, nrx, C = full.shape[:3]
+    k = cand.shape[1]
+    with np.errstate(all="ignore"):
+        ro = full[..., :-1, :]
+        rd = np.diff(full, axis=-2)
+        nmin = lambda x, init: np.minimum(x.min(axis=-1, initial=np.inf), F32(init)) if x.shape[-1] else np.full(x.shape[:-1], F32(init))  # noqa: E731
+        nmax = lambda x, init: np.maximum(x.max(axis=-1, initial=-np.inf), F32(init)) if x.shape[-1] else np.full(x.shape[:-1], F32(init))  # noqa: E731
+        if assume_quads:
+            h = ray_intersect_triangle_smooth(np.repeat(ro[..., :-1, :], 2, axis=-2),
+                                              np.repeat(rd[..., :-1, :], 2, axis=-2), tv, epsilon=epsilon,
+                                              smoothing_factor=alpha)[1]
+            inside = nmin(nmax(h.reshape(ntx, nrx, C, k, 2), 0.0), 1.0)
+        else:
+            inside = nmin(ray_intersect_triangle_smooth(ro[..., :-1, :], rd[..., :-1, :], tv, epsilon=epsilon,
+                                                        smoothing_factor=alpha)[1], 1.0)
+        same = nmin(consecutive_vertices_are_on_same_side_of_mirror_smooth(full, mirror_v, mirror_n, alpha), 1.0)
+        blocked = nmax(ray_intersect_any_triangle_smooth(ro, rd, tri_all, mask, epsilon=epsilon, hit_tol=hit_tol,
+                                                         smoothing_factor=alpha), 0.0)
+        too_small = nmax(smoothing_function(ml - dot3(rd, rd), alpha), 0.0)
+        finite = np.isfinite(full).all(axis=(-1, -2))
+        full = np.where(finite[..., None, None], full, F32(0.0)).astype(np.float32)
+        soft = np.stack([inside, same, F32(1) - blocked, F32(1) - too_small, finite.astype(np.float32)], axis=-1)
+        soft = soft.min(axis=-1)  # np.min propagates NaN like jnp.min
+        if active_rays is not None:
+            soft = soft * active_rays[None, None, :].astype(np.float32)
+    objects = np.empty((ntx, nrx, C, k + 2), dtype=np.int32)
+    objects[..., 0] = np.arange(ntx, dtype=np.int32)[:, None, None]
+    objects[..., 1:-1] = cand[None, None].astype(np.int32)
+    objects[..., -1] = np.arange(nrx, dtype=np.int32)[None, :, None]
+    return full, objects, soft.astype(np.float32)
 
 
 def consecutive_vertices_are_on_same_side_of_mirror_smooth(vertices, mirror_vertices, mirror_normals,

@@ -540,8 +540,6 @@ def test_k6_edge_cases(drt):
     # empty mesh, order 0: always line of sight
     empty = drt.Mesh.from_numpy(np.empty((0, 3), np.float32), np.empty((0, 3), np.int32))
     assert drt.trace_paths(empty, tx, rx, 0).mask.all()
-    with pytest.raises(NotImplementedError):
-        drt.trace_path_candidates(mesh, tx, rx, np.zeros((1, 1), np.int32), smoothing_factor=1.0)
 
 
 def test_k6_masked_mesh_equals_submesh(drt, two_buildings, kats):  # test_scene.py:585-647
@@ -1211,6 +1209,133 @@ def test_smoothed_primitives_match_oracle(drt, rng, alpha):
         np.testing.assert_array_equal(
             (drt.ray_intersect_any_triangle(o, d, tri, smoothing_factor=alpha) > 0.5).numpy(),
             drt.ray_intersect_any_triangle(o, d, tri).numpy())
+
+
+def _smooth_case(two_buildings, kats, order, quads, masked, rng):
+    v, t = two_buildings
+    k = kats["two_buildings_scene"]
+    tx = np.stack([np.array(k["tx"], np.float32).reshape(3), np.array([2.0, -6.0, 9.0], np.float32)])
+    rx = np.stack([np.array(k["rx"], np.float32).reshape(3), np.array([20.0, 3.0, 1.5], np.float32),
+                   np.array([-4.0, 11.0, 4.0], np.float32)])
+    T = t.shape[0]
+    if order == 0:
+        cand = np.empty((1, 0), np.int32)
+    else:
+        cand = rng.integers(0, T, size=(150, order)).astype(np.int32)
+        if quads:
+            cand -= cand % 2
+    mask = (rng.uniform(size=T) > 0.25) if masked else None
+    if quads and mask is not None:
+        mask[1::2] = mask[::2]
+    return v, t, tx, rx, cand, mask
+
+
+@pytest.mark.parametrize("alpha", [0.05, 3.0, 1000.0])
+@pytest.mark.parametrize("order", [0, 1, 2, 3])
+@pytest.mark.parametrize("quads,masked", [(False, False), (True, False), (False, True), (True, True)])
+def test_smoothed_trace_matches_oracle(drt, two_buildings, kats, rng, alpha, order, quads, masked):
+    # relaxed _trace_path_candidates (_solvers.py:599-713) on the reference's 24-triangle scene, with
+    # masks, quads and the NaNs of non-finite paths (most confidences are ~0 here: the relaxed blockage
+    # sum saturates; test_smoothed_trace_ground_and_wall covers the spread-out regime)
+    v, t, tx, rx, cand, mask = _smooth_case(two_buildings, kats, order, quads, masked, rng)
+    mesh = drt.Mesh.from_numpy(v, t, mask, assume_quads=quads)
+    got = drt.trace_path_candidates(mesh, tx, rx, cand, smoothing_factor=alpha)
+    ev, eo, em = orc.trace_path_candidates(v, t, tx, rx, cand, mask=mask, assume_quads=quads, smoothing_factor=alpha)
+    assert got.mask.dtype == torch.float32 and tuple(got.mask.shape) == em.shape
+    np.testing.assert_array_equal(bits(got.vertices.cpu().numpy()), bits(ev))
+    np.testing.assert_array_equal(got.objects.cpu().numpy(), eo)
+    gm = got.mask.cpu().numpy()
+    np.testing.assert_array_equal(np.isnan(gm), np.isnan(em))
+    np.testing.assert_allclose(gm, em, rtol=5e-5, atol=2e-6)
+    # the hard trace returns the same dense vertices / objects
+    hard = drt.trace_path_candidates(mesh, tx, rx, cand)
+    np.testing.assert_array_equal(bits(got.vertices.cpu().numpy()), bits(hard.vertices.cpu().numpy()))
+    np.testing.assert_array_equal(got.objects.cpu().numpy(), hard.objects.cpu().numpy())
+
+
+@pytest.mark.parametrize("alpha", [0.5, 4.0, 40.0])
+@pytest.mark.parametrize("order", [0, 1, 2, 3])
+@pytest.mark.parametrize("quads", [False, True])
+def test_smoothed_trace_ground_and_wall(drt, alpha, order, quads):
+    # 4 triangles (a ground quad and a wall quad): few enough that the relaxed blockage sum stays
+    # below its clip, so the confidences spread over (0, 1) and every term of the min matters
+    import itertools
+
+    v = np.array([[-10, -10, 0], [10, -10, 0], [10, 10, 0], [-10, 10, 0],
+                  [3, -4, 0], [3, 4, 0], [3, 4, 6], [3, -4, 6]], np.float32)
+    t = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7]], np.int32)
+    r = np.random.default_rng(5)
+    tx = r.uniform([-8, -8, 1], [1, 8, 8], size=(3, 3)).astype(np.float32)
+    rx = r.uniform([-8, -8, 1], [9, 8, 8], size=(40, 3)).astype(np.float32)
+    prim = range(0, 4, 2 if quads else 1)
+    cand = (np.array(list(itertools.product(prim, repeat=order)), np.int32).reshape(-1, order)
+            if order else np.empty((1, 0), np.int32))
+    for mask in (None, np.array([True, True, False, False])):
+        mesh = drt.Mesh.from_numpy(v, t, mask, assume_quads=quads)
+        got = drt.trace_path_candidates(mesh, tx, rx, cand, smoothing_factor=alpha)
+        ev, eo, em = orc.trace_path_candidates(v, t, tx, rx, cand, mask=mask, assume_quads=quads,
+                                               smoothing_factor=alpha)
+        gm = got.mask.cpu().numpy()
+        np.testing.assert_array_equal(bits(got.vertices.cpu().numpy()), bits(ev))
+        np.testing.assert_array_equal(got.objects.cpu().numpy(), eo)
+        np.testing.assert_array_equal(np.isnan(gm), np.isnan(em))
+        np.testing.assert_allclose(gm, em, rtol=5e-5, atol=2e-6)
+        assert got.num_valid_paths == int((em >= 0.5).sum()) or np.any(np.abs(em - 0.5) < 1e-4)
+        if mask is None:
+            assert np.unique(em[np.isfinite(em)]).size > 15  # a non-trivial relaxation
+
+
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_smoothed_trace_huge_slope_is_the_hard_trace(drt, two_buildings, kats, order):
+    # in the spirit of the reference's check (test_scene.py:383-440, test_utils.py:642): a huge slope
+    # reproduces the hard decisions
+    v, t = two_buildings
+    k = kats["two_buildings_scene"]
+    tx, rx = np.array(k["tx"], np.float32), np.array(k["rx"], np.float32)
+    mesh = drt.Mesh.from_numpy(v, t)
+    hard = drt.trace_paths(mesh, tx, rx, order)
+    for alpha in (1e8, 1e12):
+        soft = drt.trace_paths(mesh, tx, rx, order, smoothing_factor=alpha)
+        m = soft.mask.cpu().numpy()
+        np.testing.assert_array_equal(m >= 0.5, hard.mask.cpu().numpy())
+        # NaN (paths through parallel mirrors: non-finite vertices) counts as invalid, as in the reference
+        np.testing.assert_allclose(np.nan_to_num(m, nan=0.0), hard.mask.cpu().numpy().astype(np.float32), atol=1e-6)
+        assert soft.num_valid_paths == hard.num_valid_paths
+        a, b = soft.masked(), hard.masked()
+        np.testing.assert_array_equal(a.objects.cpu().numpy(), b.objects.cpu().numpy())
+        np.testing.assert_array_equal(bits(a.vertices.cpu().numpy()), bits(b.vertices.cpu().numpy()))
+    # Scene front end, chunked and not (ExhaustivePathTracer(chunk_size, smoothing_factor))
+    scene = drt.Scene(mesh=mesh, transmitters=torch.from_numpy(tx).cuda(), receivers=torch.from_numpy(rx).cuda())
+    whole = scene.trace_paths(order, smoothing_factor=1e8)
+    assert whole.mask.dtype == torch.float32 and whole.num_valid_paths == hard.num_valid_paths
+    if order > 0:
+        n = sum(p.num_valid_paths for p in scene.trace_paths(order, chunk_size=100, smoothing_factor=1e8))
+        assert n == hard.num_valid_paths
+
+
+def test_smoothed_trace_edge_cases(drt, two_buildings, rng):
+    v, t = two_buildings
+    mesh = drt.Mesh.from_numpy(v, t)
+    tx, rx = np.array([[0.0, 0.0, 30.0]], np.float32), np.array([[5.0, 5.0, 1.0], [np.inf, 0.0, 1.0]], np.float32)
+    # zero candidates, zero receivers
+    p = drt.trace_path_candidates(mesh, tx, rx, np.empty((0, 2), np.int32), smoothing_factor=2.0)
+    assert tuple(p.mask.shape) == (1, 2, 0) and p.mask.dtype == torch.float32
+    p = drt.trace_path_candidates(mesh, tx, rx[:0], np.zeros((3, 1), np.int32), smoothing_factor=2.0)
+    assert tuple(p.vertices.shape) == (1, 0, 3, 3, 3)
+    # a non-finite receiver: vertices zeroed like the hard trace, never valid (0 or NaN as in the reference)
+    cand = rng.integers(0, t.shape[0], size=(20, 2)).astype(np.int32)
+    p = drt.trace_path_candidates(mesh, tx, rx, cand, smoothing_factor=50.0)
+    assert not (p.mask[0, 1] >= 0.5).any() and (p.vertices[0, 1] == 0).all()
+    ev, eo, em = orc.trace_path_candidates(v, t, tx, rx, cand, smoothing_factor=50.0)
+    np.testing.assert_array_equal(np.isnan(p.mask.cpu().numpy()), np.isnan(em))
+    np.testing.assert_allclose(p.mask.cpu().numpy(), em, rtol=5e-5, atol=2e-6)
+    # empty mesh at order 0: nothing blocks; line of sight only limited by the too-small term
+    empty = drt.Mesh.from_numpy(np.empty((0, 3), np.float32), np.empty((0, 3), np.int32))
+    p = drt.trace_paths(empty, tx, rx[:1], 0, smoothing_factor=10.0)
+    e = orc.trace_path_candidates(np.empty((0, 3), np.float32), np.empty((0, 3), np.int32), tx, rx[:1],
+                                  np.empty((1, 0), np.int32), smoothing_factor=10.0)[2]
+    np.testing.assert_allclose(p.mask.cpu().numpy(), e, rtol=1e-5)
+    # gradients of the relaxed trace are not built: loud, not silent
+    txg = torch.from_numpy(tx).cuda().requires_grad_(True)
     with pytest.raises(NotImplementedError):
-        m = drt.Mesh.from_numpy(tri.reshape(-1, 3), np.arange(900, dtype=np.int32).reshape(300, 3))
-        drt.trace_path_candidates(m, o[:1], o[1:2], np.zeros((1, 1), np.int32), smoothing_factor=alpha)
+        drt.trace_path_candidates(mesh, txg, rx[:1], cand, smoothing_factor=1.0)

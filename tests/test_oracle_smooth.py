@@ -1,0 +1,57 @@
+"""CPU checks of the relaxed (smoothing_factor) restatement of the trace step
+(reference ``_solvers.py:599-713``): it has no golden vector in the reference's tests beyond "a huge
+slope reproduces the hard decisions" (``test_utils.py:642, 710``; ``test_image_method.py:252``;
+``test_scene.py:383-440``), so that is what pins it, together with structural properties."""
+
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import differt_oracle as orc
+
+
+def _all_candidates(T, order, step=1):
+    if order == 0:
+        return np.empty((1, 0), np.int32)
+    return np.array(list(itertools.product(range(0, T, step), repeat=order)), np.int32).reshape(-1, order)
+
+
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_huge_slope_reproduces_hard_trace(two_buildings, kats, order):
+    v, t = two_buildings
+    k = kats["two_buildings_scene"]
+    tx, rx = np.array(k["tx"], np.float32), np.array(k["rx"], np.float32)
+    cand = _all_candidates(t.shape[0], order)
+    hv, ho, hm = orc.trace_path_candidates(v, t, tx, rx, cand)
+    sv, so, sm = orc.trace_path_candidates(v, t, tx, rx, cand, smoothing_factor=1e8)
+    assert sm.dtype == np.float32 and sm.shape == hm.shape
+    np.testing.assert_array_equal(sm >= 0.5, hm)
+    np.testing.assert_array_equal(sv.view(np.uint32), hv.view(np.uint32))
+    np.testing.assert_array_equal(so, ho)
+
+
+@pytest.mark.parametrize("quads", [False, True])
+def test_relaxed_mask_properties(quads):
+    v = np.array([[-10, -10, 0], [10, -10, 0], [10, 10, 0], [-10, 10, 0],
+                  [3, -4, 0], [3, 4, 0], [3, 4, 6], [3, -4, 6]], np.float32)
+    t = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7]], np.int32)
+    r = np.random.default_rng(5)
+    tx = r.uniform([-8, -8, 1], [1, 8, 8], size=(2, 3)).astype(np.float32)
+    rx = r.uniform([-8, -8, 1], [9, 8, 8], size=(10, 3)).astype(np.float32)
+    cand = _all_candidates(4, 2, 2 if quads else 1)
+    _, _, m = orc.trace_path_candidates(v, t, tx, rx, cand, assume_quads=quads, smoothing_factor=4.0)
+    assert m.shape == (2, 10, cand.shape[0]) and np.all((m >= 0) & (m <= 1))
+    assert np.unique(m).size > 10
+    # masking out the wall: candidates through it get confidence exactly 0, the others can only gain
+    mask = np.array([True, True, False, False])
+    _, _, mm = orc.trace_path_candidates(v, t, tx, rx, cand, mask=mask, assume_quads=quads, smoothing_factor=4.0)
+    uses_wall = (cand >= 2).any(axis=1)
+    assert np.all(mm[..., uses_wall] == 0)
+    assert np.all(mm[..., ~uses_wall] >= m[..., ~uses_wall] - 1e-7)
+    # a masked mesh equals the sub-mesh for candidates that avoid the masked triangles
+    _, _, ms = orc.trace_path_candidates(v[:4], t[:2], tx, rx, cand[~uses_wall], assume_quads=quads,
+                                         smoothing_factor=4.0)
+    np.testing.assert_allclose(mm[..., ~uses_wall], ms, rtol=1e-6)

@@ -37,6 +37,8 @@ comp = drt.trace_valid_path_candidates(mesh, tx, rx, scenes.complete_graph_candi
 print("compact", comp.num_valid_paths)
 print("bvh", int(mesh.ray_intersect_any_triangle(o, d, accel="bvh").sum()), int((mesh.first_triangle_hit_by_ray(o, d, accel="bvh")[0] >= 0).sum()))
 print("smooth", float(drt.ray_intersect_any_triangle(o[:500], d[:500], tri, smoothing_factor=5.0).sum()))
+sm = drt.trace_path_candidates(mesh, tx, rx[:4], scenes.sampled_candidates(t.shape[0], 2, 37), smoothing_factor=5.0)
+print("smooth trace", float(torch.nan_to_num(sm.mask).sum()))
 lp = drt.launch_paths(mesh, tx, rx[:8], 1, num_rays=2000, max_dist=1.0)
 print("sbr", int(lp.masks.sum()), "mlm", int((drt.compute_tx_mlm(mesh, tx, max_order=1, dim_x=4, dim_y=4, num_rays=2000, receiver_height=1.5, min_x=0.0, max_x=300.0, min_y=0.0, max_y=300.0) != 0).sum()))
 paths, valid = trace_path_candidates_sharded(mesh, tx, rx, torch.from_numpy(scenes.complete_graph_candidates(t.shape[0], 1)).cuda())
