@@ -76,6 +76,11 @@ PROTOTYPES: dict[str, tuple] = {
         C.c_int,
         [ptr, i64, i64, ptr, ptr, ptr, i32, i64, ptr, i64, ptr, i64, i32, ptr, f32, f32, f32, f32, ptr, size_t,
          ptr, ptr, ptr]),
+    "drt_trace_smooth_vjp_workspace_bytes": (size_t, [i64, i64, i64, i64, i64, i32]),
+    "drt_trace_path_candidates_smooth_vjp": (
+        C.c_int,
+        [ptr, i64, i64, ptr, ptr, ptr, i32, i64, ptr, i64, ptr, i64, i32, ptr, f32, f32, f32, f32, ptr, ptr, ptr,
+         ptr, ptr, size_t, ptr, ptr, ptr]),
     "drt_bvh_bytes": (size_t, [i64]),
     "drt_bvh_workspace_bytes": (size_t, [i64]),
     "drt_bvh_build": (C.c_int, [ptr, i64, ptr, f32, ptr, size_t, ptr]),

@@ -4,8 +4,8 @@
 // (ray_intersect_any_triangle), _solver_image_method.py:448-454 (same side of mirrors).
 // Comparisons become sigmoids, AND becomes min, the OR over triangles becomes a sum clipped at 1.
 // Outputs are floats in [0, 1]; with the transcendental involved parity is to tolerance (1e-5), not
-// bit-exact.  The smoothed trace (_solvers.py:599-713) is the last entry point of this file; the
-// gradients of the relaxed outputs are not built.
+// bit-exact.  The relaxed trace (_solvers.py:599-713) and its reverse mode are the last two entry
+// points of this file.
 #include "common.cuh"
 #include "image_core.cuh"
 
@@ -245,6 +245,319 @@ static int launch_trace_smooth(const SmoothTraceArgs &a, bool quads, cudaStream_
     return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
 }
 
+// ------------------------------------------------------------------------------------------------
+// reverse mode of the relaxed trace (what jax.grad gives on _solvers.py:576-713)
+// ------------------------------------------------------------------------------------------------
+// min / max route the cotangent to their (first) extremal argument — JAX shares it between exact
+// ties, which only happen between saturated terms whose sigmoid derivative is 0 anyway; the
+// same-side term is a function of signs (zero gradient); the clip of the blockage sum passes the
+// cotangent while the sum is below 1.  Non-finite paths and NaN confidences get a zero gradient.
+
+struct MtGrad {  // cotangents of one relaxed Möller–Trumbore evaluation
+    float3 o, d, v0, e1, e2;
+};
+
+__device__ __forceinline__ void atomic_add3s(float *p, float3 v) {
+    if (v.x != 0.f) atomicAdd(p, v.x);
+    if (v.y != 0.f) atomicAdd(p + 1, v.y);
+    if (v.z != 0.f) atomicAdd(p + 2, v.z);
+}
+
+// g: cotangent of hit (blockage == false) or of min(hit, sigmoid((thr - t) alpha)) (blockage == true).
+// Returns false when nothing flows (saturated, a == 0 or NaN).
+__device__ __forceinline__ bool mt_smooth_grad(const float3 o, const float3 d, const Tri &tr, const float eps,
+                                               const float alpha, const float thr, const bool blockage,
+                                               const float g, MtGrad &out) {
+    const float3 h = cross3(d, tr.e2);
+    const float a = dot3(h, tr.e1);
+    if (a == 0.0f) return false;  // where(a == 0, inf, a): constant branch
+    const float f = __frcp_rn(a);
+    const float3 s = sub3(o, tr.v0);
+    const float su = dot3(s, h);
+    const float u = f * su;
+    const float3 q = cross3(s, tr.e1);
+    const float qv = dot3(q, d);
+    const float v = f * qv;
+    const float qt = dot3(q, tr.e2);
+    const float t = f * qt;
+    float best = smooth(fabsf(a) - eps, alpha);
+    int which = 0;
+    bool nan = best != best;
+#define DRT_CONSIDER(val, id)            \
+    {                                    \
+        const float x_ = (val);          \
+        nan = nan || (x_ != x_);         \
+        if (x_ < best) {                 \
+            best = x_;                   \
+            which = (id);                \
+        }                                \
+    }
+    DRT_CONSIDER(smooth(u - 0.0f, alpha), 1)
+    DRT_CONSIDER(smooth(1.0f - u, alpha), 2)
+    DRT_CONSIDER(1.0f, 7)
+    DRT_CONSIDER(smooth(v - 0.0f, alpha), 3)
+    DRT_CONSIDER(smooth(1.0f - (u + v), alpha), 4)
+    DRT_CONSIDER(smooth(t - eps, alpha), 5)
+    if (blockage) DRT_CONSIDER(smooth(thr - t, alpha), 6)
+#undef DRT_CONSIDER
+    if (nan || which == 7) return false;
+    const float ds = g * alpha * best * (1.0f - best);  // d sigmoid(x alpha) / dx, times the cotangent
+    if (ds == 0.0f || ds != ds) return false;
+    float ga = 0.f, gu = 0.f, gv = 0.f, gt = 0.f;
+    switch (which) {
+        case 0: ga = a < 0.0f ? -ds : ds; break;
+        case 1: gu = ds; break;
+        case 2: gu = -ds; break;
+        case 3: gv = ds; break;
+        case 4: gu = -ds; gv = -ds; break;
+        case 5: gt = ds; break;
+        default: gt = -ds; break;
+    }
+    const float gf = gu * su + gv * qv + gt * qt;
+    const float gsu = gu * f, gqv = gv * f, gqt = gt * f;
+    ga -= gf * f * f;                                            // f = 1 / a
+    const float3 gq = add3(scale3(d, gqv), scale3(tr.e2, gqt));  // qv = q.d, qt = q.e2
+    const float3 gh = add3(scale3(s, gsu), scale3(tr.e1, ga));   // su = s.h, a = h.e1
+    const float3 gs = add3(scale3(h, gsu), cross3(tr.e1, gq));   // q = s x e1
+    out.o = gs;                                                  // s = o - v0
+    out.v0 = make_float3(-gs.x, -gs.y, -gs.z);
+    out.d = add3(scale3(q, gqv), cross3(tr.e2, gh));             // h = d x e2
+    out.e1 = add3(scale3(h, ga), cross3(gq, s));
+    out.e2 = add3(scale3(q, gqt), cross3(gh, d));
+    return true;
+}
+
+struct SmoothVjpArgs {
+    SmoothTraceArgs f;          // the forward's arguments (out_* unused except out_mask = saved confidences)
+    const int32_t *triangles;   // [T, 3]
+    int64_t V;
+    const float *g_mask;        // [P]
+    const float *g_out_vertices;  // nullable [P, k+2, 3]: cotangent of the dense path vertices
+    float *g_full;              // [P, k+2, 3] workspace: total cotangent of the path vertices
+    float *g_verts_direct;      // [V, 3] workspace: cotangent reaching the mesh through triangle geometry
+};
+
+// scatter of (v0, e1, e2) cotangents of triangle `tri` onto its three mesh vertices
+__device__ __forceinline__ void scatter_triangle_grad(const SmoothVjpArgs &a, int64_t tri, const MtGrad &m) {
+    const int32_t *ix = a.triangles + 3 * tri;
+    const int64_t i0 = min(max(int64_t(ix[0]), int64_t(0)), a.V - 1);
+    const int64_t i1 = min(max(int64_t(ix[1]), int64_t(0)), a.V - 1);
+    const int64_t i2 = min(max(int64_t(ix[2]), int64_t(0)), a.V - 1);
+    atomic_add3s(a.g_verts_direct + 3 * i0, sub3(sub3(m.v0, m.e1), m.e2));  // e1 = v1 - v0, e2 = v2 - v0
+    atomic_add3s(a.g_verts_direct + 3 * i1, m.e1);
+    atomic_add3s(a.g_verts_direct + 3 * i2, m.e2);
+}
+
+// one thread per path: recompute the forward's stage terms, find which one the confidence came from,
+// write the total cotangent of the path vertices (downstream + stage) and flag the paths whose
+// confidence came from the blockage term for the warp-per-path kernel below.
+template <int K, bool QUADS>
+__global__ void __launch_bounds__(128) trace_smooth_vjp_stage_kernel(const SmoothVjpArgs a) {
+    constexpr int KK = K > 0 ? K : 1;
+    constexpr int NT = QUADS ? 2 : 1;
+    const SmoothTraceArgs &fa = a.f;
+    const int64_t p = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (p >= fa.P) return;
+    const int64_t c = p % fa.C, pair = p / fa.C;
+    const int64_t irx = pair % fa.nrx, itx = pair / fa.nrx;
+
+    float3 mv[KK], mn[KK];
+    Tri tri[KK][NT];
+    int32_t ti[KK];
+    bool active = true;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        int32_t t = fa.cand[c * K + i];
+        t = min(max(t, 0), int32_t(fa.T - (QUADS ? 2 : 1)));
+        ti[i] = t;
+#pragma unroll
+        for (int q = 0; q < NT; ++q) {
+            const float4 ta = fa.pack[t + q].a, tb = fa.pack[t + q].b, tc = fa.pack[t + q].c;
+            tri[i][q] = unpack(ta, tb, tc);
+            if (q == 0) {
+                mv[i] = make_float3(ta.x, ta.y, ta.z);
+                mn[i] = make_float3(tc.y, tc.z, tc.w);
+            }
+            if (fa.tri_mask != nullptr) active = active && fa.tri_mask[t + q] != 0;
+        }
+    }
+    float3 full[K + 2];
+    full[0] = ld3(fa.tx + 3 * itx);
+    full[K + 1] = ld3(fa.rx + 3 * irx);
+    image_method_path<K>(full, mv, mn);
+
+    float inside = 1.0f, same = 1.0f, small = 0.0f;
+    int inside_i = -1, inside_q = 0, small_s = -1;
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i <= K; ++i) {
+        const float3 o = full[i];
+        const float3 d = sub3(full[i + 1], full[i]);
+        const float sm = smooth(fa.min_len - dot3(d, d), fa.alpha);
+        if (sm > small) {
+            small = sm;
+            small_s = i;
+        }
+        if (sm != sm) small = sm;
+        if (i < K) {
+            float tt;
+            float hit = mt_smooth(o, d, tri[i][0], fa.eps, fa.alpha, tt);
+            int q = 0;
+            if (QUADS) {
+                const float h1 = mt_smooth(o, d, tri[i][NT - 1], fa.eps, fa.alpha, tt);
+                if (h1 > hit) q = 1;
+                hit = nanmax(nanmax(hit, h1), 0.0f);
+            }
+            if (hit < inside) {
+                inside = hit;
+                inside_i = i;
+                inside_q = q;
+            }
+            if (hit != hit) inside = hit;
+            const float dp = dot3(sub3(full[i], mv[i]), mn[i]);
+            const float dn = dot3(sub3(full[i + 2], mv[i]), mn[i]);
+            const float sp = dp != dp ? dp : float(dp > 0.0f) - float(dp < 0.0f);
+            const float sn = dn != dn ? dn : float(dn > 0.0f) - float(dn < 0.0f);
+            same = nanmin(same, smooth(sp * sn, fa.alpha));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < K + 2; ++i) finite = finite && finite3(full[i]);
+
+    float3 gfull[K + 2];
+#pragma unroll
+    for (int i = 0; i < K + 2; ++i)
+        gfull[i] = a.g_out_vertices ? ld3(a.g_out_vertices + (p * (K + 2) + i) * 3) : make_float3(0.f, 0.f, 0.f);
+
+    const float g = a.g_mask[p];
+    const float m_stage = nanmin(nanmin(inside, same), 1.0f - small);
+    const float conf = fa.out_mask[p];  // the forward's min(stage, 1 - blocked) * active
+    uint8_t to_blockage = 0;
+    if (finite && active && g != 0.0f && g == g && m_stage == m_stage && conf == conf) {
+        if (conf < m_stage) {
+            to_blockage = 1;  // 1 - blocked is the minimum
+        } else if (inside <= same && inside <= 1.0f - small) {
+            if (inside_i >= 0) {
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    if (i != inside_i) continue;
+                    MtGrad mg;
+                    const float3 o = full[i], d = sub3(full[i + 1], full[i]);
+                    if (mt_smooth_grad(o, d, tri[i][(QUADS && inside_q) ? NT - 1 : 0], fa.eps, fa.alpha, 0.0f, false,
+                                       g, mg)) {
+                        gfull[i] = add3(gfull[i], sub3(mg.o, mg.d));  // d = full[i+1] - full[i]
+                        gfull[i + 1] = add3(gfull[i + 1], mg.d);
+                        scatter_triangle_grad(a, ti[i] + ((QUADS && inside_q) ? 1 : 0), mg);
+                    }
+                }
+            }
+        } else if (!(same <= 1.0f - small)) {
+            // 1 - too_small is the minimum: d(1 - sigmoid((min_len - d.d) alpha)) = 2 alpha s (1 - s) d
+#pragma unroll
+            for (int i = 0; i <= K; ++i) {
+                if (i != small_s) continue;
+                const float3 d = sub3(full[i + 1], full[i]);
+                const float3 gd = scale3(d, 2.0f * g * fa.alpha * small * (1.0f - small));
+                gfull[i] = sub3(gfull[i], gd);
+                gfull[i + 1] = add3(gfull[i + 1], gd);
+            }
+        }
+    }
+    a.f.flags[p] = to_blockage;
+    float *gf = a.g_full + p * (K + 2) * 3;
+#pragma unroll
+    for (int i = 0; i < K + 2; ++i) st3(gf + 3 * i, gfull[i]);
+}
+
+// one warp per flagged path: recompute the per-segment blockage sums, pick the segment the max came
+// from, and if its sum is below the clip send -g through every active triangle's term.
+template <int NSEG>
+__global__ void __launch_bounds__(256) trace_smooth_vjp_blocked_kernel(const SmoothVjpArgs a) {
+    const SmoothTraceArgs &fa = a.f;
+    const int lane = threadIdx.x & 31;
+    const int64_t p = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+    if (p >= fa.P || fa.flags[p] == 0) return;  // warp-uniform
+    const float *v = fa.out_vertices + p * (NSEG + 1) * 3;
+    float3 o[NSEG], d[NSEG];
+    float acc[NSEG];
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s) {
+        o[s] = ld3(v + 3 * s);
+        d[s] = sub3(ld3(v + 3 * s + 3), o[s]);
+        acc[s] = 0.0f;
+    }
+    for (int64_t j = lane; j < fa.T; j += 32) {
+        const float4 ra = fa.pack_active[j].a, rb = fa.pack_active[j].b, rc = fa.pack_active[j].c;
+        if (ra.x != ra.x && ra.y != ra.y && ra.z != ra.z && ra.w == 0.0f) continue;
+        const Tri tr = unpack(ra, rb, rc);
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) {
+            float t;
+            const float hit = mt_smooth(o[s], d[s], tr, fa.eps, fa.alpha, t);
+            acc[s] += nanmin(hit, smooth(fa.thr - t, fa.alpha));
+        }
+    }
+    int best_s = 0;
+    float best = -1.0f;
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s) {
+        float x = acc[s];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(kFull, x, off);
+        if (x > best) {
+            best = x;
+            best_s = s;
+        }
+    }
+    if (!(best < 1.0f)) return;  // clipped (or NaN): the cotangent stops here
+    const float g = -a.g_mask[p];  // confidence = 1 - blocked
+    const float3 os = ld3(v + 3 * best_s);
+    const float3 ds = sub3(ld3(v + 3 * best_s + 3), os);
+    float3 go = make_float3(0.f, 0.f, 0.f), gd = make_float3(0.f, 0.f, 0.f);
+    for (int64_t j = lane; j < fa.T; j += 32) {
+        const float4 ra = fa.pack_active[j].a, rb = fa.pack_active[j].b, rc = fa.pack_active[j].c;
+        if (ra.x != ra.x && ra.y != ra.y && ra.z != ra.z && ra.w == 0.0f) continue;
+        MtGrad mg;
+        if (mt_smooth_grad(os, ds, unpack(ra, rb, rc), fa.eps, fa.alpha, fa.thr, true, g, mg)) {
+            go = add3(go, mg.o);
+            gd = add3(gd, mg.d);
+            scatter_triangle_grad(a, j, mg);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        go.x += __shfl_xor_sync(kFull, go.x, off);
+        go.y += __shfl_xor_sync(kFull, go.y, off);
+        go.z += __shfl_xor_sync(kFull, go.z, off);
+        gd.x += __shfl_xor_sync(kFull, gd.x, off);
+        gd.y += __shfl_xor_sync(kFull, gd.y, off);
+        gd.z += __shfl_xor_sync(kFull, gd.z, off);
+    }
+    if (lane == 0) {  // this warp owns the path: plain read-modify-write
+        float *gf = a.g_full + (p * (NSEG + 1) + best_s) * 3;
+        const float3 g0 = add3(ld3(gf), sub3(go, gd)), g1 = add3(ld3(gf + 3), gd);
+        st3(gf, g0);
+        st3(gf + 3, g1);
+    }
+}
+
+__global__ void add_inplace_kernel(int64_t n, float *__restrict__ dst, const float *__restrict__ src) {
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
+template <int K>
+static int launch_trace_smooth_vjp(const SmoothVjpArgs &a, bool quads, cudaStream_t s) {
+    const unsigned blocks = unsigned((a.f.P + 127) / 128);
+    if (quads)
+        trace_smooth_vjp_stage_kernel<K, true><<<blocks, 128, 0, s>>>(a);
+    else
+        trace_smooth_vjp_stage_kernel<K, false><<<blocks, 128, 0, s>>>(a);
+    if (cudaGetLastError() != cudaSuccess) return DRT_ERR_CUDA;
+    if (a.f.T > 0) trace_smooth_vjp_blocked_kernel<K + 1><<<unsigned((a.f.P * 32 + 255) / 256), 256, 0, s>>>(a);
+    return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
+}
+
 static int fill_batch3(int32_t ndim, const int64_t *shape, const int64_t *s0, const int64_t *s1,
                        const int64_t *s2, Batch4 &bt, int64_t &n) {
     if (ndim < 0 || ndim > DRT_MAX_BATCH_DIMS) return DRT_ERR_UNSUPPORTED;
@@ -374,6 +687,94 @@ int drt_trace_path_candidates_smooth(drt_stream_t stream, int64_t V, int64_t T, 
         case 8: return launch_trace_smooth<8>(a, q, s);
         default: return DRT_ERR_UNSUPPORTED;
     }
+}
+
+size_t drt_trace_smooth_vjp_workspace_bytes(int64_t V, int64_t T, int64_t ntx, int64_t nrx, int64_t C,
+                                            int32_t order) {
+    if (V < 0 || T < 0 || ntx < 0 || nrx < 0 || C < 0 || order < 0) return 0;
+    const size_t P = size_t(ntx) * size_t(nrx) * size_t(C);
+    const size_t a256 = 255;
+    return 2 * drt_mesh_pack_bytes(T) + ((P + a256) & ~a256) + ((P * size_t(order + 2) * 12 + a256) & ~a256) +
+           ((size_t(V) * 12 + a256) & ~a256) + 256;
+}
+
+int drt_trace_path_candidates_smooth_vjp(drt_stream_t stream, int64_t V, int64_t T, const float *vertices,
+                                         const int32_t *triangles, const uint8_t *triangle_mask,
+                                         int32_t assume_quads, int64_t ntx, const float *tx, int64_t nrx,
+                                         const float *rx, int64_t C, int32_t order, const int32_t *cand,
+                                         float epsilon, float hit_tol, float min_len, float smoothing_factor,
+                                         const float *out_vertices, const float *out_mask, const float *g_out_vertices,
+                                         const float *g_out_mask, void *workspace, size_t workspace_bytes,
+                                         float *g_tx, float *g_rx, float *g_vertices) {
+    if (V < 0 || T < 0 || ntx < 0 || nrx < 0 || C < 0 || order < 0) return DRT_ERR_BAD_EXTENT;
+    if (order > DRT_MAX_ORDER) return DRT_ERR_UNSUPPORTED;
+    const int64_t P = ntx * nrx * C;
+    if (P >= (int64_t(1) << 32)) return DRT_ERR_BAD_EXTENT;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (P == 0 || g_out_mask == nullptr)  // nothing but (possibly) the path-vertex cotangent
+        return drt_trace_path_candidates_vjp(stream, V, T, vertices, triangles, ntx, tx, nrx, rx, C, order, cand,
+                                             g_out_vertices, g_tx, g_rx, g_vertices);
+    if (!tx || !rx || !out_vertices || !out_mask || (order > 0 && !cand)) return DRT_ERR_NULL_POINTER;
+    if (order > 0 && T < (assume_quads ? 2 : 1)) return DRT_ERR_BAD_EXTENT;
+    if (T > 0 && (!vertices || !triangles)) return DRT_ERR_NULL_POINTER;
+    if (!workspace || workspace_bytes < drt_trace_smooth_vjp_workspace_bytes(V, T, ntx, nrx, C, order))
+        return DRT_ERR_WORKSPACE;
+    char *ws = static_cast<char *>(workspace);
+    const size_t pb = drt_mesh_pack_bytes(T), a256 = 255;
+    const size_t off_flags = 2 * pb;
+    const size_t off_gfull = off_flags + ((size_t(P) + a256) & ~a256);
+    const size_t off_gv = off_gfull + ((size_t(P) * size_t(order + 2) * 12 + a256) & ~a256);
+    SmoothVjpArgs a{};
+    SmoothTraceArgs &f = a.f;
+    f.pack = reinterpret_cast<const Tri48 *>(ws);
+    f.pack_active = f.pack;
+    f.flags = reinterpret_cast<uint8_t *>(ws + off_flags);
+    if (T > 0) {
+        int rc = drt_mesh_pack(stream, V, T, vertices, triangles, nullptr, ws);
+        if (rc != DRT_OK) return rc;
+        if (triangle_mask) {
+            rc = drt_mesh_pack(stream, V, T, vertices, triangles, triangle_mask, ws + pb);
+            if (rc != DRT_OK) return rc;
+            f.pack_active = reinterpret_cast<const Tri48 *>(ws + pb);
+        }
+    }
+    f.tri_mask = triangle_mask;
+    f.tx = tx; f.rx = rx; f.cand = cand;
+    f.T = T; f.ntx = ntx; f.nrx = nrx; f.C = C; f.P = P;
+    f.eps = epsilon; f.thr = 1.0f - hit_tol; f.min_len = min_len; f.alpha = smoothing_factor;
+    f.out_vertices = const_cast<float *>(out_vertices);
+    f.out_mask = const_cast<float *>(out_mask);
+    a.triangles = triangles;
+    a.V = V;
+    a.g_mask = g_out_mask;
+    a.g_out_vertices = g_out_vertices;
+    a.g_full = reinterpret_cast<float *>(ws + off_gfull);
+    a.g_verts_direct = reinterpret_cast<float *>(ws + off_gv);
+    if (V > 0 && cudaMemsetAsync(a.g_verts_direct, 0, size_t(V) * 12, s) != cudaSuccess) return DRT_ERR_CUDA;
+    const bool q = assume_quads != 0;
+    int rc = DRT_ERR_UNSUPPORTED;
+    switch (order) {
+        case 0: rc = launch_trace_smooth_vjp<0>(a, q, s); break;
+        case 1: rc = launch_trace_smooth_vjp<1>(a, q, s); break;
+        case 2: rc = launch_trace_smooth_vjp<2>(a, q, s); break;
+        case 3: rc = launch_trace_smooth_vjp<3>(a, q, s); break;
+        case 4: rc = launch_trace_smooth_vjp<4>(a, q, s); break;
+        case 5: rc = launch_trace_smooth_vjp<5>(a, q, s); break;
+        case 6: rc = launch_trace_smooth_vjp<6>(a, q, s); break;
+        case 7: rc = launch_trace_smooth_vjp<7>(a, q, s); break;
+        case 8: rc = launch_trace_smooth_vjp<8>(a, q, s); break;
+        default: break;
+    }
+    if (rc != DRT_OK) return rc;
+    // through the image method, the mirror gathers and the normals (K6b), then the direct part
+    rc = drt_trace_path_candidates_vjp(stream, V, T, vertices, triangles, ntx, tx, nrx, rx, C, order, cand,
+                                       a.g_full, g_tx, g_rx, g_vertices);
+    if (rc != DRT_OK) return rc;
+    if (V > 0) {
+        add_inplace_kernel<<<unsigned((V * 3 + 255) / 256), 256, 0, s>>>(V * 3, g_vertices, a.g_verts_direct);
+        if (cudaGetLastError() != cudaSuccess) return DRT_ERR_CUDA;
+    }
+    return DRT_OK;
 }
 
 }  // extern "C"

@@ -57,6 +57,58 @@ class _TraceVertices(torch.autograd.Function):
         return g_v, g_tx, g_rx, None, None, None
 
 
+class _SmoothTrace(torch.autograd.Function):
+    """Relaxed trace (``smoothing_factor``): ``(vertices, confidence, objects)`` with the gradient
+    ``jax.grad`` gives on the reference's relaxed branch (``_solvers.py:576-713``) — through the
+    confidence AND through the path vertices — to ``mesh.vertices``, ``tx`` and ``rx``."""
+
+    @staticmethod
+    def forward(ctx, mesh_vertices, tx, rx, triangles, cand, mask_u8, quads, eps, tol, min_len, alpha):
+        dev = mesh_vertices.device
+        ntx, nrx, (C, k) = tx.shape[0], rx.shape[0], cand.shape
+        V, T = mesh_vertices.shape[0], triangles.shape[0]
+        out_v = torch.empty((ntx, nrx, C, k + 2, 3), dtype=torch.float32, device=dev)
+        out_o = torch.empty((ntx, nrx, C, k + 2), dtype=torch.int32, device=dev)
+        out_f = torch.empty((ntx, nrx, C), dtype=torch.float32, device=dev)
+        ws = torch.empty(max(lib.drt_trace_smooth_workspace_bytes(T, ntx, nrx, C), 1), dtype=torch.uint8, device=dev)
+        check(
+            lib.drt_trace_path_candidates_smooth(
+                stream_ptr(), V, T, ptr(mesh_vertices), ptr(triangles), ptr(mask_u8), int(quads), ntx, ptr(tx),
+                nrx, ptr(rx), C, k, ptr(cand), eps, tol, min_len, alpha, ptr(ws), ws.numel(), ptr(out_v),
+                ptr(out_o), ptr(out_f),
+            )
+        )
+        ctx.save_for_backward(mesh_vertices, tx, rx, triangles, cand, mask_u8, out_v, out_f)
+        ctx.params = (quads, eps, tol, min_len, alpha)
+        ctx.mark_non_differentiable(out_o)
+        ctx.set_materialize_grads(False)
+        return out_v, out_f, out_o
+
+    @staticmethod
+    def backward(ctx, g_v, g_f, _g_o):
+        mesh_vertices, tx, rx, triangles, cand, mask_u8, out_v, out_f = ctx.saved_tensors
+        quads, eps, tol, min_len, alpha = ctx.params
+        ntx, nrx, (C, k) = tx.shape[0], rx.shape[0], cand.shape
+        V, T = mesh_vertices.shape[0], triangles.shape[0]
+        g_mv, g_tx, g_rx = torch.zeros_like(mesh_vertices), torch.zeros_like(tx), torch.zeros_like(rx)
+        if g_v is None and g_f is None:
+            return (g_mv, g_tx, g_rx) + (None,) * 8
+        g_v = None if g_v is None else g_v.contiguous().to(torch.float32)
+        g_f = None if g_f is None else g_f.contiguous().to(torch.float32)
+        ws = torch.empty(max(lib.drt_trace_smooth_vjp_workspace_bytes(V, T, ntx, nrx, C, k), 1), dtype=torch.uint8,
+                         device=mesh_vertices.device)
+        if g_f is None:
+            g_f = torch.zeros_like(out_f)
+        check(
+            lib.drt_trace_path_candidates_smooth_vjp(
+                stream_ptr(), V, T, ptr(mesh_vertices), ptr(triangles), ptr(mask_u8), int(quads), ntx, ptr(tx),
+                nrx, ptr(rx), C, k, ptr(cand), eps, tol, min_len, alpha, ptr(out_v), ptr(out_f), ptr(g_v),
+                ptr(g_f), ptr(ws), ws.numel(), ptr(g_tx), ptr(g_rx), ptr(g_mv),
+            )
+        )
+        return (g_mv, g_tx, g_rx) + (None,) * 8
+
+
 def trace_path_candidates(
     mesh: Mesh,
     tx_vertices,
@@ -106,22 +158,13 @@ def trace_path_candidates(
     else:
         it = torch.zeros((1, 1, 1, 1), dtype=torch.int32, device=dev).expand(ntx, nrx, C, k)
     if smoothing_factor is not None:
-        # relaxed validation (_solvers.py:599-713): float mask in [0, 1], forward only
-        if torch.is_grad_enabled() and any(x.requires_grad for x in (mesh.vertices, tx, rx)):
-            raise NotImplementedError("gradients through the relaxed trace are not built (DESIGN.md §6b)")
-        out_f = torch.empty((ntx, nrx, C), dtype=torch.float32, device=dev)
-        ws = torch.empty(max(lib.drt_trace_smooth_workspace_bytes(T, ntx, nrx, C), 1), dtype=torch.uint8, device=dev)
-        mask_u8 = mesh._mask_u8()  # named: must outlive the call
-        check(
-            lib.drt_trace_path_candidates_smooth(
-                stream_ptr(), mesh.vertices.shape[0], T, ptr(mesh.vertices.detach()), ptr(mesh.triangles),
-                ptr(mask_u8), int(mesh.assume_quads), ntx, ptr(tx.detach()), nrx, ptr(rx.detach()),
-                C, k, ptr(cand),
-                10.0 * F32_EPS if epsilon is None else float(epsilon),
-                100.0 * F32_EPS if hit_tol is None else float(hit_tol),
-                10.0 * F32_EPS if min_len is None else float(min_len),
-                float(smoothing_factor), ptr(ws), ws.numel(), ptr(out_v), ptr(out_o), ptr(out_f),
-            )
+        # relaxed validation (_solvers.py:599-713): float confidence in [0, 1], differentiable
+        out_v, out_f, out_o = _SmoothTrace.apply(
+            mesh.vertices, tx, rx, mesh.triangles, cand, mesh._mask_u8(), bool(mesh.assume_quads),
+            10.0 * F32_EPS if epsilon is None else float(epsilon),
+            100.0 * F32_EPS if hit_tol is None else float(hit_tol),
+            10.0 * F32_EPS if min_len is None else float(min_len),
+            float(smoothing_factor),
         )
         return TracedPaths(vertices=out_v, objects=out_o, mask=out_f, interaction_types=it,
                            confidence_threshold=confidence_threshold)

@@ -288,7 +288,7 @@ DRT_API int drt_digraph_candidates(drt_stream_t stream, int64_t num_nodes, int32
                            int32_t stride_multiplier, int32_t *out);
 
 /* ---------------------------------------------------------------------------------------------
- * N4  (forward only) smoothed variants of the primitives and of the trace: comparisons → sigmoid(x * smoothing_factor)
+ * N4  smoothed variants of the primitives (forward only) and of the trace (forward + reverse): comparisons → sigmoid(x * smoothing_factor)
  *     (reference: differt/src/differt/utils.py:70-89), AND → min, OR over triangles → sum clipped at 1
  *     (_utils.py:1279-1318, 1465-1476; _solver_image_method.py:448-454).  Float outputs in [0,1];
  *     parity to 1e-5 (transcendental), not bit-exact.  Masked-out triangles of a pack contribute 0.
@@ -313,8 +313,8 @@ DRT_API int drt_consecutive_vertices_are_on_same_side_of_mirror_smooth(
  * _solvers.py:576-719, the `smoothing_factor is not None` branches).  Same inputs and dense
  * out_vertices / out_objects as drt_trace_path_candidates (K6; vertices bit-identical to it), but
  * out_mask is float32 [Ntx, Nrx, C]: min(inside, same_side, 1 - blocked, 1 - too_small, finite),
- * times 1/0 for candidates that use a masked-out triangle.  NaN propagates as in jnp.min.  Forward
- * only.  Cost: every path segment against every active triangle (the relaxed any-hit is a sum: no
+ * times 1/0 for candidates that use a masked-out triangle.  NaN propagates as in jnp.min.
+ * Cost: every path segment against every active triangle (the relaxed any-hit is a sum: no
  * early exit).  workspace: device scratch of drt_trace_smooth_workspace_bytes(...) bytes. */
 DRT_API size_t drt_trace_smooth_workspace_bytes(int64_t num_triangles, int64_t num_tx, int64_t num_rx,
                                         int64_t num_candidates);
@@ -325,6 +325,27 @@ DRT_API int drt_trace_path_candidates_smooth(
     int32_t order, const int32_t *path_candidates, float epsilon, float hit_tol, float min_len,
     float smoothing_factor, void *workspace, size_t workspace_bytes, float *out_vertices,
     int32_t *out_objects, float *out_mask);
+
+/* Reverse mode of the relaxed trace: what jax.grad gives on _solvers.py:576-713.  Inputs: the
+ * forward's arguments, its saved out_vertices / out_mask, the cotangents g_out_vertices [P, k+2, 3]
+ * (nullable) and g_out_mask [P] (nullable: then this is drt_trace_path_candidates_vjp).  Outputs
+ * (overwritten): g_tx [Ntx,3], g_rx [Nrx,3], g_vertices [V,3].  The cotangent of a confidence goes to
+ * the term its min came from: the relaxed inside test of one interaction (path vertices + that
+ * triangle's vertices), the too-small segment, or — when the blockage sum of the worst segment is
+ * below its clip — every active triangle of the mesh (float atomics: not bit-reproducible); the
+ * same-side term depends on signs only.  min / max send the cotangent to their FIRST extremal
+ * argument where JAX shares it between exact ties; non-finite paths get none. */
+DRT_API size_t drt_trace_smooth_vjp_workspace_bytes(int64_t num_vertices, int64_t num_triangles,
+                                            int64_t num_tx, int64_t num_rx, int64_t num_candidates,
+                                            int32_t order);
+DRT_API int drt_trace_path_candidates_smooth_vjp(
+    drt_stream_t stream, int64_t num_vertices, int64_t num_triangles, const float *vertices,
+    const int32_t *triangles, const uint8_t *triangle_mask, int32_t assume_quads, int64_t num_tx,
+    const float *tx_vertices, int64_t num_rx, const float *rx_vertices, int64_t num_candidates,
+    int32_t order, const int32_t *path_candidates, float epsilon, float hit_tol, float min_len,
+    float smoothing_factor, const float *out_vertices, const float *out_mask,
+    const float *g_out_vertices, const float *g_out_mask, void *workspace, size_t workspace_bytes,
+    float *g_tx, float *g_rx, float *g_vertices);
 
 /* ---------------------------------------------------------------------------------------------
  * N2  OPT-IN bounding-volume hierarchy (linear BVH over Morton-sorted triangles) for the queries the

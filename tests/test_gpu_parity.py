@@ -1335,7 +1335,70 @@ def test_smoothed_trace_edge_cases(drt, two_buildings, rng):
     e = orc.trace_path_candidates(np.empty((0, 3), np.float32), np.empty((0, 3), np.int32), tx, rx[:1],
                                   np.empty((1, 0), np.int32), smoothing_factor=10.0)[2]
     np.testing.assert_allclose(p.mask.cpu().numpy(), e, rtol=1e-5)
-    # gradients of the relaxed trace are not built: loud, not silent
-    txg = torch.from_numpy(tx).cuda().requires_grad_(True)
-    with pytest.raises(NotImplementedError):
-        drt.trace_path_candidates(mesh, txg, rx[:1], cand, smoothing_factor=1.0)
+
+
+def _ground_and_wall(order, quads):
+    import itertools
+
+    # not axis-aligned on purpose: every component of every cotangent is exercised
+    v = np.array([[-10, -10, 0.3], [10, -10, -0.2], [10, 10, 0.4], [-10, 10, 0.1],
+                  [3, -4, 0], [3.5, 4, 0], [3.2, 4.3, 6], [2.8, -4, 6.2]], np.float32)
+    t = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7]], np.int32)
+    r = np.random.default_rng(5)
+    tx = r.uniform([-8, -8, 1], [1, 8, 8], size=(3, 3)).astype(np.float32)
+    rx = r.uniform([-8, -8, 1], [9, 8, 8], size=(20, 3)).astype(np.float32)
+    if order == 0:
+        cand = np.empty((1, 0), np.int32)
+    else:  # consecutive mirrors from different quads: no (near-)coplanar double reflections, which are
+        # ill-conditioned in fp32 (the fp64 gradient oracle would take other branches)
+        prim = range(0, 4, 2 if quads else 1)
+        cand = np.array([c for c in itertools.product(prim, repeat=order)
+                         if all(c[i] // 2 != c[i + 1] // 2 for i in range(order - 1))], np.int32).reshape(-1, order)
+    return v, t, tx, rx, cand
+
+
+@pytest.mark.parametrize("alpha", [0.5, 4.0, 40.0])
+@pytest.mark.parametrize("order", [0, 1, 2, 3])
+@pytest.mark.parametrize("quads", [False, True])
+def test_smoothed_trace_gradient_vs_autograd_oracle(drt, alpha, order, quads):
+    # what jax.grad gives on the relaxed branch (_solvers.py:576-713): cotangents on the confidences AND on
+    # the path vertices, to mesh.vertices / tx / rx; the oracle is the float64 torch restatement
+    from oracle import smooth_grad_oracle as sg
+
+    v, t, tx, rx, cand = _ground_and_wall(order, quads)
+    r = np.random.default_rng(11)
+    w = r.normal(size=(tx.shape[0], rx.shape[0], cand.shape[0])).astype(np.float32)
+    # (order 3 has far, ill-conditioned image points: fp32 vs fp64 differ by 1e-3 there; K6b's own tests cover them)
+    gw = ((0.01 if order < 3 else 0.0) * r.normal(size=(*w.shape, order + 2, 3))).astype(np.float32)
+    for mask in ((None, np.array([True, True, True, False])) if not quads else (None,)):
+        mesh = drt.Mesh.from_numpy(v, t, mask, assume_quads=quads)
+        mesh.vertices.requires_grad_(True)
+        txc = torch.from_numpy(tx).cuda().requires_grad_(True)
+        rxc = torch.from_numpy(rx).cuda().requires_grad_(True)
+        paths = drt.trace_path_candidates(mesh, txc, rxc, cand, smoothing_factor=alpha)
+        assert not torch.isnan(paths.mask).any()
+        ((paths.mask * torch.from_numpy(w).cuda()).sum() + (paths.vertices * torch.from_numpy(gw).cuda()).sum()).backward()
+
+        V = torch.tensor(v, dtype=torch.float64, requires_grad=True)
+        TX = torch.tensor(tx, dtype=torch.float64, requires_grad=True)
+        RX = torch.tensor(rx, dtype=torch.float64, requires_grad=True)
+        full, conf, idx = sg.relaxed_trace(V, t, TX, RX, cand, mask=mask, assume_quads=quads, smoothing_factor=alpha)
+        assert idx.numel() == w.size  # every path of this scene is finite
+        np.testing.assert_allclose(paths.mask.detach().cpu().numpy().reshape(-1), conf.detach().numpy(), rtol=1e-4, atol=1e-5)
+        ((conf * torch.from_numpy(w.reshape(-1)).double()).sum()
+         + (full * torch.from_numpy(gw.reshape(-1, order + 2, 3)).double()).sum()).backward()
+        for name, got, exp in (("tx", txc.grad, TX.grad), ("rx", rxc.grad, RX.grad), ("vertices", mesh.vertices.grad, V.grad)):
+            e = exp.numpy()
+            np.testing.assert_allclose(got.cpu().numpy(), e, rtol=2e-3, atol=2e-3 * max(np.abs(e).max(), 1e-6),
+                                       err_msg=f"{name} alpha={alpha} order={order} quads={quads} mask={mask is not None}")
+        # a cotangent on the vertices alone gives the hard trace's gradient (same image-method VJP)
+        if mask is None and order == 2:
+            def grads(**kw):
+                m = drt.Mesh(mesh.vertices.detach().clone().requires_grad_(True), mesh.triangles, assume_quads=quads)
+                a = txc.detach().clone().requires_grad_(True)
+                b = rxc.detach().clone().requires_grad_(True)
+                (drt.trace_path_candidates(m, a, b, cand, **kw).vertices * torch.from_numpy(gw).cuda()).sum().backward()
+                return [x.grad.cpu().numpy() for x in (m.vertices, a, b)]
+
+            for got, exp in zip(grads(smoothing_factor=alpha), grads()):
+                np.testing.assert_allclose(got, exp, rtol=1e-4, atol=1e-6)

@@ -55,3 +55,65 @@ def test_relaxed_mask_properties(quads):
     _, _, ms = orc.trace_path_candidates(v[:4], t[:2], tx, rx, cand[~uses_wall], assume_quads=quads,
                                          smoothing_factor=4.0)
     np.testing.assert_allclose(mm[..., ~uses_wall], ms, rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# the float64 torch restatement used as the gradient oracle of the relaxed trace
+# ------------------------------------------------------------------------------------------------
+
+
+def _scene():
+    v = np.array([[-10, -10, 0.3], [10, -10, -0.2], [10, 10, 0.4], [-10, 10, 0.1],
+                  [3, -4, 0], [3.5, 4, 0], [3.2, 4.3, 6], [2.8, -4, 6.2]], np.float32)
+    t = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7]], np.int32)
+    r = np.random.default_rng(5)
+    tx = r.uniform([-8, -8, 1], [1, 8, 8], size=(2, 3)).astype(np.float32)
+    rx = r.uniform([-8, -8, 1], [9, 8, 8], size=(6, 3)).astype(np.float32)
+    return v, t, tx, rx
+
+
+@pytest.mark.parametrize("order,quads", [(0, False), (1, False), (2, False), (2, True), (3, False)])
+def test_gradient_oracle_forward_matches_numpy_oracle(order, quads):
+    import torch
+
+    from oracle import smooth_grad_oracle as sg
+
+    v, t, tx, rx = _scene()
+    prim = range(0, 4, 2 if quads else 1)
+    cand = (np.array([c for c in itertools.product(prim, repeat=order)
+                      if all(c[i] // 2 != c[i + 1] // 2 for i in range(order - 1))], np.int32).reshape(-1, order)
+            if order else np.empty((1, 0), np.int32))
+    for alpha in (0.5, 4.0, 40.0):
+        for mask in (None, np.array([True, True, True, False]) if not quads else None):
+            ev, _, em = orc.trace_path_candidates(v, t, tx, rx, cand, mask=mask, assume_quads=quads, smoothing_factor=alpha)
+            full, conf, idx = sg.relaxed_trace(torch.tensor(v, dtype=torch.float64), t, torch.tensor(tx, dtype=torch.float64),
+                                               torch.tensor(rx, dtype=torch.float64), cand, mask=mask, assume_quads=quads,
+                                               smoothing_factor=alpha)
+            assert idx.numel() == em.size
+            np.testing.assert_allclose(conf.numpy(), em.reshape(-1), rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(full.numpy(), ev.reshape(-1, order + 2, 3), rtol=2e-3, atol=1e-3)  # far, ill-conditioned points
+
+
+def test_gradient_oracle_agrees_with_finite_differences():
+    import torch
+
+    from oracle import smooth_grad_oracle as sg
+
+    v, t, tx, rx = _scene()
+    cand = np.array([[0, 2], [3, 1], [2, 0]], np.int32)
+    w = torch.tensor(np.random.default_rng(3).normal(size=2 * 6 * 3))
+
+    def loss(V, TX, RX):
+        return (sg.relaxed_trace(V, t, TX, RX, cand, smoothing_factor=4.0)[1] * w).sum()
+
+    args = [torch.tensor(x, dtype=torch.float64, requires_grad=True) for x in (v, tx, rx)]
+    loss(*args).backward()
+    r = np.random.default_rng(4)
+    for k, a in enumerate(args):  # directional derivatives, central differences
+        d = torch.tensor(r.normal(size=tuple(a.shape)))
+        h = 1e-6
+        plus = [x.detach() + (h * d if i == k else 0) for i, x in enumerate(args)]
+        minus = [x.detach() - (h * d if i == k else 0) for i, x in enumerate(args)]
+        fd = (loss(*plus) - loss(*minus)).item() / (2 * h)
+        an = (a.grad * d).sum().item()
+        assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)), (k, fd, an)

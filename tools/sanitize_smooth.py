@@ -26,5 +26,13 @@ for quads in (False, True):
                 cand -= cand % 2
             p = drt.trace_path_candidates(mesh, tx, rx, cand, smoothing_factor=7.0)
             print(quads, masked, order, float(torch.nan_to_num(p.mask).sum()), p.num_valid_paths, p.masked().vertices.shape[0])
+            # reverse mode: cotangents on the confidences and on the path vertices
+            mg = drt.Mesh(mesh.vertices.clone().requires_grad_(True), mesh.triangles, mesh.mask, assume_quads=quads)
+            txg = torch.from_numpy(tx).cuda().requires_grad_(True)
+            rxg = torch.from_numpy(rx).cuda().requires_grad_(True)
+            for a in (0.3, 7.0):
+                q = drt.trace_path_candidates(mg, txg, rxg, cand, smoothing_factor=a)
+                (torch.nan_to_num(q.mask).sum() + torch.nan_to_num(q.vertices).sum()).backward()
+            print("   grad", float(torch.nan_to_num(mg.vertices.grad).abs().sum()), float(torch.nan_to_num(txg.grad).abs().sum()))
 torch.cuda.synchronize()
 print("sanitize run complete")
