@@ -10,9 +10,8 @@ Differentiation surface (the reference's ``custom_vjp`` surface, SURVEY.md §3.5
 the hit distance ``t`` of ``first_triangle_hit_by_ray`` / ``ray_intersect_triangle`` carry gradients
 (``torch.autograd``); boolean / index outputs never do.  ``smoothing_factor`` is supported, forward
 only, by ``ray_intersect_triangle``, ``ray_intersect_any_triangle`` and
-``consecutive_vertices_are_on_same_side_of_mirror`` (float outputs); the fused trace raises
-``NotImplementedError`` — exactly the case in which the reference itself bypasses its accelerated
-path (``_solvers.py:675-680``).
+``consecutive_vertices_are_on_same_side_of_mirror`` (float outputs); the relaxed trace
+(``solvers.trace_path_candidates(smoothing_factor=...)``) is differentiable end to end.
 """
 
 from __future__ import annotations
