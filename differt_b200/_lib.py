@@ -71,6 +71,10 @@ PROTOTYPES: dict[str, tuple] = {
     "drt_ray_intersect_any_triangle_smooth": (C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, f32, f32, ptr]),
     "drt_consecutive_vertices_are_on_same_side_of_mirror_smooth": (
         C.c_int, [ptr, i32, p_i64, i32, ptr, p_i64, ptr, p_i64, ptr, p_i64, f32, ptr]),
+    "drt_ray_intersect_triangle_smooth_vjp": (
+        C.c_int, [ptr, i64, ptr, ptr, ptr, f32, f32, ptr, ptr, ptr, ptr, ptr]),
+    "drt_ray_intersect_any_triangle_smooth_vjp": (
+        C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, f32, f32, ptr, ptr, ptr, ptr]),
     "drt_trace_smooth_workspace_bytes": (size_t, [i64, i64, i64, i64]),
     "drt_trace_path_candidates_smooth": (
         C.c_int,

@@ -263,14 +263,16 @@ __device__ __forceinline__ void atomic_add3s(float *p, float3 v) {
     if (v.z != 0.f) atomicAdd(p + 2, v.z);
 }
 
-// g: cotangent of hit (blockage == false) or of min(hit, sigmoid((thr - t) alpha)) (blockage == true).
-// Returns false when nothing flows (saturated, a == 0 or NaN).
-__device__ __forceinline__ bool mt_smooth_grad(const float3 o, const float3 d, const Tri &tr, const float eps,
-                                               const float alpha, const float thr, const bool blockage,
-                                               const float g, MtGrad &out) {
+// Seeds (ga, gu, gv, gt) → cotangents of (o, d, v0, e1, e2).  Recomputes the forward
+// (h = d x e2, a = h.e1, f = 1/a, s = o - v0, u = f s.h, q = s x e1, v = f q.d, t = f q.e2).
+// `select` != 0: add g times the derivative of the relaxed hit (1) or of min(hit, sigmoid((thr - t) alpha))
+// (2), routed to the first minimal term.  Returns false when nothing flows (a == 0, NaN, saturated).
+__device__ __forceinline__ bool mt_smooth_adjoint(const float3 o, const float3 d, const Tri &tr, const float eps,
+                                                  const float alpha, const float thr, const int select,
+                                                  const float g, float gt, MtGrad &out) {
     const float3 h = cross3(d, tr.e2);
     const float a = dot3(h, tr.e1);
-    if (a == 0.0f) return false;  // where(a == 0, inf, a): constant branch
+    if (a == 0.0f) return false;  // where(a == 0, inf, a): f = 0 and every output is constant
     const float f = __frcp_rn(a);
     const float3 s = sub3(o, tr.v0);
     const float su = dot3(s, h);
@@ -280,9 +282,11 @@ __device__ __forceinline__ bool mt_smooth_grad(const float3 o, const float3 d, c
     const float v = f * qv;
     const float qt = dot3(q, tr.e2);
     const float t = f * qt;
-    float best = smooth(fabsf(a) - eps, alpha);
-    int which = 0;
-    bool nan = best != best;
+    float ga = 0.f, gu = 0.f, gv = 0.f;
+    if (select != 0) {
+        float best = smooth(fabsf(a) - eps, alpha);
+        int which = 0;
+        bool nan = best != best;
 #define DRT_CONSIDER(val, id)            \
     {                                    \
         const float x_ = (val);          \
@@ -292,27 +296,28 @@ __device__ __forceinline__ bool mt_smooth_grad(const float3 o, const float3 d, c
             which = (id);                \
         }                                \
     }
-    DRT_CONSIDER(smooth(u - 0.0f, alpha), 1)
-    DRT_CONSIDER(smooth(1.0f - u, alpha), 2)
-    DRT_CONSIDER(1.0f, 7)
-    DRT_CONSIDER(smooth(v - 0.0f, alpha), 3)
-    DRT_CONSIDER(smooth(1.0f - (u + v), alpha), 4)
-    DRT_CONSIDER(smooth(t - eps, alpha), 5)
-    if (blockage) DRT_CONSIDER(smooth(thr - t, alpha), 6)
+        DRT_CONSIDER(smooth(u - 0.0f, alpha), 1)
+        DRT_CONSIDER(smooth(1.0f - u, alpha), 2)
+        DRT_CONSIDER(1.0f, 7)
+        DRT_CONSIDER(smooth(v - 0.0f, alpha), 3)
+        DRT_CONSIDER(smooth(1.0f - (u + v), alpha), 4)
+        DRT_CONSIDER(smooth(t - eps, alpha), 5)
+        if (select == 2) DRT_CONSIDER(smooth(thr - t, alpha), 6)
 #undef DRT_CONSIDER
-    if (nan || which == 7) return false;
-    const float ds = g * alpha * best * (1.0f - best);  // d sigmoid(x alpha) / dx, times the cotangent
-    if (ds == 0.0f || ds != ds) return false;
-    float ga = 0.f, gu = 0.f, gv = 0.f, gt = 0.f;
-    switch (which) {
-        case 0: ga = a < 0.0f ? -ds : ds; break;
-        case 1: gu = ds; break;
-        case 2: gu = -ds; break;
-        case 3: gv = ds; break;
-        case 4: gu = -ds; gv = -ds; break;
-        case 5: gt = ds; break;
-        default: gt = -ds; break;
+        float ds = g * alpha * best * (1.0f - best);  // d sigmoid(x alpha) / dx, times the cotangent
+        if (nan || which == 7 || ds != ds) ds = 0.0f;
+        switch (which) {
+            case 0: ga = a < 0.0f ? -ds : ds; break;
+            case 1: gu = ds; break;
+            case 2: gu = -ds; break;
+            case 3: gv = ds; break;
+            case 4: gu = -ds; gv = -ds; break;
+            case 5: gt += ds; break;
+            case 6: gt -= ds; break;
+            default: break;
+        }
     }
+    if (ga == 0.0f && gu == 0.0f && gv == 0.0f && gt == 0.0f) return false;
     const float gf = gu * su + gv * qv + gt * qt;
     const float gsu = gu * f, gqv = gv * f, gqt = gt * f;
     ga -= gf * f * f;                                            // f = 1 / a
@@ -325,6 +330,93 @@ __device__ __forceinline__ bool mt_smooth_grad(const float3 o, const float3 d, c
     out.e1 = add3(scale3(h, ga), cross3(gq, s));
     out.e2 = add3(scale3(q, gqt), cross3(gh, d));
     return true;
+}
+
+// g: cotangent of hit (blockage == false) or of min(hit, sigmoid((thr - t) alpha)) (blockage == true)
+__device__ __forceinline__ bool mt_smooth_grad(const float3 o, const float3 d, const Tri &tr, const float eps,
+                                               const float alpha, const float thr, const bool blockage,
+                                               const float g, MtGrad &out) {
+    return mt_smooth_adjoint(o, d, tr, eps, alpha, thr, blockage ? 2 : 1, g, 0.0f, out);
+}
+
+// reverse mode of the relaxed primitives called on their own ------------------------------------
+
+// elementwise: cotangents of (t, hit) → (o, d, triangle vertices) per element; the host sums over
+// broadcast axes (autograd of expand)
+__global__ void mt_smooth_vjp_kernel(int64_t n, const float *__restrict__ o, const float *__restrict__ d,
+                                     const float *__restrict__ tri, float eps, float alpha,
+                                     const float *__restrict__ g_t, const float *__restrict__ g_hit,
+                                     float *__restrict__ g_o, float *__restrict__ g_d, float *__restrict__ g_tri) {
+    const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const float3 v0 = ld3(tri + 9 * i), v1 = ld3(tri + 9 * i + 3), v2 = ld3(tri + 9 * i + 6);
+    Tri tr;
+    tr.v0 = v0;
+    tr.e1 = sub3(v1, v0);
+    tr.e2 = sub3(v2, v0);
+    MtGrad mg;
+    const float3 z = make_float3(0.f, 0.f, 0.f);
+    mg.o = mg.d = mg.v0 = mg.e1 = mg.e2 = z;
+    const float gh = g_hit ? g_hit[i] : 0.0f, gt = g_t ? g_t[i] : 0.0f;
+    if (!mt_smooth_adjoint(ld3(o + 3 * i), ld3(d + 3 * i), tr, eps, alpha, 0.0f, gh != 0.0f ? 1 : 0, gh, gt, mg))
+        mg.o = mg.d = mg.v0 = mg.e1 = mg.e2 = z;
+    st3(g_o + 3 * i, mg.o);
+    st3(g_d + 3 * i, mg.d);
+    st3(g_tri + 9 * i, sub3(sub3(mg.v0, mg.e1), mg.e2));
+    st3(g_tri + 9 * i + 3, mg.e1);
+    st3(g_tri + 9 * i + 6, mg.e2);
+}
+
+// one warp per ray: recompute the clipped sum exactly like any_smooth_kernel; below the clip the
+// cotangent goes through every active triangle's term
+__global__ void __launch_bounds__(256)
+any_smooth_vjp_kernel(int64_t R, int64_t T, const float *__restrict__ o, const float *__restrict__ d,
+                      const Tri48 *__restrict__ pack, float eps, float thr, float alpha,
+                      const float *__restrict__ g_out, float *__restrict__ g_o, float *__restrict__ g_d,
+                      float *g_tri) {
+    const int lane = threadIdx.x & 31;
+    const int64_t ray = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+    if (ray >= R) return;
+    const float3 oo = ld3(o + 3 * ray), dd = ld3(d + 3 * ray);
+    float acc = 0.0f;
+    for (int64_t j = lane; j < T; j += 32) {
+        const float4 a = pack[j].a, b = pack[j].b, c = pack[j].c;
+        if (a.x != a.x && a.y != a.y && a.z != a.z && a.w == 0.0f) continue;
+        float t;
+        const float hit = mt_smooth(oo, dd, unpack(a, b, c), eps, alpha, t);
+        acc += nanmin(hit, smooth(thr - t, alpha));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
+    float3 go = make_float3(0.f, 0.f, 0.f), gd = make_float3(0.f, 0.f, 0.f);
+    const float g = g_out[ray];
+    if (acc < 1.0f && g != 0.0f && g == g) {
+        for (int64_t j = lane; j < T; j += 32) {
+            const float4 a = pack[j].a, b = pack[j].b, c = pack[j].c;
+            if (a.x != a.x && a.y != a.y && a.z != a.z && a.w == 0.0f) continue;
+            MtGrad mg;
+            if (mt_smooth_adjoint(oo, dd, unpack(a, b, c), eps, alpha, thr, 2, g, 0.0f, mg)) {
+                go = add3(go, mg.o);
+                gd = add3(gd, mg.d);
+                atomic_add3s(g_tri + 9 * j, sub3(sub3(mg.v0, mg.e1), mg.e2));
+                atomic_add3s(g_tri + 9 * j + 3, mg.e1);
+                atomic_add3s(g_tri + 9 * j + 6, mg.e2);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        go.x += __shfl_xor_sync(kFull, go.x, off);
+        go.y += __shfl_xor_sync(kFull, go.y, off);
+        go.z += __shfl_xor_sync(kFull, go.z, off);
+        gd.x += __shfl_xor_sync(kFull, gd.x, off);
+        gd.y += __shfl_xor_sync(kFull, gd.y, off);
+        gd.z += __shfl_xor_sync(kFull, gd.z, off);
+    }
+    if (lane == 0) {
+        st3(g_o + 3 * ray, go);
+        st3(g_d + 3 * ray, gd);
+    }
 }
 
 struct SmoothVjpArgs {
@@ -775,6 +867,39 @@ int drt_trace_path_candidates_smooth_vjp(drt_stream_t stream, int64_t V, int64_t
         if (cudaGetLastError() != cudaSuccess) return DRT_ERR_CUDA;
     }
     return DRT_OK;
+}
+
+int drt_ray_intersect_triangle_smooth_vjp(drt_stream_t stream, int64_t n, const float *o, const float *d,
+                                          const float *tri, float epsilon, float smoothing_factor,
+                                          const float *g_t, const float *g_hit, float *g_o, float *g_d,
+                                          float *g_tri) {
+    if (n < 0) return DRT_ERR_BAD_EXTENT;
+    if (n == 0) return DRT_OK;
+    if (!o || !d || !tri || !g_o || !g_d || !g_tri) return DRT_ERR_NULL_POINTER;
+    mt_smooth_vjp_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        n, o, d, tri, epsilon, smoothing_factor, g_t, g_hit, g_o, g_d, g_tri);
+    return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
+}
+
+int drt_ray_intersect_any_triangle_smooth_vjp(drt_stream_t stream, int64_t R, const float *o, const float *d,
+                                              const void *pack, int64_t T, float epsilon, float hit_tol,
+                                              float smoothing_factor, const float *g_out, float *g_o,
+                                              float *g_d, float *g_tri) {
+    if (R < 0 || T < 0) return DRT_ERR_BAD_EXTENT;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (T > 0 && !g_tri) return DRT_ERR_NULL_POINTER;
+    if (T > 0 && cudaMemsetAsync(g_tri, 0, size_t(T) * 36, s) != cudaSuccess) return DRT_ERR_CUDA;
+    if (R == 0) return DRT_OK;
+    if (!g_o || !g_d) return DRT_ERR_NULL_POINTER;
+    if (T == 0) {
+        if (cudaMemsetAsync(g_o, 0, size_t(R) * 12, s) != cudaSuccess) return DRT_ERR_CUDA;
+        return cudaMemsetAsync(g_d, 0, size_t(R) * 12, s) == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
+    }
+    if (!o || !d || !pack || !g_out) return DRT_ERR_NULL_POINTER;
+    any_smooth_vjp_kernel<<<unsigned((R * 32 + 255) / 256), 256, 0, s>>>(
+        R, T, o, d, static_cast<const Tri48 *>(pack), epsilon, 1.0f - hit_tol, smoothing_factor, g_out, g_o, g_d,
+        g_tri);
+    return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
 }
 
 }  // extern "C"

@@ -8,10 +8,11 @@ done by the CUDA library behind the C ABI (``include/differt_b200.h``) — there
 
 Differentiation surface (the reference's ``custom_vjp`` surface): ``image_method`` and
 the hit distance ``t`` of ``first_triangle_hit_by_ray`` / ``ray_intersect_triangle`` carry gradients
-(``torch.autograd``); boolean / index outputs never do.  ``smoothing_factor`` is supported, forward
-only, by ``ray_intersect_triangle``, ``ray_intersect_any_triangle`` and
-``consecutive_vertices_are_on_same_side_of_mirror`` (float outputs); the relaxed trace
-(``solvers.trace_path_candidates(smoothing_factor=...)``) is differentiable end to end.
+(``torch.autograd``); boolean / index outputs never do.  ``smoothing_factor`` is supported by
+``ray_intersect_triangle``, ``ray_intersect_any_triangle`` (float outputs, differentiable),
+``consecutive_vertices_are_on_same_side_of_mirror`` (a function of signs: zero gradient, like the
+reference's) and the trace (``solvers.trace_path_candidates(smoothing_factor=...)``, differentiable
+end to end).
 """
 
 from __future__ import annotations
@@ -173,6 +174,78 @@ class _FirstHitDistanceGrad(torch.autograd.Function):
         return None, g_v, None, g_o, g_d, None
 
 
+class _SmoothTriangle(torch.autograd.Function):
+    """Relaxed Möller–Trumbore on flat ``[n, …]`` inputs with its reverse mode: both ``t`` and the
+    relaxed ``hit`` carry gradients (``jax.grad`` of ``_utils.py:1263-1322`` with smoothing)."""
+
+    @staticmethod
+    def forward(ctx, o, d, tv, eps, alpha):
+        n = o.shape[0]
+        t = torch.empty(n, dtype=torch.float32, device=o.device)
+        hit = torch.empty(n, dtype=torch.float32, device=o.device)
+        ndim, shape, (so, sd, st), keep = batch_strides((n,), [(o, 1), (d, 1), (tv, 2)])
+        check(
+            lib.drt_ray_intersect_triangle_smooth(
+                stream_ptr(), ndim, shape, ptr(keep[0]), so, ptr(keep[1]), sd, ptr(keep[2]), st, eps, alpha,
+                ptr(t), ptr(hit),
+            )
+        )
+        ctx.save_for_backward(o, d, tv)
+        ctx.params = (eps, alpha)
+        ctx.set_materialize_grads(False)
+        return t, hit
+
+    @staticmethod
+    def backward(ctx, g_t, g_hit):
+        o, d, tv = ctx.saved_tensors
+        eps, alpha = ctx.params
+        g_o, g_d, g_tv = torch.zeros_like(o), torch.zeros_like(d), torch.zeros_like(tv)
+        if g_t is not None or g_hit is not None:
+            g_t = None if g_t is None else g_t.contiguous().to(torch.float32)
+            g_hit = None if g_hit is None else g_hit.contiguous().to(torch.float32)
+            check(
+                lib.drt_ray_intersect_triangle_smooth_vjp(
+                    stream_ptr(), o.shape[0], ptr(o), ptr(d), ptr(tv), eps, alpha, ptr(g_t), ptr(g_hit),
+                    ptr(g_o), ptr(g_d), ptr(g_tv),
+                )
+            )
+        return g_o, g_d, g_tv, None, None
+
+
+class _SmoothAnyTriangle(torch.autograd.Function):
+    """Relaxed any-hit of flat rays against one mesh, with its reverse mode
+    (``jax.grad`` of ``_utils.py:1452-1476``)."""
+
+    @staticmethod
+    def forward(ctx, o, d, tv, act, eps, tol, alpha):
+        T = tv.shape[0]
+        pack = pack_triangle_vertices(tv, act)
+        res = torch.empty(o.shape[0], dtype=torch.float32, device=o.device)
+        check(
+            lib.drt_ray_intersect_any_triangle_smooth(
+                stream_ptr(), o.shape[0], ptr(o), ptr(d), ptr(pack), T, eps, tol, alpha, ptr(res)
+            )
+        )
+        ctx.save_for_backward(o, d, tv, act)
+        ctx.params = (eps, tol, alpha)
+        return res
+
+    @staticmethod
+    def backward(ctx, g):
+        o, d, tv, act = ctx.saved_tensors
+        eps, tol, alpha = ctx.params
+        pack = pack_triangle_vertices(tv, act)
+        g = g.contiguous().to(torch.float32)
+        g_o, g_d, g_tv = torch.empty_like(o), torch.empty_like(d), torch.empty_like(tv)
+        check(
+            lib.drt_ray_intersect_any_triangle_smooth_vjp(
+                stream_ptr(), o.shape[0], ptr(o), ptr(d), ptr(pack), tv.shape[0], eps, tol, alpha, ptr(g),
+                ptr(g_o), ptr(g_d), ptr(g_tv),
+            )
+        )
+        return g_o, g_d, g_tv, None, None, None, None
+
+
 def ray_intersect_triangle(
     ray_origins, ray_directions, triangle_vertices, *, epsilon=None, smoothing_factor=None
 ):
@@ -180,7 +253,7 @@ def ray_intersect_triangle(
 
     ``t`` is returned even where ``hit`` is false; ``epsilon`` defaults to ``10 * eps(float32)``.
     With ``smoothing_factor`` the hit is a float in [0, 1] (sigmoid relaxation, reference
-    ``_utils.py:1279-1318``); that variant is forward-only (no gradient).
+    ``_utils.py:1279-1318``) and both outputs are differentiable.
     """
     pl = Placement()
     o = pl.put(ray_origins, torch.float32)
@@ -191,6 +264,13 @@ def ray_intersect_triangle(
     t = torch.empty(batch, dtype=torch.float32, device=o.device)
     if smoothing_factor is not None:
         hit_f = torch.empty(batch, dtype=torch.float32, device=o.device)
+        if n > 0 and torch.is_grad_enabled() and any(x.requires_grad for x in (o, d, tv)):
+            # autograd of `expand` sums the per-element cotangents over the broadcast axes
+            t, hit_f = _SmoothTriangle.apply(
+                o.expand(*batch, 3).reshape(n, 3).contiguous(), d.expand(*batch, 3).reshape(n, 3).contiguous(),
+                tv.expand(*batch, 3, 3).reshape(n, 3, 3).contiguous(), _default(epsilon, 10.0), float(smoothing_factor),
+            )
+            return pl.out(t.reshape(batch)), pl.out(hit_f.reshape(batch))
         if n > 0:
             ndim, shape, (so, sd, st), keep = batch_strides(batch, [(o.detach(), 1), (d.detach(), 1), (tv.detach(), 2)])
             check(
@@ -273,12 +353,21 @@ def ray_intersect_any_triangle(
         o.shape[:-1], d.shape[:-1], tv.shape[:-3], () if act is None else act.shape[:-1]
     )
     T = int(tv.shape[-3])
-    if smoothing_factor is not None:  # forward-only sigmoid relaxation (_utils.py:1465-1476) → float
+    if smoothing_factor is not None:  # sigmoid relaxation (_utils.py:1465-1476) → float
         outf = torch.zeros(batch, dtype=torch.float32, device=o.device)
         if T == 0 or numel(batch) == 0:
             return pl.out(outf)
         ob, db = o.expand(*batch, 3), d.expand(*batch, 3)
         eps, tol = _default(kwargs.get("epsilon"), 10.0), _default(hit_tol, 100.0)
+        if torch.is_grad_enabled() and any(x.requires_grad for x in (o, d, tv)):
+            mesh_batch = torch.broadcast_shapes(tv.shape[:-3], () if act is None else act.shape[:-1])
+            if numel(mesh_batch) != 1:
+                raise NotImplementedError("gradient of the relaxed any-hit over a BATCH of meshes is not built")
+            res = _SmoothAnyTriangle.apply(
+                ob.reshape(-1, 3).contiguous(), db.reshape(-1, 3).contiguous(), tv.reshape(-1, 3, 3).contiguous(),
+                None if act is None else act.reshape(-1).contiguous(), eps, tol, float(smoothing_factor),
+            )
+            return pl.out(res.reshape(batch))
         for sel, tvi, acti in _mesh_batches(batch, tv, act):
             oi, di = ob[sel].reshape(-1, 3).contiguous(), db[sel].reshape(-1, 3).contiguous()
             pack = pack_triangle_vertices(tvi.contiguous(), None if acti is None else acti.contiguous())

@@ -288,7 +288,7 @@ DRT_API int drt_digraph_candidates(drt_stream_t stream, int64_t num_nodes, int32
                            int32_t stride_multiplier, int32_t *out);
 
 /* ---------------------------------------------------------------------------------------------
- * N4  smoothed variants of the primitives (forward only) and of the trace (forward + reverse): comparisons → sigmoid(x * smoothing_factor)
+ * N4  smoothed variants of the primitives and of the trace, forward and reverse mode: comparisons → sigmoid(x * smoothing_factor)
  *     (reference: differt/src/differt/utils.py:70-89), AND → min, OR over triangles → sum clipped at 1
  *     (_utils.py:1279-1318, 1465-1476; _solver_image_method.py:448-454).  Float outputs in [0,1];
  *     parity to 1e-5 (transcendental), not bit-exact.  Masked-out triangles of a pack contribute 0.
@@ -308,6 +308,24 @@ DRT_API int drt_consecutive_vertices_are_on_same_side_of_mirror_smooth(
     const float *vertices, const int64_t *v_strides_host, const float *mirror_vertices,
     const int64_t *mv_strides_host, const float *mirror_normals, const int64_t *mn_strides_host,
     float smoothing_factor, float *out);
+
+/* Reverse mode of the two relaxed primitives called on their own (flat, already broadcast inputs).
+ * Elementwise: cotangents g_t / g_hit [n] (each nullable) → g_o, g_d [n,3], g_triangle_vertices
+ * [n,3,3] (overwritten; the caller sums over its broadcast axes).  Any-hit: cotangent g_out [R] →
+ * g_o, g_d [R,3] (overwritten) and g_triangle_vertices [T,3,3] (zeroed, then accumulated with float
+ * atomics); rays whose sum reached the clip at 1 pass nothing.  The same-side relaxation depends on
+ * signs only: its gradient is identically zero and has no entry point. */
+DRT_API int drt_ray_intersect_triangle_smooth_vjp(drt_stream_t stream, int64_t n, const float *ray_origins,
+                                          const float *ray_directions, const float *triangle_vertices,
+                                          float epsilon, float smoothing_factor, const float *g_t,
+                                          const float *g_hit, float *g_origins, float *g_directions,
+                                          float *g_triangle_vertices);
+DRT_API int drt_ray_intersect_any_triangle_smooth_vjp(drt_stream_t stream, int64_t num_rays,
+                                              const float *ray_origins, const float *ray_directions,
+                                              const void *pack, int64_t num_triangles, float epsilon,
+                                              float hit_tol, float smoothing_factor, const float *g_out,
+                                              float *g_origins, float *g_directions,
+                                              float *g_triangle_vertices);
 
 /* The relaxed trace + validate step: _trace_path_candidates with smoothing_factor (reference:
  * _solvers.py:576-719, the `smoothing_factor is not None` branches).  Same inputs and dense

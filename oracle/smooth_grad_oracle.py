@@ -27,9 +27,15 @@ def _sig(x, alpha):
     return torch.sigmoid(x * alpha)
 
 
+def _cross(a, b):  # broadcasting cross product (torch.linalg.cross wants equal ranks)
+    return torch.stack((a[..., 1] * b[..., 2] - a[..., 2] * b[..., 1],
+                        a[..., 2] * b[..., 0] - a[..., 0] * b[..., 2],
+                        a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0]), -1)
+
+
 def _mt(o, d, v0, e1, e2, eps, alpha):
     """relaxed Möller–Trumbore → (t, hit); broadcasting on the leading axes"""
-    h = torch.linalg.cross(d, e2)
+    h = _cross(d, e2)
     a = (h * e1).sum(-1)
     a = torch.where(a == 0, torch.full_like(a, float("inf")), a)
     hit = _sig(a.abs() - eps, alpha)
@@ -38,7 +44,7 @@ def _mt(o, d, v0, e1, e2, eps, alpha):
     u = f * (s * h).sum(-1)
     one = torch.ones_like(hit)
     hit = torch.stack((hit, _sig(u, alpha), _sig(1.0 - u, alpha), one), -1).amin(-1)
-    q = torch.linalg.cross(s, e1)
+    q = _cross(s, e1)
     v = f * (q * d).sum(-1)
     hit = torch.stack((hit, _sig(v, alpha), _sig(1.0 - (u + v), alpha), one), -1).amin(-1)
     t = f * (q * e2).sum(-1)
@@ -123,3 +129,26 @@ def relaxed_trace(vertices, triangles, tx, rx, cand, *, mask=None, assume_quads=
     sel = torch.nonzero(finite).reshape(-1)
     full, conf = forward(sel)
     return full, conf, idx[sel]
+
+
+def ray_intersect_triangle_smooth(ray_origins, ray_directions, triangle_vertices, *, epsilon=None,
+                                  smoothing_factor=1.0):
+    """``_utils.py:1263-1322`` with smoothing, differentiable float64 tensors, broadcasting →
+    ``(t, hit)``."""
+    eps = 10 * F32_EPS if epsilon is None else float(epsilon)
+    tv = triangle_vertices
+    return _mt(ray_origins, ray_directions, tv[..., 0, :], tv[..., 1, :] - tv[..., 0, :],
+               tv[..., 2, :] - tv[..., 0, :], eps, float(smoothing_factor))
+
+
+def ray_intersect_any_triangle_smooth(ray_origins, ray_directions, triangle_vertices, active=None, *,
+                                      epsilon=None, hit_tol=None, smoothing_factor=1.0):
+    """``_utils.py:1452-1476`` with smoothing: clipped sum over the active triangles."""
+    thr = 1.0 - (100 * F32_EPS if hit_tol is None else float(hit_tol))
+    alpha = float(smoothing_factor)
+    t, hit = ray_intersect_triangle_smooth(ray_origins[..., None, :], ray_directions[..., None, :],
+                                           triangle_vertices, epsilon=epsilon, smoothing_factor=alpha)
+    term = torch.minimum(hit, _sig(thr - t, alpha))
+    if active is not None:
+        term = term * torch.as_tensor(np.asarray(active, bool)).to(term.dtype)
+    return term.sum(-1).clamp(max=1.0)

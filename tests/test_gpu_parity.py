@@ -1337,6 +1337,54 @@ def test_smoothed_trace_edge_cases(drt, two_buildings, rng):
     np.testing.assert_allclose(p.mask.cpu().numpy(), e, rtol=1e-5)
 
 
+@pytest.mark.parametrize("alpha", [0.5, 4.0, 40.0])
+def test_smoothed_primitives_gradients_vs_autograd_oracle(drt, alpha):
+    # jax.grad of the relaxed primitives (_utils.py:1263-1322, 1452-1476): float64 torch oracle
+    from oracle import smooth_grad_oracle as sg
+
+    r = np.random.default_rng(21)
+    tri = r.normal(size=(7, 3, 3)).astype(np.float32)
+    o = r.normal(size=(60, 3)).astype(np.float32)
+    d = (r.normal(size=(60, 3)) * 2).astype(np.float32)
+    wt, wh = r.normal(size=(60, 7)).astype(np.float32), r.normal(size=(60, 7)).astype(np.float32)
+
+    def leaves(dtype, dev):
+        return [torch.tensor(x, dtype=dtype, device=dev, requires_grad=True) for x in (o, d, tri)]
+
+    # elementwise, with broadcasting on both sides ([60,1] rays x [7] triangles): t and hit carry gradients
+    co, cd, ct = leaves(torch.float32, "cuda")
+    t, hit = drt.ray_intersect_triangle(co[:, None], cd[:, None], ct, smoothing_factor=alpha)
+    ((t * torch.from_numpy(wt).cuda()).sum() + (hit * torch.from_numpy(wh).cuda()).sum()).backward()
+    eo, ed, et = leaves(torch.float64, "cpu")
+    t64, hit64 = sg.ray_intersect_triangle_smooth(eo[:, None], ed[:, None], et, smoothing_factor=alpha)
+    np.testing.assert_allclose(hit.detach().cpu().numpy(), hit64.detach().numpy(), rtol=1e-4, atol=1e-5)
+    ((t64 * torch.from_numpy(wt).double()).sum() + (hit64 * torch.from_numpy(wh).double()).sum()).backward()
+    for name, got, exp in (("o", co.grad, eo.grad), ("d", cd.grad, ed.grad), ("tri", ct.grad, et.grad)):
+        e = exp.numpy()
+        np.testing.assert_allclose(got.cpu().numpy(), e, rtol=2e-3, atol=2e-3 * np.abs(e).max(), err_msg=name)
+
+    # any-hit: few triangles so that some sums stay below the clip, with and without a mask
+    w = r.normal(size=60).astype(np.float32)
+    for act in (None, np.array([True, False, True, True, False, True, True])):
+        co, cd, ct = leaves(torch.float32, "cuda")
+        got = drt.ray_intersect_any_triangle(co, cd, ct, act, smoothing_factor=alpha)
+        (got * torch.from_numpy(w).cuda()).sum().backward()
+        eo, ed, et = leaves(torch.float64, "cpu")
+        exp = sg.ray_intersect_any_triangle_smooth(eo, ed, et, act, smoothing_factor=alpha)
+        np.testing.assert_allclose(got.detach().cpu().numpy(), exp.detach().numpy(), rtol=1e-4, atol=1e-5)
+        assert (exp < 1).any()
+        (exp * torch.from_numpy(w).double()).sum().backward()
+        for name, g, e in (("o", co.grad, eo.grad), ("d", cd.grad, ed.grad), ("tri", ct.grad, et.grad)):
+            e = e.numpy()
+            np.testing.assert_allclose(g.cpu().numpy(), e, rtol=2e-3, atol=2e-3 * max(np.abs(e).max(), 1e-6), err_msg=name)
+        if act is not None:
+            assert (ct.grad[~torch.from_numpy(act).cuda()] == 0).all()  # masked-out triangles get no gradient
+    # the same-side relaxation is a function of signs: no gradient, as in the reference
+    v = torch.from_numpy(r.normal(size=(5, 4, 3)).astype(np.float32)).cuda().requires_grad_(True)
+    mv = torch.from_numpy(r.normal(size=(5, 2, 3)).astype(np.float32)).cuda()
+    assert not drt.consecutive_vertices_are_on_same_side_of_mirror(v, mv, mv, smoothing_factor=alpha).requires_grad
+
+
 def _ground_and_wall(order, quads):
     import itertools
 

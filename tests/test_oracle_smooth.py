@@ -117,3 +117,24 @@ def test_gradient_oracle_agrees_with_finite_differences():
         fd = (loss(*plus) - loss(*minus)).item() / (2 * h)
         an = (a.grad * d).sum().item()
         assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)), (k, fd, an)
+
+
+def test_gradient_oracle_primitives_match_numpy_oracle():
+    import torch
+
+    from oracle import smooth_grad_oracle as sg
+
+    r = np.random.default_rng(21)
+    tri = r.normal(size=(7, 3, 3)).astype(np.float32)
+    o = r.normal(size=(60, 3)).astype(np.float32)
+    d = (r.normal(size=(60, 3)) * 2).astype(np.float32)
+    T64 = lambda x: torch.tensor(x, dtype=torch.float64)  # noqa: E731
+    for alpha in (0.5, 4.0, 40.0):
+        t, hit = sg.ray_intersect_triangle_smooth(T64(o)[:, None], T64(d)[:, None], T64(tri), smoothing_factor=alpha)
+        et, eh = orc.ray_intersect_triangle_smooth(o[:, None], d[:, None], tri, smoothing_factor=alpha)
+        np.testing.assert_allclose(hit.numpy(), eh, rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(t.numpy(), et, rtol=1e-3, atol=1e-4)
+        for act in (None, np.array([True, False, True, True, False, True, True])):
+            got = sg.ray_intersect_any_triangle_smooth(T64(o), T64(d), T64(tri), act, smoothing_factor=alpha)
+            exp = orc.ray_intersect_any_triangle_smooth(o, d, tri, act, smoothing_factor=alpha)
+            np.testing.assert_allclose(got.numpy(), exp, rtol=1e-4, atol=1e-5)
