@@ -14,6 +14,7 @@ from .geometry import (
     image_method,
     image_of_vertex_with_respect_to_mirror,
     intersection_of_ray_with_plane,
+    path_length,
     ray_intersect_any_triangle,
     ray_intersect_triangle,
     triangles_visible_from_vertex,
@@ -42,6 +43,7 @@ __all__ = [
     "compute_tx_mlm",
     "launch_paths",
     "launch_rays",
+    "path_length",
     "TracedPaths",
     "VisiblePathCandidates",
     "generate_visible_path_candidates",

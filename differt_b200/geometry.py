@@ -120,6 +120,14 @@ def normalize(vectors, keepdims: bool = False):
     return pl.out(v / safe), pl.out(lengths if keepdims else lengths.squeeze(-1))
 
 
+def path_length(path):
+    """Reference ``_utils.py:150-182``: sum of the segment lengths of ``[*batch, path_length, 3]``
+    (host-side helper on ``torch`` ops: differentiable, the usual ``fun`` of ``TracedPaths.reduce``)."""
+    pl = Placement()
+    p = pl.put(path, torch.float32)
+    return pl.out(torch.linalg.norm(p[..., 1:, :] - p[..., :-1, :], dim=-1).sum(dim=-1))
+
+
 def assemble_path(from_vertex, intermediate_vertices, to_vertex=None):
     """Reference ``_utils.py:514-565``: concatenate ``[from, *intermediate, to]`` on axis -2."""
     pl = Placement()

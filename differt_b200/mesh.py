@@ -288,6 +288,20 @@ class TracedPaths:
             confidence_threshold=self.confidence_threshold,
         )
 
+    def reduce(self, fun, axis=None) -> torch.Tensor:
+        """``sum(fun(vertices) * mask)`` over ``axis`` (all axes by default) — reference
+        ``_paths.py:461-479``: the first consumer of traced paths (received power, delay spread …).
+        With a float mask (relaxed trace) the confidences weight the sum and the result is
+        differentiable w.r.t. the scene through both ``vertices`` and ``mask``; with a boolean mask
+        invalid paths contribute exactly zero (``where=mask``: their ``fun`` value, possibly NaN or
+        inf, is never added)."""
+        values = fun(self.vertices)
+        if self.mask.dtype != torch.bool:
+            values = values * self.mask
+        else:
+            values = torch.where(self.mask, values, torch.zeros_like(values))
+        return values.sum() if axis is None else values.sum(dim=axis)
+
     @property
     def masked_vertices(self) -> torch.Tensor:
         return self.masked().vertices

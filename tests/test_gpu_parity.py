@@ -1385,6 +1385,50 @@ def test_smoothed_primitives_gradients_vs_autograd_oracle(drt, alpha):
     assert not drt.consecutive_vertices_are_on_same_side_of_mirror(v, mv, mv, smoothing_factor=alpha).requires_grad
 
 
+def test_reduce_and_gradient_ascent_on_relaxed_power(drt):
+    # TracedPaths.reduce (_paths.py:461-479) + path_length (_utils.py:150-182): the consumer the relaxed
+    # trace exists for.  J(tx) = sum over order-0/1 paths of confidence / length^2 is differentiable in
+    # the transmitter position; check d J against a finite difference and climb it.
+    v, t, _, rx, _ = _ground_and_wall(1, False)
+    mesh = drt.Mesh.from_numpy(v, t)
+    rxc = torch.from_numpy(rx).cuda()
+
+    def power(tx, alpha=4.0):
+        total = 0.0
+        for order in (0, 1):
+            paths = drt.trace_paths(mesh, tx, rxc, order, smoothing_factor=alpha)
+            total = total + paths.reduce(lambda p: 1.0 / drt.path_length(p) ** 2)
+        return total
+
+    tx = torch.tensor([[-6.0, 1.0, 2.0]], device="cuda", requires_grad=True)
+    j0 = power(tx)
+    j0.backward()
+    g = tx.grad.clone()
+    assert torch.isfinite(g).all() and g.abs().max() > 0
+    step = 1e-2 * g / g.norm()
+    with torch.no_grad():
+        fd = (power(tx + step) - power(tx - step)) / 2e-2
+    assert abs(fd.item() - g.norm().item()) <= 0.05 * g.norm().item()
+    cur = tx.detach().clone()
+    for _ in range(25):
+        cur.requires_grad_(True)
+        j = power(cur)
+        (gc,) = torch.autograd.grad(j, cur)
+        cur = (cur + 0.3 * gc / gc.norm()).detach()
+    assert power(cur).item() > 1.2 * j0.item()
+
+    # boolean mask: reduce adds the valid paths only, whatever fun returns on the others
+    hard = drt.trace_paths(mesh, tx.detach(), rxc, 1)
+    lengths = drt.path_length(hard.vertices)
+    exp = lengths[hard.mask].sum()
+    got = hard.reduce(lambda p: torch.where(hard.mask, drt.path_length(p), torch.full_like(lengths, float("nan"))))
+    torch.testing.assert_close(got, exp)
+    per_rx = hard.reduce(drt.path_length, axis=-1)
+    assert tuple(per_rx.shape) == (1, rx.shape[0])
+    torch.testing.assert_close(per_rx.sum(), exp)
+    np.testing.assert_allclose(drt.path_length(np.array([[1.0, 0, 0], [1, 1, 0], [1, 0, 0]], np.float32)), 2.0)
+
+
 def _ground_and_wall(order, quads):
     import itertools
 
