@@ -12,28 +12,47 @@
 namespace drt {
 
 __device__ __forceinline__ float smooth(float x, float alpha) {  // jax.nn.sigmoid(x * alpha)
-    return __fdiv_rn(1.0f, 1.0f + expf(-(x * alpha)));
+    // 1 / y correctly rounded: the same value as __fdiv_rn(1, y), without the generic division path
+    return __frcp_rn(1.0f + expf(-(x * alpha)));
 }
 
 // jnp.min / jnp.minimum propagate NaN; fminf would drop it
 __device__ __forceinline__ float nanmin(float a, float b) { return (a != a || b != b) ? CUDART_NAN_F : fminf(a, b); }
 
-// _utils.py:1263-1322 with smoothing_factor; returns the smoothed hit, writes t
+// The sigmoid is monotone, so the reference's min over sigmoids (_utils.py:1279-1318: AND → min) is the
+// sigmoid of the min of their arguments (max for a negative slope): ONE exponential per relaxed test
+// instead of seven.  NaN arguments propagate like in jnp.min; the constant 1 of the reference's stacks
+// never wins (sigmoid <= 1).  `m` is min_i x_i for alpha >= 0, max_i x_i otherwise.
+struct RelaxedArgs {
+    float sgn;  // +1 (alpha >= 0) or -1
+    float m;    // running extremum of sgn * x_i
+    __device__ __forceinline__ explicit RelaxedArgs(float alpha, float x0) : sgn(alpha < 0.0f ? -1.0f : 1.0f), m(sgn * x0) {}
+    __device__ __forceinline__ void add(float x) { m = nanmin(m, sgn * x); }
+    __device__ __forceinline__ float value(float alpha) const { return smooth(sgn * m, alpha); }
+};
+
+// _utils.py:1263-1322 with smoothing_factor; returns the smoothed hit, writes t.  `extra` (blockage):
+// also folds sigmoid((thr - t) alpha) into the min (_utils.py:1465-1473).
 __device__ __forceinline__ float mt_smooth(const float3 o, const float3 d, const Tri &tr, const float eps,
-                                           const float alpha, float &t) {
+                                           const float alpha, float &t, const bool extra = false,
+                                           const float thr = 0.0f) {
     const float3 h = cross3(d, tr.e2);
     float a = dot3(h, tr.e1);
     a = (a == 0.0f) ? CUDART_INF_F : a;
-    float hit = smooth(fabsf(a) - eps, alpha);
+    RelaxedArgs r(alpha, fabsf(a) - eps);
     const float f = __frcp_rn(a);
     const float3 s = sub3(o, tr.v0);
     const float u = f * dot3(s, h);
-    hit = nanmin(nanmin(hit, smooth(u - 0.0f, alpha)), nanmin(smooth(1.0f - u, alpha), 1.0f));
+    r.add(u - 0.0f);
+    r.add(1.0f - u);
     const float3 q = cross3(s, tr.e1);
     const float v = f * dot3(q, d);
-    hit = nanmin(nanmin(hit, smooth(v - 0.0f, alpha)), nanmin(smooth(1.0f - (u + v), alpha), 1.0f));
+    r.add(v - 0.0f);
+    r.add(1.0f - (u + v));
     t = f * dot3(q, tr.e2);
-    return nanmin(hit, smooth(t - eps, alpha));
+    r.add(t - eps);
+    if (extra) r.add(thr - t);
+    return r.value(alpha);
 }
 
 __global__ void mt_smooth_elementwise_kernel(int64_t n, Batch4 bt, const float *__restrict__ o,
@@ -69,8 +88,7 @@ any_smooth_kernel(int64_t R, int64_t T, const float *__restrict__ o, const float
         const float4 a = pack[j].a, b = pack[j].b, c = pack[j].c;
         if (a.x != a.x && a.y != a.y && a.z != a.z && a.w == 0.0f) continue;  // never-hit record: inactive
         float t;
-        const float hit = mt_smooth(oo, dd, unpack(a, b, c), eps, alpha, t);
-        acc += nanmin(hit, smooth(thr - t, alpha));
+        acc += mt_smooth(oo, dd, unpack(a, b, c), eps, alpha, t, true, thr);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
@@ -215,8 +233,7 @@ __global__ void __launch_bounds__(256) trace_smooth_blocked_kernel(const SmoothT
 #pragma unroll
             for (int s = 0; s < NSEG; ++s) {
                 float t;
-                const float hit = mt_smooth(o[s], d[s], tr, a.eps, a.alpha, t);
-                acc[s] += nanmin(hit, smooth(a.thr - t, a.alpha));
+                acc[s] += mt_smooth(o[s], d[s], tr, a.eps, a.alpha, t, true, a.thr);
             }
         }
         float blocked = 0.0f;
@@ -284,28 +301,30 @@ __device__ __forceinline__ bool mt_smooth_adjoint(const float3 o, const float3 d
     const float t = f * qt;
     float ga = 0.f, gu = 0.f, gv = 0.f;
     if (select != 0) {
-        float best = smooth(fabsf(a) - eps, alpha);
+        // first extremal argument (the forward's RelaxedArgs), then one sigmoid derivative
+        const float sg = alpha < 0.0f ? -1.0f : 1.0f;
+        float best = sg * (fabsf(a) - eps);
         int which = 0;
         bool nan = best != best;
 #define DRT_CONSIDER(val, id)            \
     {                                    \
-        const float x_ = (val);          \
+        const float x_ = sg * (val);     \
         nan = nan || (x_ != x_);         \
         if (x_ < best) {                 \
             best = x_;                   \
             which = (id);                \
         }                                \
     }
-        DRT_CONSIDER(smooth(u - 0.0f, alpha), 1)
-        DRT_CONSIDER(smooth(1.0f - u, alpha), 2)
-        DRT_CONSIDER(1.0f, 7)
-        DRT_CONSIDER(smooth(v - 0.0f, alpha), 3)
-        DRT_CONSIDER(smooth(1.0f - (u + v), alpha), 4)
-        DRT_CONSIDER(smooth(t - eps, alpha), 5)
-        if (select == 2) DRT_CONSIDER(smooth(thr - t, alpha), 6)
+        DRT_CONSIDER(u - 0.0f, 1)
+        DRT_CONSIDER(1.0f - u, 2)
+        DRT_CONSIDER(v - 0.0f, 3)
+        DRT_CONSIDER(1.0f - (u + v), 4)
+        DRT_CONSIDER(t - eps, 5)
+        if (select == 2) DRT_CONSIDER(thr - t, 6)
 #undef DRT_CONSIDER
-        float ds = g * alpha * best * (1.0f - best);  // d sigmoid(x alpha) / dx, times the cotangent
-        if (nan || which == 7 || ds != ds) ds = 0.0f;
+        const float sv = smooth(sg * best, alpha);
+        float ds = g * alpha * sv * (1.0f - sv);  // d sigmoid(x alpha) / dx, times the cotangent
+        if (nan || ds != ds) ds = 0.0f;
         switch (which) {
             case 0: ga = a < 0.0f ? -ds : ds; break;
             case 1: gu = ds; break;
@@ -313,8 +332,7 @@ __device__ __forceinline__ bool mt_smooth_adjoint(const float3 o, const float3 d
             case 3: gv = ds; break;
             case 4: gu = -ds; gv = -ds; break;
             case 5: gt += ds; break;
-            case 6: gt -= ds; break;
-            default: break;
+            default: gt -= ds; break;
         }
     }
     if (ga == 0.0f && gu == 0.0f && gv == 0.0f && gt == 0.0f) return false;
@@ -383,8 +401,7 @@ any_smooth_vjp_kernel(int64_t R, int64_t T, const float *__restrict__ o, const f
         const float4 a = pack[j].a, b = pack[j].b, c = pack[j].c;
         if (a.x != a.x && a.y != a.y && a.z != a.z && a.w == 0.0f) continue;
         float t;
-        const float hit = mt_smooth(oo, dd, unpack(a, b, c), eps, alpha, t);
-        acc += nanmin(hit, smooth(thr - t, alpha));
+        acc += mt_smooth(oo, dd, unpack(a, b, c), eps, alpha, t, true, thr);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(kFull, acc, off);
@@ -585,8 +602,7 @@ __global__ void __launch_bounds__(256) trace_smooth_vjp_blocked_kernel(const Smo
 #pragma unroll
         for (int s = 0; s < NSEG; ++s) {
             float t;
-            const float hit = mt_smooth(o[s], d[s], tr, fa.eps, fa.alpha, t);
-            acc[s] += nanmin(hit, smooth(fa.thr - t, fa.alpha));
+            acc[s] += mt_smooth(o[s], d[s], tr, fa.eps, fa.alpha, t, true, fa.thr);
         }
     }
     int best_s = 0;
