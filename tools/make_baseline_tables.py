@@ -3,12 +3,12 @@
 import json,re
 json.dump({
  "source": "profiles/r1_ncu_dram_traffic_bench_workload.csv (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum; bench workload urban10k_1tx_4096rx_order3; 30 consecutive launches of the blockage kernels = a little more than one step)",
- "dram_bytes_per_launch": int(2071018240 * 3 / 16 * 1 + 2071018240 * 0),
- "dram_bytes_per_step": 2071018240 + 24238336,
+ "dram_bytes_per_launch": 2071018240 + 24238336,
  "per_kernel": {
    "path_head_kernel<4> (16 launches: cascade passes over all candidates + greedy-round passes over the samples)": {"dram_bytes": 2071018240, "ns": 89383232},
    "hit_count_kernel<4> (14 launches: ordering pass rounds)": {"dram_bytes": 24238336, "ns": 10832832}},
- "note": "the blockage pass reads the 1.0 GB of path vertices written by stage A (60 B per candidate, fetched as partial 32 B sectors) and writes the mask bytes and the survivor lists; the packed mesh never comes from DRAM"
+ "note": "the blockage pass reads the 1.0 GB of path vertices written by stage A (60 B per candidate, fetched as partial 32 B sectors) and writes the mask bytes and the survivor lists; the packed mesh never comes from DRAM",
+ "dram_bytes_per_launch_note": "per step = per bracketed blockage pass (the unit roofline.achieved uses)"
 }, open('/root/repo/profiles/traffic.json','w'), indent=1)
 p='/root/repo/bench.py'
 s=open(p).read()
