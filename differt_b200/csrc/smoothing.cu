@@ -16,8 +16,13 @@ __device__ __forceinline__ float smooth(float x, float alpha) {  // jax.nn.sigmo
     return __frcp_rn(1.0f + expf(-(x * alpha)));
 }
 
-// jnp.min / jnp.minimum propagate NaN; fminf would drop it
-__device__ __forceinline__ float nanmin(float a, float b) { return (a != a || b != b) ? CUDART_NAN_F : fminf(a, b); }
+// jnp.min / jnp.minimum propagate NaN; fminf would drop it.  One FMNMX.NAN instead of two compares,
+// a select and a min.
+__device__ __forceinline__ float nanmin(float a, float b) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
 
 // The sigmoid is monotone, so the reference's min over sigmoids (_utils.py:1279-1318: AND → min) is the
 // sigmoid of the min of their arguments (max for a negative slope): ONE exponential per relaxed test
@@ -115,7 +120,11 @@ same_side_smooth_kernel(int64_t n, int K, Batch4 bt, const float *__restrict__ v
 }
 
 // jnp.max propagates NaN as well
-__device__ __forceinline__ float nanmax(float a, float b) { return (a != a || b != b) ? CUDART_NAN_F : fmaxf(a, b); }
+__device__ __forceinline__ float nanmax(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
 
 struct SmoothTraceArgs {
     const Tri48 *pack;        // geometry of every triangle (mask NOT applied): mirrors + inside test
