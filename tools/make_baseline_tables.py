@@ -69,7 +69,7 @@ for r in k["rows"]:
 # the relaxed (smoothing_factor) trace, measured separately (tools/bench_relaxed.py)
 rl=json.load(open('/root/repo/profiles/r1_relaxed_trace.json'))
 lines+=["","### Relaxed (`smoothing_factor`) trace, forward and reverse mode (`tools/bench_relaxed.py`, `profiles/r1_relaxed_trace.json`)","",
-"Street canyon (986 triangles), 1 TX × 256 RX × 4096 sampled order-2 candidates = 1.05·10⁶ paths; the relaxed blockage is a clipped SUM over all triangles, so all 3.1·10⁹ (segment, triangle) pairs are evaluated — no early exit, no ordering.  The `min` over the reference's seven sigmoids per pair is computed as the sigmoid of the min of their arguments (one `expf` + one reciprocal per pair): 40.7 → 32.6 (reciprocal instead of division) → 14.7 (one sigmoid) → 11.8 ms (NaN-propagating `min.NaN.f32`, fused by ptxas into 3-input `FMNMX3.NAN`, instead of compare/select chains).  `ncu --set full` of the blockage kernel (`profiles/r1_ncu_full_relaxed_blockage.json`): issue-slot utilisation 86 %, DRAM traffic 56 MB per launch (the packed mesh stays in L1/L2: 99.9 % L1 hit rate) — instruction-issue bound like the hard path.","",
+"Street canyon (986 triangles), 1 TX × 256 RX × 4096 sampled order-2 candidates = 1.05·10⁶ paths; the relaxed blockage is a clipped SUM over all triangles, so all 3.1·10⁹ (segment, triangle) pairs are evaluated — no early exit, no ordering.  The `min` over the reference's seven sigmoids per pair is computed as the sigmoid of the min of their arguments (one `expf` + one reciprocal per pair): 40.7 → 32.6 (reciprocal instead of division) → 14.7 (one sigmoid) → 11.8 ms (NaN-propagating `min.NaN.f32`, fused by ptxas into 3-input `FMNMX3.NAN`, instead of compare/select chains).  `ncu --set full` of the blockage kernel (`profiles/r1_ncu_full_relaxed_blockage.json`): issue-slot utilisation 89 % (124 warp instructions per evaluation), DRAM traffic 56 MB per launch (the packed mesh stays in L1/L2: 99.9 % L1 hit rate) — instruction-issue bound like the hard path.","",
 "| kernel | ms | relaxed pair evaluations / s | note |","|---|---|---|---|"]
 for r in rl["rows"]:
     lines.append(f"| {r['kernel'].strip()} | {r['ms']:.3f} | {r['relaxed_tests_per_s']:.3g} | {r['note']} |")
