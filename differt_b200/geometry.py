@@ -51,14 +51,6 @@ __all__ = [
 _SORT_MIN_RAYS = 4096
 
 
-def _no_smoothing(smoothing_factor: Any) -> None:
-    if smoothing_factor is not None:
-        raise NotImplementedError(
-            "smoothing_factor is not supported here (SURVEY.md §8a); "
-            "the reference falls back to pure JAX in this case (_solvers.py:665-674)"
-        )
-
-
 def _default(value, factor: float) -> float:
     return factor * F32_EPS if value is None else float(value)
 

@@ -249,3 +249,90 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(DrtCompleteGraphCandidates, CompleteGraphCandidate
                                   .Attr<int64_t>("start")
                                   .Attr<int64_t>("stride_multiplier")
                                   .Ret<ffi::Buffer<ffi::S32>>());
+
+// relaxed (smoothing_factor) trace, forward: float confidences (_solvers.py:599-713)
+static ffi::Error TraceSmoothImpl(cudaStream_t stream, ffi::ScratchAllocator scratch,
+                                  ffi::Buffer<ffi::F32> vertices, ffi::Buffer<ffi::S32> triangles,
+                                  ffi::Buffer<ffi::U8> mask, ffi::Buffer<ffi::F32> tx, ffi::Buffer<ffi::F32> rx,
+                                  ffi::Buffer<ffi::S32> candidates, bool assume_quads, float epsilon,
+                                  float hit_tol, float min_len, float smoothing_factor,
+                                  ffi::ResultBuffer<ffi::F32> out_vertices, ffi::ResultBuffer<ffi::S32> out_objects,
+                                  ffi::ResultBuffer<ffi::F32> out_mask) {
+    const int64_t V = vertices.dimensions()[0], T = triangles.dimensions()[0];
+    const int64_t ntx = tx.dimensions()[0], nrx = rx.dimensions()[0], C = candidates.dimensions()[0];
+    const size_t ws_bytes = drt_trace_smooth_workspace_bytes(T, ntx, nrx, C);
+    auto ws = scratch.Allocate(ws_bytes);
+    if (!ws.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "trace workspace");
+    const uint8_t *m = mask.element_count() ? mask.typed_data() : nullptr;
+    return Check(drt_trace_path_candidates_smooth(
+        stream, V, T, vertices.typed_data(), triangles.typed_data(), m, assume_quads ? 1 : 0, ntx, tx.typed_data(),
+        nrx, rx.typed_data(), C, static_cast<int32_t>(candidates.dimensions()[1]), candidates.typed_data(), epsilon,
+        hit_tol, min_len, smoothing_factor, *ws, ws_bytes, out_vertices->typed_data(), out_objects->typed_data(),
+        out_mask->typed_data()));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DrtTracePathCandidatesSmooth, TraceSmoothImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Ctx<ffi::ScratchAllocator>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Attr<bool>("assume_quads")
+                                  .Attr<float>("epsilon")
+                                  .Attr<float>("hit_tol")
+                                  .Attr<float>("min_len")
+                                  .Attr<float>("smoothing_factor")
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::S32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>());
+
+// ... and its reverse mode: residuals (out_vertices, out_mask), cotangents of both → vertices, tx, rx
+static ffi::Error TraceSmoothVjpImpl(cudaStream_t stream, ffi::ScratchAllocator scratch,
+                                     ffi::Buffer<ffi::F32> vertices, ffi::Buffer<ffi::S32> triangles,
+                                     ffi::Buffer<ffi::U8> mask, ffi::Buffer<ffi::F32> tx, ffi::Buffer<ffi::F32> rx,
+                                     ffi::Buffer<ffi::S32> candidates, ffi::Buffer<ffi::F32> out_vertices,
+                                     ffi::Buffer<ffi::F32> out_mask, ffi::Buffer<ffi::F32> g_out_vertices,
+                                     ffi::Buffer<ffi::F32> g_out_mask, bool assume_quads, float epsilon,
+                                     float hit_tol, float min_len, float smoothing_factor,
+                                     ffi::ResultBuffer<ffi::F32> g_vertices, ffi::ResultBuffer<ffi::F32> g_tx,
+                                     ffi::ResultBuffer<ffi::F32> g_rx) {
+    const int64_t V = vertices.dimensions()[0], T = triangles.dimensions()[0];
+    const int64_t ntx = tx.dimensions()[0], nrx = rx.dimensions()[0], C = candidates.dimensions()[0];
+    const int32_t k = static_cast<int32_t>(candidates.dimensions()[1]);
+    const size_t ws_bytes = drt_trace_smooth_vjp_workspace_bytes(V, T, ntx, nrx, C, k);
+    auto ws = scratch.Allocate(ws_bytes);
+    if (!ws.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "trace VJP workspace");
+    const uint8_t *m = mask.element_count() ? mask.typed_data() : nullptr;
+    return Check(drt_trace_path_candidates_smooth_vjp(
+        stream, V, T, vertices.typed_data(), triangles.typed_data(), m, assume_quads ? 1 : 0, ntx, tx.typed_data(),
+        nrx, rx.typed_data(), C, k, candidates.typed_data(), epsilon, hit_tol, min_len, smoothing_factor,
+        out_vertices.typed_data(), out_mask.typed_data(), g_out_vertices.typed_data(), g_out_mask.typed_data(), *ws,
+        ws_bytes, g_tx->typed_data(), g_rx->typed_data(), g_vertices->typed_data()));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DrtTracePathCandidatesSmoothVjp, TraceSmoothVjpImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Ctx<ffi::ScratchAllocator>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Attr<bool>("assume_quads")
+                                  .Attr<float>("epsilon")
+                                  .Attr<float>("hit_tol")
+                                  .Attr<float>("min_len")
+                                  .Attr<float>("smoothing_factor")
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>());
