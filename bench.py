@@ -107,9 +107,10 @@ _REASONS = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_pow
 
 
 class ClockSampler:
-    """`nvidia-smi -lms 200` on this rank's GPU.  It is started BEFORE the warm-up steps (its NVML
-    start-up contends with kernel launches for a few hundred ms) and keeps polling through the timed
-    region; only the samples stamped inside [mark_start(), stop()] are reported."""
+    """`nvidia-smi -lms 200` on this rank's GPU.  It is started at the very beginning of the run and
+    the warm-up waits for its first sample (its NVML start-up contends with kernel launches for a few
+    hundred ms — seconds on an 8-GPU box); it keeps polling through the timed region and only the
+    samples stamped inside [mark_start(), stop()] are reported."""
 
     def __init__(self, device_index: int) -> None:
         import torch
@@ -127,6 +128,28 @@ class ClockSampler:
         except Exception:  # nvidia-smi missing: report no clocks rather than fail the bench
             self.proc = None
         self.t0 = time.time()
+        import atexit
+
+        atexit.register(self._kill)  # never leave the poller behind if the bench dies early
+
+    def _kill(self) -> None:
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.kill()
+
+    def wait_ready(self, timeout: float = 8.0) -> None:
+        """Block until nvidia-smi has printed its first sample (NVML initialised, steady polling) or
+        `timeout` elapses — so that its start-up can never fall inside the timed region, however few
+        warm-up and timed steps the caller asks for."""
+        if self.proc is None:
+            return
+        deadline = time.time() + timeout
+        while time.time() < deadline and self.proc.poll() is None:
+            try:
+                if os.path.getsize(self.file.name) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.05)
 
     def mark_start(self) -> None:
         self.t0 = time.time()
@@ -295,6 +318,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # started first, seconds before anything is timed (see ClockSampler)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -366,7 +391,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         torch.cuda.synchronize()
 
     # ---- kernel-level leg: inputs resident in HBM ------------------------------------------------
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_ready()
     for _ in range(6):  # set-up: allocator steady state and cold-start effects of a fresh box, before the
         step_resident(False)  # W warm-ups
     for _ in range(args.warmup):
