@@ -78,3 +78,31 @@ def test_public_api_refuses_to_run_without_a_gpu():
         drt.ray_intersect_triangle(np.zeros(3, np.float32), np.ones(3, np.float32), np.zeros((3, 3), np.float32))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         drt.Mesh.box()
+
+
+def test_traced_paths_float_mask_semantics_and_reduce():
+    # _paths.py:101-103, 270-283, 461-479: a float mask is a confidence, valid when >= the threshold
+    # (NaN never is); reduce() weights by it, or skips invalid paths entirely for a boolean mask
+    from differt_b200.mesh import TracedPaths
+
+    v = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)
+    o = torch.zeros((2, 3, 3), dtype=torch.int32)
+    it = torch.zeros((2, 3, 1), dtype=torch.int32)
+    conf = torch.tensor([[0.5, 0.49999, float("nan")], [1.0, 0.0, 0.75]])
+    soft = TracedPaths(vertices=v, objects=o, mask=conf, interaction_types=it)
+    assert soft.num_valid_paths == 3 and soft._valid().tolist() == [[True, False, False], [True, False, True]]
+    assert TracedPaths(vertices=v, objects=o, mask=conf, interaction_types=it, confidence_threshold=0.8).num_valid_paths == 1
+    length = lambda p: torch.linalg.norm(p[..., 1:, :] - p[..., :-1, :], dim=-1).sum(-1)  # noqa: E731
+    w = torch.nan_to_num(conf)
+    soft0 = TracedPaths(vertices=v, objects=o, mask=w, interaction_types=it)
+    torch.testing.assert_close(soft0.reduce(length), (length(v) * w).sum())
+    torch.testing.assert_close(soft0.reduce(length, axis=-1), (length(v) * w).sum(-1))
+    hard = TracedPaths(vertices=v, objects=o, mask=conf >= 0.5, interaction_types=it)
+    poisoned = lambda p: torch.where(hard.mask, length(p), torch.full((2, 3), float("inf")))  # noqa: E731
+    torch.testing.assert_close(hard.reduce(poisoned), length(v)[hard.mask].sum())
+    assert hard.num_valid_paths == 3 and hard.reshape(6).mask.shape == (6,)
+    # differentiable through both the vertices and the confidences
+    vg, cg = v.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    TracedPaths(vertices=vg, objects=o, mask=cg, interaction_types=it).reduce(length).backward()
+    torch.testing.assert_close(cg.grad, length(v))
+    assert vg.grad.abs().sum() > 0
