@@ -138,3 +138,15 @@ def test_gradient_oracle_primitives_match_numpy_oracle():
             got = sg.ray_intersect_any_triangle_smooth(T64(o), T64(d), T64(tri), act, smoothing_factor=alpha)
             exp = orc.ray_intersect_any_triangle_smooth(o, d, tri, act, smoothing_factor=alpha)
             np.testing.assert_allclose(got.numpy(), exp, rtol=1e-4, atol=1e-5)
+
+
+def test_smoothing_function_reference_kats():
+    # differt/tests/test_utils.py:58-82: limits of the sigmoid relaxation
+    r = np.random.default_rng(0)
+    alpha = r.uniform(0, 100, size=(20, 1)).astype(np.float32)
+    got = orc.smoothing_function(np.array([-1e8, 0.0, 1e8], np.float32), alpha)
+    np.testing.assert_allclose(got, np.broadcast_to(np.array([0.0, 0.5, 1.0], np.float32), got.shape), atol=1e-6)
+    x = (r.normal(size=(40, 1, 10)) * 1000.0).astype(np.float32)
+    x[0, 0, 0] = 0.0
+    np.testing.assert_array_equal(orc.smoothing_function(x, 1e8), 0.5 * (np.sign(x) + 1))
+    assert orc.smoothing_function(x, alpha).shape == (40, 20, 10)
