@@ -398,9 +398,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     # state HERE and the timed region never calls cudaMalloc (it would, once, in its second step).
     paths = None
     for _ in range(6):  # set-up: allocator steady state and cold-start effects of a fresh box, before the
-        paths = step_resident(False)  # W warm-ups
+        paths = step_resident(True)  # W warm-ups (same flags as the timed steps; the ring is reset below)
     for _ in range(args.warmup):
-        paths = step_resident(False)
+        paths = step_resident(True)
     barrier()
     stats_acc.zero_()
     _lib.check(_lib.lib.drt_profile_reset())
