@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
@@ -124,7 +125,61 @@ def _load() -> C.CDLL:
     return lib
 
 
-lib = _load()
+class _CurrentStream:
+    """Placeholder for the stream argument (``_tensor.stream_ptr()``): resolved by the call wrapper
+    once the device of the operands is known."""
+
+
+CURRENT_STREAM = _CurrentStream()
+_tls = threading.local()
+
+
+def begin_call() -> _CurrentStream:
+    """Start collecting the operands of one library call (always evaluated first: it is the first
+    argument of every stream-ordered entry point)."""
+    _tls.device = None
+    return CURRENT_STREAM
+
+
+def note_device(index: int) -> None:
+    """Called by ``_tensor.ptr`` for every device operand of the call being assembled."""
+    seen = getattr(_tls, "device", None)
+    if seen is None:
+        _tls.device = index
+    elif seen != index:
+        raise ValueError(f"differt_b200: operands live on different devices (cuda:{seen} and cuda:{index})")
+
+
+class _Library:
+    """The C ABI with device-correct launches: a call whose first argument is ``stream_ptr()`` runs
+    with the operands' device current and on THAT device's current stream — the kernels' dynamic
+    shared-memory attributes, the SM count and the stream are all per device (a process may drive
+    several GPUs, as JAX's single-process mode does)."""
+
+    def __init__(self, cdll: C.CDLL) -> None:
+        self._cdll = cdll
+
+    def __getattr__(self, name: str):
+        fn = getattr(self._cdll, name)
+
+        def call(*args):
+            if not args or args[0] is not CURRENT_STREAM:
+                return fn(*args)
+            import torch
+
+            dev = getattr(_tls, "device", None)
+            _tls.device = None
+            if dev is None or dev == torch.cuda.current_device():
+                return fn(C.c_void_p(torch.cuda.current_stream().cuda_stream), *args[1:])
+            with torch.cuda.device(dev):
+                return fn(C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), *args[1:])
+
+        call.__name__ = name
+        setattr(self, name, call)  # cache: __getattr__ is only consulted on a miss
+        return call
+
+
+lib = _Library(_load())
 
 
 class DrtError(RuntimeError):

@@ -12,7 +12,7 @@ from typing import Sequence
 import numpy as np
 import torch
 
-from ._lib import DRT_MAX_BATCH_DIMS, i64_array
+from ._lib import DRT_MAX_BATCH_DIMS, begin_call, i64_array, note_device
 
 F32_EPS = float(np.finfo(np.float32).eps)
 
@@ -25,12 +25,18 @@ def require_cuda() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def stream_ptr() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr():
+    """First argument of every stream-ordered library call: the current stream of the device the
+    call's operands live on (resolved by ``_lib._Library`` once ``ptr`` has seen them)."""
+    return begin_call()
 
 
 def ptr(t: torch.Tensor | None) -> C.c_void_p:
-    return C.c_void_p(0 if t is None or t.numel() == 0 else t.data_ptr())
+    if t is None or t.numel() == 0:
+        return C.c_void_p(0)
+    if t.is_cuda:
+        note_device(t.device.index)
+    return C.c_void_p(t.data_ptr())
 
 
 class Placement:

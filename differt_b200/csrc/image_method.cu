@@ -159,7 +159,7 @@ static int fill_batch(int32_t ndim, const int64_t *shape, const int64_t *s0, con
 
 static unsigned grid_for(int64_t n, int threads) {
     const int64_t blocks = (n + threads - 1) / threads;
-    return unsigned(blocks < 148 * 16 ? blocks : 148 * 16);
+    return unsigned(blocks < int64_t(drt::device_sm_count()) * 16 ? blocks : int64_t(drt::device_sm_count()) * 16);
 }
 
 }  // namespace drt

@@ -268,7 +268,7 @@ int drt_ray_intersect_triangle(drt_stream_t stream, int32_t ndim, const int64_t 
         return DRT_ERR_NULL_POINTER;
     const int threads = 256;
     const int64_t blocks = (n + threads - 1) / threads;
-    const unsigned grid = unsigned(blocks < 148 * 16 ? blocks : 148 * 16);
+    const unsigned grid = unsigned(blocks < int64_t(drt::device_sm_count()) * 16 ? blocks : int64_t(drt::device_sm_count()) * 16);
     mt_elementwise_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
         n, bt, o, d, tri, epsilon, t_out, hit_out);
     DRT_CHECK_CUDA(cudaGetLastError());

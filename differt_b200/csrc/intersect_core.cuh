@@ -339,16 +339,9 @@ template <int RPW, int MODE, class Src, class Sink>
 inline cudaError_t launch_intersect(cudaStream_t stream, const CoreParams &p, const Src &src,
                                     const Sink &sink, int64_t max_units) {
     auto kern = intersect_kernel<RPW, MODE, Src, Sink>;
-    static bool configured = false;  // benign race: idempotent attribute set
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(kSmemBytes));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static unsigned long long configured = 0;  // per-device bits (common.cuh)
+    if (cudaError_t e = ensure_dynamic_smem(kern, kSmemBytes, configured); e != cudaSuccess) return e;
+    const int sms = device_sm_count();
     constexpr int kWarpsK = WarpsFor<MODE>::value;
     const int64_t blocks = (max_units + kWarpsK - 1) / kWarpsK;
     if (blocks <= 0) return cudaSuccess;

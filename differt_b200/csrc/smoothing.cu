@@ -710,7 +710,7 @@ int drt_ray_intersect_triangle_smooth(drt_stream_t stream, int32_t ndim, const i
     if (n == 0) return DRT_OK;
     if (!o || !d || !tri || !t_out || !hit_out) return DRT_ERR_NULL_POINTER;
     const int64_t blocks = (n + 255) / 256;
-    mt_smooth_elementwise_kernel<<<unsigned(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0,
+    mt_smooth_elementwise_kernel<<<unsigned(blocks < int64_t(drt::device_sm_count()) * 16 ? blocks : int64_t(drt::device_sm_count()) * 16), 256, 0,
                                    static_cast<cudaStream_t>(stream)>>>(n, bt, o, d, tri, epsilon,
                                                                         smoothing_factor, t_out, hit_out);
     return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
@@ -742,7 +742,7 @@ int drt_consecutive_vertices_are_on_same_side_of_mirror_smooth(
     if (n == 0 || order == 0) return DRT_OK;
     if (!vertices || !mv || !mn || !out) return DRT_ERR_NULL_POINTER;
     const int64_t blocks = (n * order + 255) / 256;
-    same_side_smooth_kernel<<<unsigned(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0,
+    same_side_smooth_kernel<<<unsigned(blocks < int64_t(drt::device_sm_count()) * 16 ? blocks : int64_t(drt::device_sm_count()) * 16), 256, 0,
                               static_cast<cudaStream_t>(stream)>>>(n, order, bt, vertices, mv, mn,
                                                                    smoothing_factor, out);
     return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;

@@ -791,7 +791,7 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
     const int threads = 128;
     const int64_t cblocks = (a.C + threads - 1) / threads;
     if (a.ntx > 65535) return DRT_ERR_UNSUPPORTED;
-    int64_t chunks = (int64_t(148) * 32 + cblocks * a.ntx - 1) / (cblocks * a.ntx);
+    int64_t chunks = (int64_t(device_sm_count()) * 32 + cblocks * a.ntx - 1) / (cblocks * a.ntx);
     chunks = chunks < 1 ? 1 : (chunks > a.nrx ? a.nrx : chunks);
     if (chunks > 65535) chunks = 65535;
     const int64_t rx_per_chunk = (a.nrx + chunks - 1) / chunks;
@@ -855,9 +855,9 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
             // remaining records.  Sample lists ping-pong between list2 and list3 (free at this point).
             {
                 auto hk0 = path_head_kernel<NSEG>;
-                if (cudaFuncSetAttribute(hk0, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPathHeadSmem)) !=
-                    cudaSuccess)
-                    return DRT_ERR_CUDA;
+                static unsigned long long configured0 = 0;
+                if (ensure_dynamic_smem(hk0, kPathHeadSmem, configured0) != cudaSuccess) return DRT_ERR_CUDA;
+                const int sms0 = device_sm_count();
                 uint32_t *sl_in = list2, *sl_out = list3;
                 int64_t *cnt_in = list2_count, *cnt_out = list2_count + 1;
                 sample_list_kernel<<<unsigned((num_samples + 255) / 256), 256, 0, s>>>(num_samples, stride, sl_in);
@@ -868,7 +868,7 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
                     if (cudaMemsetAsync(cnt_out, 0, sizeof(int64_t), s) != cudaSuccess) return DRT_ERR_CUDA;
                     // samples that tile r does not block
                     const int64_t sb = (num_samples + kPathHeadWarps - 1) / kPathHeadWarps;
-                    hk0<<<unsigned(sb < 148 ? sb : 148), kPathHeadWarps * 32, kPathHeadSmem, s>>>(
+                    hk0<<<unsigned(sb < sms0 ? sb : sms0), kPathHeadWarps * 32, kPathHeadSmem, s>>>(
                         cur + size_t(r) * kTile, 1, num_samples, cnt_in, a.out_vertices, sl_in, a.eps, p.thr,
                         a.out_mask, sl_out, cnt_out, nullptr);
                     // recount the records after tile r on the surviving samples, re-sort them
@@ -896,20 +896,18 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
 #endif
             pack_active = cur;
             p.pack = pack_active;
+            // stats[3]: 1 + number of greedy rounds — proof for the tests that this branch ran
+            if (tests_done != nullptr)
+                set_i64_kernel<<<1, 1, 0, s>>>(tests_done + 3,
+                                               1 + (p.num_tiles - 1 < DRT_GREEDY_TILES ? p.num_tiles - 1
+                                                                                        : DRT_GREEDY_TILES));
         }
         // head pass: every candidate against the likeliest blockers, resident, barrier free
         const int NT = p.num_tiles;
         auto hk = path_head_kernel<NSEG>;
-        static bool configured = false;  // benign race: idempotent attribute set
-        if (!configured) {
-            if (cudaFuncSetAttribute(hk, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     int(kPathHeadSmem)) != cudaSuccess)
-                return DRT_ERR_CUDA;
-            configured = true;
-        }
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        static unsigned long long configured = 0;  // per-device bits (common.cuh)
+        if (ensure_dynamic_smem(hk, kPathHeadSmem, configured) != cudaSuccess) return DRT_ERR_CUDA;
+        const int sms = device_sm_count();
         // compact mode: the units are the compact slots 0 .. min(count, capacity) - 1
         const int64_t bound = compact ? a.capacity : a.P;
         if (compact) clamp_count_kernel<<<1, 1, 0, s>>>(a.list_count, a.capacity, units_scratch);
@@ -1158,7 +1156,7 @@ int drt_trace_path_candidates_vjp(drt_stream_t stream, int64_t V, int64_t T, con
     const int threads = 128;
     const int64_t cblocks = (C + threads - 1) / threads;
     if (ntx > 65535) return DRT_ERR_UNSUPPORTED;
-    int64_t chunks = (int64_t(148) * 16 + cblocks * ntx - 1) / (cblocks * ntx);
+    int64_t chunks = (int64_t(device_sm_count()) * 16 + cblocks * ntx - 1) / (cblocks * ntx);
     chunks = chunks < 1 ? 1 : (chunks > nrx ? nrx : chunks);
     if (chunks > 65535) chunks = 65535;
     const int64_t rx_per_chunk = (nrx + chunks - 1) / chunks;

@@ -87,7 +87,7 @@ extern "C" int drt_first_triangle_hit_by_ray_vjp(drt_stream_t stream, int64_t R,
     if (!vertices || !triangles || !o || !d || !faces || !g_t) return DRT_ERR_NULL_POINTER;
     const int threads = 256;
     const int64_t blocks = (R + threads - 1) / threads;
-    const unsigned grid = unsigned(blocks < 148 * 16 ? blocks : 148 * 16);
+    const unsigned grid = unsigned(blocks < int64_t(drt::device_sm_count()) * 16 ? blocks : int64_t(drt::device_sm_count()) * 16);
     drt::first_hit_vjp_kernel<<<grid, threads, 0, s>>>(R, V, T, vertices, triangles, o, d, faces, g_t,
                                                        g_vertices, g_o, g_d);
     return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;

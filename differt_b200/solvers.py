@@ -198,7 +198,8 @@ def trace_path_candidates(
         _stats_accumulate.add_(stats)
     if with_stats:
         s = stats.cpu().tolist()
-        paths.stats = {"tests_done": s[0], "candidates_blockage_tested": s[1], "head_pass_survivors": s[2]}
+        paths.stats = {"tests_done": s[0], "candidates_blockage_tested": s[1], "head_pass_survivors": s[2],
+                       "ordering_pass": s[3]}
     return paths
 
 

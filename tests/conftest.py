@@ -37,6 +37,11 @@ def bruxelles() -> tuple[np.ndarray, np.ndarray]:
     return data["vertices"], data["triangles"]
 
 
+@pytest.fixture(scope="session")
+def golden_dir() -> Path:
+    return GOLDEN
+
+
 @pytest.fixture()
 def rng() -> np.random.Generator:
     return np.random.default_rng(1234)

@@ -675,6 +675,68 @@ def test_trace_dense_equals_pruned_at_scale(drt):
 
 
 # ------------------------------------------------------------------------------------------------
+# the benchmarked code path: dense batches of >= 262 144 paths take the batch-specific ordering pass
+# (hit counts on a sample, greedy set-cover rounds with partial re-sorts) and the culled cascade —
+# code that smaller batches never reach.  Compared against the C oracle like everything else.
+# ------------------------------------------------------------------------------------------------
+
+
+def _bench_like_case(grid, order, n_rx, n_cand, seed=1234):
+    v, t = scenes.urban_grid(*grid)
+    lo, hi = v.min(0), v.max(0)
+    tx = np.array([[0.5 * (lo[0] + hi[0]) + 15.0, 0.5 * (lo[1] + hi[1]) + 15.0, 1.2 * hi[2]]], np.float32)
+    rx = scenes.receivers_grid(v, *n_rx)
+    cand = scenes.sampled_candidates(t.shape[0], order, n_cand, seed=seed)
+    return v, t, tx, rx, cand
+
+
+def test_trace_bench_scale_ordering_pass_bit_exact_vs_oracle(drt, golden_dir):
+    """BASELINE config 3 geometry (10 094 triangles, order 3) at P = 512 x 1024 = 524 288 paths, incl.
+    the candidates known to be valid: the FULL mask, vertices and objects against the C oracle."""
+    v, t, tx, rx, cand = _bench_like_case((29, 29), 3, (32, 16), 1024)
+    known = np.load(golden_dir / "urban10k_valid_candidates.npz")["order3"]
+    cand[: known.shape[0]] = known
+    mesh = drt.Mesh.from_numpy(v, t)
+    got = drt.trace_path_candidates(mesh, tx, rx, cand, dense_blockage=True, with_stats=True)
+    assert got.stats["ordering_pass"] >= 2, "the batch must be large enough to take the ordering pass"
+    ev, eo, em = co.trace_path_candidates(v, t, tx, rx, cand, early_exit=True)
+    np.testing.assert_array_equal(got.mask.cpu().numpy(), em)
+    np.testing.assert_array_equal(bits(got.vertices.cpu().numpy()), bits(ev))
+    np.testing.assert_array_equal(got.objects.cpu().numpy(), eo)
+    # the default (pruned) mode of the API must agree as well
+    pruned = drt.trace_path_candidates(mesh, tx, rx, cand)
+    assert torch.equal(pruned.mask, got.mask) and torch.equal(pruned.vertices, got.vertices)
+
+
+@pytest.mark.parametrize("grid,order,n_rx,n_cand,quads,use_mask", [
+    ((29, 29), 3, (32, 16), 768, True, False),    # assume_quads
+    ((29, 29), 2, (32, 16), 640, False, True),    # masked mesh, order 2
+    ((64, 65), 4, (32, 16), 512, False, False),   # BASELINE config 5 geometry: 49 922 triangles, order 4
+    ((29, 29), 1, (64, 64), 64, False, False),    # order 1: P = 262 144 exactly at the threshold
+])
+def test_trace_ordering_pass_variants_vs_oracle(drt, rng, grid, order, n_rx, n_cand, quads, use_mask):
+    """Other shapes of the same branch; the oracle checks a strided block of receivers (the GPU traced
+    all of them in one dense batch)."""
+    v, t, tx, rx, cand = _bench_like_case(grid, order, n_rx, n_cand, seed=7)
+    if quads:
+        cand = (cand // 2 * 2).astype(np.int32)
+        for j in range(1, order):  # re-draw consecutive repeats created by the rounding
+            same = cand[:, j] == cand[:, j - 1]
+            cand[same, j] = (cand[same, j] + 2) % (t.shape[0] // 2 * 2)
+    mask = (rng.uniform(size=t.shape[0]) <= 0.7) if use_mask else None
+    mesh = drt.Mesh.from_numpy(v, t, mask=mask, assume_quads=quads)
+    got = drt.trace_path_candidates(mesh, tx, rx, cand, dense_blockage=True, with_stats=True)
+    assert got.stats["ordering_pass"] >= 1
+    sel = np.arange(0, rx.shape[0], 32 if grid == (64, 65) else 8)
+    ev, eo, em = co.trace_path_candidates(v, t, tx, rx[sel], cand, mask=mask, assume_quads=quads,
+                                          early_exit=True)
+    np.testing.assert_array_equal(got.mask[:, sel].cpu().numpy(), em)
+    np.testing.assert_array_equal(bits(got.vertices[:, sel].cpu().numpy()), bits(ev))
+    pruned = drt.trace_path_candidates(mesh, tx, rx, cand)
+    assert torch.equal(pruned.mask, got.mask)
+
+
+# ------------------------------------------------------------------------------------------------
 # sharded trace + gather (world size 1 here; the world-size-2 merge logic is covered on CPU with gloo)
 # ------------------------------------------------------------------------------------------------
 
