@@ -9,6 +9,7 @@
 //   TracedPaths fields and a work list of the candidates that still need the blockage test.
 // Stage B (all-pairs engine, one warp per candidate, its k+1 segments register-blocked): any-hit of
 //   every segment against the whole mesh; a hit on any segment retires the candidate.
+#include "cull.cuh"
 #include "image_core.cuh"
 #include "intersect_core.cuh"
 
@@ -211,6 +212,13 @@ int drt_sort_records_by_keys(drt_stream_t stream, int64_t n, const void *pack_in
 #ifndef DRT_PATH_HEAD_CTAS
 #define DRT_PATH_HEAD_CTAS 1
 #endif
+#ifndef DRT_CULL_HEAD_TILES
+#define DRT_CULL_HEAD_TILES 4
+#endif
+#ifndef DRT_CULL_CTAS
+#define DRT_CULL_CTAS 4
+#endif
+constexpr int kCullHead = DRT_CULL_HEAD_TILES;  // head tiles in front of the culled pass (<= kPathHead)
 constexpr int kPathHead = DRT_PATH_HEAD_TILES;
 constexpr int kPathHeadWarps = DRT_PATH_HEAD_WARPS;
 constexpr size_t kPathHeadSmem = size_t(kPathHead) * kTile * sizeof(Tri48) + 16;
@@ -323,6 +331,130 @@ path_head_kernel(const Tri48 *__restrict__ pack, const int num_head_tiles, const
     }
     if (tests_done != nullptr && lane == 0 && tests)
         atomicAdd(reinterpret_cast<unsigned long long *>(tests_done), (unsigned long long)tests);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Blockage, culled pass (cull.cuh): the candidates the resident passes over the head tiles left
+// undecided — mostly UNBLOCKED ones, which would otherwise have to be tested against every triangle —
+// against the whole mesh in spatial order.  One warp per candidate.  Level 1: the lanes test 32 tile
+// nodes (256 triangles each) at a time against the candidate's segments; level 2: for every tile that
+// some segment may touch, the 32 lanes test its 32 groups (8 triangles each); level 3: the surviving
+// groups are evaluated four at a time with the exact Möller–Trumbore test (lane = triangle, only the
+// segments that survived for that group).  A (segment, triangle) pair is skipped only when node_culled
+// PROVES the reference's fp32 test reports no hit, so the mask is bit-identical to the dense evaluation.
+// Nodes and triangles are read through L1/L2 (the working set of a candidate is a few KB).
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kCullWarps = 8;
+
+template <int NSEG>
+__global__ void __launch_bounds__(kCullWarps * 32)
+path_cull_kernel(const Tri48 *__restrict__ pack, const CullNode *__restrict__ tiles, const int num_tile_nodes,
+                 const CullNode *__restrict__ groups, const int64_t num_units_host,
+                 const int64_t *__restrict__ num_units_dev, const float *__restrict__ vertices,
+                 const uint32_t *__restrict__ list, const float eps, const float thr,
+                 uint8_t *__restrict__ mask, int64_t *tests_done) {
+    __shared__ uint8_t sel_all[kCullWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *sel = sel_all[warp];
+    const int64_t num_units = num_units_dev ? *num_units_dev : num_units_host;
+    const int64_t total_warps = int64_t(gridDim.x) * kCullWarps;
+    constexpr int NV = NSEG + 1;
+    static_assert(3 * NV <= 32, "one float per lane prefetch");
+    auto path_of = [&](int64_t u) -> int64_t { return list != nullptr ? int64_t(list[u]) : u; };
+    auto fetch = [&](int64_t path) -> float { return lane < 3 * NV ? vertices[path * (3 * NV) + lane] : 0.0f; };
+
+    int64_t unit = int64_t(blockIdx.x) * kCullWarps + warp;
+    int64_t path_cur = unit < num_units ? path_of(unit) : 0;
+    float pf = unit < num_units ? fetch(path_cur) : 0.0f;
+    int64_t path_next = unit + total_warps < num_units ? path_of(unit + total_warps) : 0;
+    int64_t tests = 0;
+    for (; unit < num_units; unit += total_warps) {
+        float3 o[NSEG], d[NSEG];
+        SegCull sc[NSEG];
+        uint32_t alive = 0;
+        {
+            float3 prev = make_float3(__shfl_sync(kFull, pf, 0), __shfl_sync(kFull, pf, 1), __shfl_sync(kFull, pf, 2));
+#pragma unroll
+            for (int sgm = 0; sgm < NSEG; ++sgm) {
+                const float3 next = make_float3(__shfl_sync(kFull, pf, 3 * sgm + 3), __shfl_sync(kFull, pf, 3 * sgm + 4),
+                                                __shfl_sync(kFull, pf, 3 * sgm + 5));
+                o[sgm] = prev;
+                d[sgm] = sub3(next, prev);  // jnp.diff (_solvers.py:593)
+                // d = 0 → a = 0 → no hit; a non-finite origin or direction → NaN/inf comparisons → no hit
+                const bool dead = (d[sgm].x == 0.0f && d[sgm].y == 0.0f && d[sgm].z == 0.0f) || !finite3(prev) ||
+                                  !finite3(d[sgm]);
+                if (!dead) alive |= 1u << sgm;
+                sc[sgm] = make_seg_cull(o[sgm], d[sgm]);
+                prev = next;
+            }
+        }
+        const int64_t path = path_cur;
+        path_cur = path_next;
+        if (unit + total_warps < num_units) pf = fetch(path_cur);
+        path_next = unit + 2 * total_warps < num_units ? path_of(unit + 2 * total_warps) : 0;
+        if (alive == 0) continue;
+
+        bool blocked = false;
+        for (int tb = 0; tb < num_tile_nodes && !blocked; tb += 32) {
+            uint32_t tmask = 0;
+            if (tb + lane < num_tile_nodes) {
+                const CullNode node = tiles[tb + lane];
+#pragma unroll
+                for (int sgm = 0; sgm < NSEG; ++sgm)
+                    if ((alive >> sgm) & 1u) tmask |= node_culled(sc[sgm], node) ? 0u : (1u << sgm);
+            }
+            uint32_t tballot = __ballot_sync(kFull, tmask != 0);
+            while (tballot != 0 && !blocked) {
+                const int tl = __ffs(tballot) - 1;
+                tballot &= tballot - 1;
+                const uint32_t tm = __shfl_sync(kFull, tmask, tl);
+                const int64_t g0 = int64_t(tb + tl) * kCullFan;  // first group of the tile
+                uint32_t gmask = 0;
+                {
+                    const CullNode node = groups[g0 + lane];
+#pragma unroll
+                    for (int sgm = 0; sgm < NSEG; ++sgm)
+                        if ((tm >> sgm) & 1u) gmask |= node_culled(sc[sgm], node) ? 0u : (1u << sgm);
+                }
+                const uint32_t gballot = __ballot_sync(kFull, gmask != 0);
+                const int ng = __popc(gballot);
+                if (gmask != 0) sel[__popc(gballot & ((1u << lane) - 1u))] = uint8_t(lane);
+                __syncwarp();
+                for (int b = 0; b < ng && !blocked; b += 32 / kCullGroup) {
+                    const int which = b + lane / kCullGroup;
+                    const int gl = which < ng ? int(sel[which]) : 0;
+                    uint32_t gm = __shfl_sync(kFull, gmask, gl);
+                    if (which >= ng) gm = 0;
+                    const Tri48 *rec = pack + (g0 + gl) * kCullGroup + (lane % kCullGroup);
+                    const float4 ta = rec->a, tb4 = rec->b, tc = rec->c;
+                    const Tri tr = unpack(ta, tb4, tc);
+                    bool hit = false, weird = false;
+#pragma unroll
+                    for (int sgm = 0; sgm < NSEG; ++sgm)
+                        if ((gm >> sgm) & 1u) hit = mt_any_fast(o[sgm], d[sgm], tr, eps, thr, weird) || hit;
+                    if (__any_sync(kFull, weird)) {  // |a| outside the fast reciprocal's range: exact redo
+                        hit = false;
+#pragma unroll
+                        for (int sgm = 0; sgm < NSEG; ++sgm)
+                            if ((gm >> sgm) & 1u) {
+                                float t;
+                                hit = (mt_exact(o[sgm], d[sgm], tr, eps, t) && t < thr) || hit;
+                            }
+                    }
+                    tests += __popc(gm);
+                    blocked = __any_sync(kFull, hit);
+                }
+                __syncwarp();
+            }
+        }
+        if (blocked && lane == 0) mask[path] = 0;
+    }
+    if (tests_done != nullptr) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) tests += __shfl_xor_sync(kFull, tests, off);
+        if (lane == 0 && tests) atomicAdd(reinterpret_cast<unsigned long long *>(tests_done), (unsigned long long)tests);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -731,7 +863,9 @@ __global__ void complete_graph_candidates_kernel(int64_t n, int order, int64_t s
 }
 
 struct TraceWorkspace {
-    size_t pack_geom, pack_active, pack_sorted, pack_sorted2, hit_counts, sort_ws, sort_bytes, list, list2, list3, counters, total;
+    size_t pack_geom, pack_active, pack_sorted, pack_sorted2, hit_counts, sort_ws, sort_bytes, list, list2, list3, counters,
+        cull, total;
+    CullLayout cull_layout;
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -761,6 +895,9 @@ inline TraceWorkspace trace_workspace_layout(int64_t T, int64_t P) {
     off += align256(size_t(P > 0 ? P : 1) * sizeof(uint32_t));
     w.list3 = off;
     off += align256(size_t(P > 0 ? P : 1) * sizeof(uint32_t));
+    w.cull = off;  // spatially ordered pack + its node levels (cull.cuh)
+    w.cull_layout = cull_layout(int64_t(pack / sizeof(Tri48)));
+    off += align256(w.cull_layout.total);
     w.total = off;
     return w;
 }
@@ -786,7 +923,8 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
                  const Tri48 *pack_active, float hit_tol, int64_t *tests_done,
                  int64_t *units_scratch, uint32_t *list2, uint32_t *list3, int64_t *list2_count,
                  uint32_t *hit_counts,
-                 Tri48 *pack_sorted2, void *sort_ws, size_t sort_bytes) {
+                 Tri48 *pack_sorted2, void *sort_ws, size_t sort_bytes, const unsigned char *cull_ws,
+                 const CullLayout &cull) {
     // candidates along x, receiver chunks along y (enough of them to fill the GPU), transmitters along z
     const int threads = 128;
     const int64_t cblocks = (a.C + threads - 1) / threads;
@@ -920,8 +1058,27 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
         uint32_t *out_list = list2;
         int64_t *out_count = list2_count;  // counters[2]; counters[3] is list3's
         e = cudaSuccess;
-        for (int t0 = 0; t0 < NT && e == cudaSuccess; t0 += kPathHead) {
-            const int nh = NT - t0 < kPathHead ? NT - t0 : kPathHead;
+        // With more tiles than the head holds, ONE resident pass over the first kCullHead tiles of the
+        // ordered pack (the likeliest blockers) decides most blocked candidates, and the rest — mostly
+        // unblocked ones — goes to the culled pass over the whole mesh in spatial order (cull.cuh).  The
+        // cull's proof needs FLT_MIN <= eps and 0 < thr <= 1; other parameters keep the plain cascade.
+        const bool use_cull = cull_ws != nullptr && NT > kCullHead && p.eps >= 1.17549435e-38f && p.thr > 0.0f &&
+                              p.thr <= 1.0f;
+        const int head_step = use_cull ? kCullHead : kPathHead;
+        for (int t0 = 0; t0 < NT && e == cudaSuccess; t0 += head_step) {
+            if (use_cull && t0 > 0) {
+                auto ck = path_cull_kernel<NSEG>;
+                const int64_t cblocks2 = (bound + kCullWarps - 1) / kCullWarps;
+                const int64_t cres = int64_t(sms) * DRT_CULL_CTAS;
+                ck<<<unsigned(cblocks2 < cres ? cblocks2 : cres), kCullWarps * 32, 0, s>>>(
+                    reinterpret_cast<const Tri48 *>(cull_ws + cull.pack),
+                    reinterpret_cast<const CullNode *>(cull_ws + cull.tiles), int(cull.num_tiles),
+                    reinterpret_cast<const CullNode *>(cull_ws + cull.groups), bound, in_count, a.out_vertices, in_list,
+                    a.eps, p.thr, a.out_mask, tests_done);
+                e = cudaGetLastError();
+                break;
+            }
+            const int nh = NT - t0 < head_step ? NT - t0 : head_step;
             hk<<<unsigned(hblocks < hres ? hblocks : hres), kPathHeadWarps * 32, kPathHeadSmem, s>>>(
                 pack_active + size_t(t0) * kTile, nh, bound, in_count, a.out_vertices, in_list, a.eps, p.thr,
                 a.out_mask, out_list, out_count, tests_done);
@@ -933,7 +1090,7 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
             const bool to3 = out_list == list2;
             out_list = to3 ? list3 : list2;
             out_count = to3 ? list2_count + 1 : list2_count;
-            if (e == cudaSuccess && t0 + kPathHead < NT) e = cudaMemsetAsync(out_count, 0, sizeof(int64_t), s);
+            if (e == cudaSuccess && t0 + head_step < NT) e = cudaMemsetAsync(out_count, 0, sizeof(int64_t), s);
         }
     } else {
         if (compact) return DRT_ERR_UNSUPPORTED;  // compact mode is built for orders <= 5
@@ -1000,6 +1157,13 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
         if (rc != DRT_OK) return rc;
         pack_active = pack_sorted;
     }
+    const unsigned char *cull_ws = nullptr;
+    if (order + 1 <= 6 && int64_t(drt_mesh_pack_bytes(T) / sizeof(Tri48)) > int64_t(kCullHead) * kTile) {
+        rc = cull_build(s, int64_t(drt_mesh_pack_bytes(T) / sizeof(Tri48)), pack_active, ws + w.cull, w.cull_layout,
+                        ws + w.sort_ws, w.sort_bytes);
+        if (rc != DRT_OK) return rc;
+        cull_ws = ws + w.cull;
+    }
     int64_t *counters = reinterpret_cast<int64_t *>(ws + w.counters);
     if (cudaMemsetAsync(counters, 0, 256, s) != cudaSuccess) return DRT_ERR_CUDA;
     const bool dense = (flags & DRT_TRACE_DENSE_BLOCKAGE) != 0;
@@ -1034,7 +1198,7 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
                              units_scratch, list2, list3, counters + 2,                           \
                              reinterpret_cast<uint32_t *>(ws + w.hit_counts),                      \
                              reinterpret_cast<Tri48 *>(ws + w.pack_sorted2), ws + w.sort_ws,      \
-                             w.sort_bytes);                                                       \
+                             w.sort_bytes, cull_ws, w.cull_layout);                               \
         break;
     switch (order) {
         DRT_TRACE_CASE(0) DRT_TRACE_CASE(1) DRT_TRACE_CASE(2) DRT_TRACE_CASE(3) DRT_TRACE_CASE(4)
@@ -1094,6 +1258,13 @@ int drt_trace_valid_path_candidates(drt_stream_t stream, int64_t V, int64_t T, c
         if (rc != DRT_OK) return rc;
         pack_active = pack_sorted;
     }
+    const unsigned char *cull_ws = nullptr;
+    if (int64_t(drt_mesh_pack_bytes(T) / sizeof(Tri48)) > int64_t(kCullHead) * kTile) {
+        rc = cull_build(s, int64_t(drt_mesh_pack_bytes(T) / sizeof(Tri48)), pack_active, ws + w.cull, w.cull_layout,
+                        ws + w.sort_ws, w.sort_bytes);
+        if (rc != DRT_OK) return rc;
+        cull_ws = ws + w.cull;
+    }
     int64_t *counters = reinterpret_cast<int64_t *>(ws + w.counters);
     if (cudaMemsetAsync(counters, 0, 256, s) != cudaSuccess) return DRT_ERR_CUDA;
     TraceArgs a{};
@@ -1124,7 +1295,7 @@ int drt_trace_valid_path_candidates(drt_stream_t stream, int64_t V, int64_t T, c
                              reinterpret_cast<uint32_t *>(ws + w.list3), counters + 2,                   \
                              reinterpret_cast<uint32_t *>(ws + w.hit_counts),                            \
                              reinterpret_cast<Tri48 *>(ws + w.pack_sorted2), ws + w.sort_ws,            \
-                             w.sort_bytes);                                                             \
+                             w.sort_bytes, cull_ws, w.cull_layout);                                     \
         break;
     switch (order) {
         DRT_TRACE_CASE(0) DRT_TRACE_CASE(1) DRT_TRACE_CASE(2) DRT_TRACE_CASE(3) DRT_TRACE_CASE(4)

@@ -1092,6 +1092,133 @@ def test_exact_zero_and_tie_cases_on_a_lattice_scene(drt, rng):
             np.testing.assert_array_equal(bits(got.vertices.cpu().numpy()), bits(ev))
 
 
+# ------------------------------------------------------------------------------------------------
+# the culled blockage pass (csrc/cull.cuh) on inputs built to defeat a bounding-volume cull: meshes
+# with more than 2048 triangles take it for every candidate the head tiles leave undecided
+# ------------------------------------------------------------------------------------------------
+
+
+def _plane_basis(rng):
+    n = rng.normal(size=3)
+    n /= np.linalg.norm(n)
+    a = np.cross(n, [1.0, 0.0, 0.0])
+    a /= np.linalg.norm(a)
+    return a, np.cross(n, a), n
+
+
+def _coplanar_clusters(rng, n_planes=4, clusters_per_plane=3, tri_per_cluster=500):
+    """Clusters of small triangles lying in a few tilted planes → (vertices, triangles, planes) with
+    planes = [(origin, a, b, normal, [cluster centres in plane coordinates])]."""
+    tris, planes = [], []
+    for _ in range(n_planes):
+        a, b, n = _plane_basis(rng)
+        c0 = rng.uniform(-300, 300, 3)
+        centres = rng.uniform(-400, 400, (clusters_per_plane, 2))
+        for c in centres:
+            uv = c + rng.uniform(-5, 5, (tri_per_cluster, 3, 2))
+            tris.append(c0 + uv[..., 0:1] * a + uv[..., 1:2] * b)
+        planes.append((c0, a, b, n, centres))
+    tv = np.concatenate(tris).astype(np.float32)
+    t = np.arange(3 * tv.shape[0], dtype=np.int32).reshape(-1, 3)
+    return tv.reshape(-1, 3), t, planes
+
+
+@pytest.mark.parametrize("lift", [0.0, 1e-3, 0.3])
+def test_cull_reproduces_noise_hits_of_segments_in_the_plane_of_far_triangles(drt, lift):
+    """Segments lying in (lift = 0) or at a tiny angle to (lift > 0, metres of out-of-plane offset over
+    hundreds of metres) the plane of triangles that are hundreds of metres AWAY: the determinant is
+    rounding noise and the reference's fp32 test reports hits there.  Order-0 paths (one segment
+    tx → rx each), 64 x 4096 = 262 144 of them, against 6000 triangles."""
+    rng = np.random.default_rng(5)
+    v, t, planes = _coplanar_clusters(rng)
+    tx, rx = [], []
+    for c0, a, b, n, _ in planes:
+        for pts, count in ((tx, 16), (rx, 1024)):
+            uv = rng.uniform(-2500, 2500, (count, 2))
+            off = rng.uniform(-lift, lift, (count, 1))
+            pts.append(c0 + uv[:, 0:1] * a + uv[:, 1:2] * b + off * n)
+    tx, rx = np.concatenate(tx).astype(np.float32), np.concatenate(rx).astype(np.float32)
+    cand = np.zeros((1, 0), np.int32)
+    mesh = drt.Mesh.from_numpy(v, t)
+    ev, eo, em, st = co.trace_path_candidates(v, t, tx, rx, cand, early_exit=True, stages=True)
+    blocked = st["blocked"][..., 0]
+    # how far from every cluster centre of ITS plane does each same-plane segment pass?
+    far_hits = 0
+    for k, (c0, a, b, n, centres) in enumerate(planes):
+        p_tx = np.stack(((tx[16 * k:16 * k + 16] - c0) @ a, (tx[16 * k:16 * k + 16] - c0) @ b), -1)
+        p_rx = np.stack(((rx[1024 * k:1024 * k + 1024] - c0) @ a, (rx[1024 * k:1024 * k + 1024] - c0) @ b), -1)
+        o2 = p_tx[:, None, :]
+        d2 = p_rx[None, :, :] - o2
+        dist = np.full(d2.shape[:2], np.inf)
+        for c in centres:
+            tt = np.clip(((c - o2) * d2).sum(-1) / np.maximum((d2 * d2).sum(-1), 1e-9), 0.0, 1.0)
+            dist = np.minimum(dist, np.linalg.norm(o2 + tt[..., None] * d2 - c, axis=-1))
+        far_hits += int((blocked[16 * k:16 * k + 16, 1024 * k:1024 * k + 1024] & (dist > 50.0)).sum())
+    if lift == 0.0:
+        assert far_hits > 20, "the case must contain hits far away from the triangles that cause them"
+    for dense in (True, False):
+        got = drt.trace_path_candidates(mesh, tx, rx, cand, dense_blockage=dense, with_stats=True)
+        np.testing.assert_array_equal(got.mask.cpu().numpy(), em)
+    # the cull did its job on everything it could prove: far fewer tests than the dense count
+    assert got.stats["tests_done"] < 0.5 * tx.shape[0] * rx.shape[0] * t.shape[0]
+
+
+def test_cull_with_degenerate_triangles_extreme_magnitudes_and_masks(drt, rng):
+    """3000 triangles: slivers, zero-area and duplicated ones, a few astronomically large or far ones,
+    tiny ones, a masked third — everything that makes a node un-cullable or its margin huge."""
+    n_tri = 3000
+    kind = rng.uniform(size=(n_tri, 1, 1))
+    scale = np.where(kind < 0.9, 10.0 ** rng.uniform(-2, 1.5, size=(n_tri, 1, 1)),
+                     np.where(kind < 0.95, 10.0 ** rng.uniform(-9, -5, size=(n_tri, 1, 1)),
+                              10.0 ** rng.uniform(8, 13, size=(n_tri, 1, 1))))
+    centre = rng.normal(size=(n_tri, 1, 3)) * np.where(scale < 1e3, 300.0, 1e14)
+    tv = (centre + rng.normal(size=(n_tri, 3, 3)) * scale).astype(np.float32)
+    tv[:40, 1] = tv[:40, 0]                                              # zero area
+    tv[40:80, 2] = tv[40:80, 0] + (tv[40:80, 1] - tv[40:80, 0]) * 0.5    # collinear
+    tv[80:160, 2] = tv[80:160, 1] + np.float32(1e-6)                     # slivers
+    tv[160:200] = tv[200:240]                                            # duplicates
+    v = tv.reshape(-1, 3)
+    t = np.arange(3 * n_tri, dtype=np.int32).reshape(n_tri, 3)
+    tx = (rng.normal(size=(4, 3)) * 300).astype(np.float32)
+    rx = (rng.normal(size=(64, 3)) * 300).astype(np.float32)
+    rx[:8] = v[rng.integers(0, v.shape[0], 8)]                           # receivers ON mesh vertices
+    for order, n_cand in ((0, 1), (1, 1000), (2, 500)):
+        cand = scenes.sampled_candidates(n_tri, order, n_cand) if order else np.zeros((1, 0), np.int32)
+        for mask in (None, rng.uniform(size=n_tri) < 0.66):
+            mesh = drt.Mesh.from_numpy(v, t, mask=mask)
+            with np.errstate(all="ignore"):
+                ev, eo, em, st = co.trace_path_candidates(v, t, tx, rx, cand, mask=mask, early_exit=True, stages=True)
+            for dense in (True, False):
+                got = drt.trace_path_candidates(mesh, tx, rx, cand, dense_blockage=dense)
+                np.testing.assert_array_equal(got.mask.cpu().numpy(), em)
+                np.testing.assert_array_equal(bits(got.vertices.cpu().numpy()), bits(ev))
+            comp = drt.trace_valid_path_candidates(mesh, tx, rx, cand)
+            np.testing.assert_array_equal(comp.index.cpu().numpy(), np.flatnonzero(em.reshape(-1)))
+        if order == 0:
+            assert st["blocked"].any() and (~st["blocked"]).any()
+
+
+@pytest.mark.parametrize("hit_tol,epsilon", [(None, None), (0.0, None), (0.25, 1e-4), (-0.5, None), (None, 0.0)])
+def test_cull_parameter_ranges(drt, rng, hit_tol, epsilon):
+    """hit_tol / epsilon inside and outside the range the cull's proof covers (outside, the plain cascade
+    must run): 10 094 triangles, order-1 candidates through the street level."""
+    v, t = scenes.urban_grid(29, 29)
+    tx = np.array([[435.0, 435.0, 30.0]], np.float32)
+    rx = scenes.receivers_grid(v, 12, 12)
+    cand = scenes.sampled_candidates(t.shape[0], 1, 600)
+    kw = {}
+    if hit_tol is not None:
+        kw["hit_tol"] = hit_tol
+    if epsilon is not None:
+        kw["epsilon"] = epsilon
+    mesh = drt.Mesh.from_numpy(v, t)
+    ev, eo, em, st = co.trace_path_candidates(v, t, tx, rx, cand, early_exit=True, stages=True, **kw)
+    for dense in (True, False):
+        got = drt.trace_path_candidates(mesh, tx, rx, cand, dense_blockage=dense, **kw)
+        np.testing.assert_array_equal(got.mask.cpu().numpy(), em)
+    assert st["blocked"].any() and (~st["blocked"]).any()
+
+
 @pytest.mark.parametrize("solver", ["exhaustive", "hybrid"])
 def test_chunked_trace_equals_one_shot_masked(drt, two_buildings, kats, solver):
     """Scene.trace_paths(chunk_size=...) semantics (_scene.py:738-751) and the merged valid paths:
