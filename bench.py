@@ -6,16 +6,17 @@
 
 A *step* is one pass of the hot path over one batch of synthetic input: trace-and-validate
 (`_trace_path_candidates`, reference differt/src/differt/geometry/_solvers.py:499-770) of every
-(tx, rx, candidate) of the workload, with the blockage test evaluated for every candidate like the
+(tx, rx, candidate) of the workload, with the blockage test decided for every candidate like the
 reference does ("dense"), the reverse mode of `vertices.sum()` w.r.t. tx, rx and the mesh vertices
 (BASELINE config 3 is "with VJP"), followed by the compaction of the valid paths (`TracedPaths.masked()`)
-and — for N > 1, where every rank traces its own shard of the candidates — ONE all-gather of the
-survivors.  The metric is BASELINE.json's: ray–triangle tests per second, counted as SURVEY.md
-§8(d) defines it — every (ray, triangle) pair the step DECIDES, rays x triangles ("algorithmic",
-what the reference's dense evaluation executes) — so that `value` is whole-job throughput in the
-same unit for both arms.  The Möller–Trumbore evaluations the kernel actually executed (device
-counter; fewer, because an any-hit query stops at the first blocking tile) are reported next to it
-as `executed_tests_per_s`, and the roofline is computed from the EXECUTED count only.
+and — for N > 1, where the FIXED workload's candidates are sharded over the ranks (strong scaling) —
+ONE all-gather of the survivors.  The metric is BASELINE.json's: ray–triangle tests per second,
+counted as SURVEY.md §8(d) defines it — every (ray, triangle) pair the step DECIDES, rays x
+triangles ("algorithmic", what the reference's dense evaluation executes) — in BOTH arms: the GPU
+arm and the CPU arm (`--impl reference`, `cpu_baseline`) both stop a candidate at its first blocker,
+both report decided pairs per second, so their ratio is a ratio of times for the same job.  The
+Möller–Trumbore evaluations actually executed are reported next to it in both arms
+(`executed_tests_per_s`), and the roofline is computed from measured instruction counts only.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions of `value`, `e2e`,
 `roofline` and `cpu_baseline`.
@@ -49,9 +50,9 @@ WORKLOADS = {
     "urban10k_1tx_4096rx_order3": dict(scene=("urban", 29, 29), rx=(64, 64), order=3, cand=4096),
     # BASELINE.json configs[1], one chunk of the exhaustive candidate list
     "canyon1k_1tx_256rx_order2": dict(scene=("canyon", 41), rx=(16, 16), order=2, cand=65536),
-    # BASELINE.json configs[3] per GPU: 16 TX x 4096 RX, order 3, the 4096 candidates sharded over 8 GPUs
-    "urban10k_16tx_4096rx_order3": dict(scene=("urban", 29, 29), rx=(64, 64), order=3, cand=512, ntx=16),
-    # BASELINE.json configs[4] per GPU: 50k-triangle mesh, 1 TX x 16 384 RX, order 4, 2048 candidates
+    # BASELINE.json configs[3]: 16 TX x 4096 RX, order 3, 4096 candidates sharded over the GPUs
+    "urban10k_16tx_4096rx_order3": dict(scene=("urban", 29, 29), rx=(64, 64), order=3, cand=4096, ntx=16),
+    # BASELINE.json configs[4]: 50k-triangle mesh, 1 TX x 16 384 RX, order 4, 2048 candidates (sweep: --cand)
     "urban50k_1tx_16384rx_order4": dict(scene=("urban", 64, 65), rx=(128, 128), order=4, cand=2048),
     # small variant for quick checks (not a bench line)
     "urban10k_small": dict(scene=("urban", 29, 29), rx=(16, 16), order=3, cand=1024),
@@ -59,10 +60,34 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "urban10k_1tx_4096rx_order3"
 
 
-def build_workload(name: str, rank: int, world: int):
-    """Seeded synthetic inputs (host, NumPy).  Every rank gets its own `cand` candidates (weak
-    scaling): candidates rank*cand .. (rank+1)*cand of a global list of world*cand."""
-    from differt_b200 import scenes
+_SCENES = None
+
+
+def load_scenes():
+    """`differt_b200/scenes.py` (NumPy only) loaded BY PATH: building a workload must not import the
+    product package — importing it dlopens libdiffert_b200.so, which the reference arm never touches."""
+    global _SCENES
+    if _SCENES is None:
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("_bench_scenes", ROOT / "differt_b200" / "scenes.py")
+        _SCENES = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_SCENES)
+    return _SCENES
+
+
+def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
+    """Same contiguous split as differt_b200.distributed.shard_bounds (restated: see load_scenes)."""
+    base, extra = divmod(int(n), world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def build_workload(name: str, rank: int, world: int, *, weak: bool = False):
+    """Seeded synthetic inputs (host, NumPy).  The workload is FIXED (strong scaling): its `cand`
+    candidates are split into `world` contiguous shards and rank r traces shard r.  `weak=True` gives
+    every rank `cand` candidates of its own instead (the extra weak-scaling leg)."""
+    scenes = load_scenes()
 
     w = WORKLOADS[name]
     if w["scene"][0] == "urban":
@@ -78,19 +103,22 @@ def build_workload(name: str, rank: int, world: int):
         xx, yy = np.meshgrid(gx, gy, indexing="ij")
         tx = np.stack((xx, yy, np.full_like(xx, 1.2 * hi[2])), -1).reshape(-1, 3).astype(np.float32)
     rx = scenes.receivers_grid(v, *w["rx"])
-    cand_all = scenes.sampled_candidates(t.shape[0], w["order"], w["cand"] * world, seed=1234)
-    start = rank * w["cand"]
-    cand = np.ascontiguousarray(cand_all[start:start + w["cand"]])
+    total = w["cand"] * (world if weak else 1)
+    cand_all = scenes.sampled_candidates(t.shape[0], w["order"], total, seed=1234)
     # candidates known to be valid for some receivers (found by tools/find_valid_candidates.py and
-    # re-validated by the CPU oracle in tests/) lead every shard, so that the step produces real paths
+    # re-validated by the CPU oracle in tests/) are spread over the list, so that every shard of the
+    # step produces real paths
     fixture = ROOT / "tests" / "golden" / "urban10k_valid_candidates.npz"
     if w["scene"] == ("urban", 29, 29) and fixture.exists():
         known = np.load(fixture)[f"order{w['order']}"]
-        n = min(known.shape[0], cand.shape[0] // 4)
-        cand[:n] = known[:n]
+        n = min(known.shape[0], total // 4)
+        slots = (np.arange(n) * (total // max(n, 1))).astype(np.int64)
+        cand_all[slots] = known[:n]
+    start, stop = (rank * w["cand"], (rank + 1) * w["cand"]) if weak else shard_bounds(total, world, rank)
+    cand = np.ascontiguousarray(cand_all[start:stop])
     return dict(
         name=name, vertices=v, triangles=t, tx=tx, rx=rx, order=w["order"], cand=cand,
-        cand_global=w["cand"] * world, cand_start=start,
+        cand_global=total, cand_start=start,
     )
 
 
@@ -224,33 +252,56 @@ def cpu_threads() -> int:
     return co.num_threads()
 
 
-def cpu_step(wl: dict, cand, rx):
-    """One dense (no early exit) trace + validate on the host cores → (tests, seconds, valid)."""
+def cpu_step(wl: dict, cand, rx, early_exit: int = 2):
+    """One trace + validate on the host cores → (decided pairs, executed tests, seconds, valid).
+    `early_exit=2`: a candidate stops at its first blocker — the same short cut the GPU arm takes,
+    identical outputs; 0 = every (ray, triangle) pair evaluated like the reference's fori_loop."""
     from oracle import c_oracle as co
 
     t0 = time.perf_counter()
     _, _, mask, tests = co.trace_path_candidates(
-        wl["vertices"], wl["triangles"], wl["tx"], rx, cand, early_exit=False, count_tests=True
+        wl["vertices"], wl["triangles"], wl["tx"], rx, cand, early_exit=early_exit, count_tests=True
     )
-    return tests, time.perf_counter() - t0, int(mask.sum())
+    dt = time.perf_counter() - t0
+    decided = int(wl["tx"].shape[0]) * int(rx.shape[0]) * int(cand.shape[0]) * (wl["order"] + 1) * int(wl["triangles"].shape[0])
+    return decided, tests, dt, int(mask.sum())
 
 
 def cpu_calibrate(wl: dict, seconds: float):
-    """Pick a sample that takes about `seconds` on this host."""
+    """Pick a sample that takes about `seconds` on this host (early-exit evaluation)."""
     cand, rx, _ = cpu_sample(wl, 2e8)
     cpu_step(wl, cand[:8], rx[:1])  # load + thread pool warm-up
-    tests, dt, _ = cpu_step(wl, cand, rx)
-    rate = tests / max(dt, 1e-6)
+    decided, _, dt, _ = cpu_step(wl, cand, rx)
+    rate = decided / max(dt, 1e-6)
     return cpu_sample(wl, rate * seconds)
+
+
+def cpu_baseline_block(wl: dict, seconds: float) -> dict:
+    """The `cpu_baseline` object: the oracle port on all host threads on a bounded sample of the
+    workload — decided pairs/s with the early exit (comparable with the GPU arm's `value`), the
+    executed rate, and the dense (no early exit, the reference's literal evaluation) rate on a
+    quarter of the sample."""
+    cores = cpu_threads()
+    cand, rx, sample = cpu_calibrate(wl, seconds)
+    decided, tests, dt, _ = cpu_step(wl, cand, rx)
+    q = max(1, rx.shape[0] // 4)
+    d_decided, d_tests, d_dt, _ = cpu_step(wl, cand, rx[:q], early_exit=0)
+    return {
+        "value": decided / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": dt,
+        "host_cpus": os.cpu_count(),
+        "what": "oracle/oracle.c (C/OpenMP/AVX2 restatement of the reference algorithm; JAX/Warp not installable "
+                "here), a candidate stops at its first blocker like the GPU arm: decided pairs per second",
+        "executed_tests_per_s": tests / dt, "executed_fraction_of_algorithmic": tests / max(decided, 1),
+        "dense_no_early_exit_tests_per_s": d_tests / d_dt,
+    }
 
 
 def run_reference(args, rank: int) -> None:
     """`--impl reference`: the reference's CPU algorithm (oracle port; JAX/Warp are not installable
-    here — DESIGN.md) on all host threads, bounded sample per step.  Rank 0 only."""
+    here — DESIGN.md) on all host threads, bounded sample per step, the same early exit and the same
+    unit (decided pairs per second) as the GPU arm.  Rank 0 only.  Loads nothing of the product."""
     if rank != 0:
         return
-    from oracle import c_oracle as co
-
     wl = build_workload(args.workload, 0, 1)
     cores = cpu_threads()
     # bounded sample per step, sized so that the whole --steps K --warmup W run stays near two minutes
@@ -258,43 +309,56 @@ def run_reference(args, rank: int) -> None:
     cand, rx, sample = cpu_calibrate(wl, per_step)
     for _ in range(args.warmup):
         cpu_step(wl, cand, rx)
-    tests = 0
+    decided = tests = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        n, _, valid = cpu_step(wl, cand, rx)
-        tests += n
+        n, e, _, valid = cpu_step(wl, cand, rx)
+        decided += n
+        tests += e
     dt = time.perf_counter() - t0
-    value = tests / dt
+    value = decided / dt
+    q = max(1, rx.shape[0] // 4)
+    _, d_tests, d_dt, _ = cpu_step(wl, cand, rx[:q], early_exit=0)
     emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(wl, 1, sample=sample),
+        "executed_tests_per_s": tests / dt, "executed_fraction_of_algorithmic": tests / max(decided, 1),
+        "dense_no_early_exit_tests_per_s": d_tests / d_dt,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "host_cpus": os.cpu_count()},
+                         "host_cpus": os.cpu_count(),
+                         "what": "oracle/oracle.c, a candidate stops at its first blocker: decided pairs per second"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
 
 
 def launches_per_step(wl: dict, with_vjp: bool) -> int:
+    """Kernels of OURS launched per step (CUB's radix-sort kernels are not counted): pack, area keys +
+    gather, the cull structure (bounds, keys, iota + gather, group nodes, tile nodes), stage A, the
+    ordering pass (hit count, iota + gather, sample list, set, then per greedy round: resident pass on
+    the samples, hit count, iota + gather), the stats marker, the resident head pass, the culled pass,
+    3 compaction kernels, the VJP.  profiles/inst_counts.json holds the ncu-counted figure."""
     tiles = -(-int(wl["triangles"].shape[0]) // 512)
     rounds = min(4, tiles - 1)
-    return 1 + 2 + 1 + (3 + 1 + 4 * rounds) + -(-tiles // 8) + 3 + (1 if with_vjp else 0)
+    cull = 6 if tiles > 4 else 0
+    return 1 + 2 + cull + 1 + (3 + 2 + 4 * rounds + 1) + 1 + (1 if cull else -(-tiles // 8) - 1) + 3 + (1 if with_vjp else 0)
 
 
 def workload_config(wl: dict, world: int, **extra) -> dict:
     T = int(wl["triangles"].shape[0])
-    pairs = int(wl["tx"].shape[0] * wl["rx"].shape[0] * wl["cand"].shape[0])
+    pairs = int(wl["tx"].shape[0] * wl["rx"].shape[0] * wl["cand_global"])
     cfg = {
         "workload": wl["name"], "triangles": T, "num_tx": int(wl["tx"].shape[0]),
         "num_rx": int(wl["rx"].shape[0]), "order": int(wl["order"]),
-        "candidates_per_gpu": int(wl["cand"].shape[0]), "candidate_pairs_per_gpu": pairs,
-        "algorithmic_tests_per_gpu_step": pairs * (wl["order"] + 1) * T,
-        "blockage": "dense: every segment of every candidate is submitted to the any-hit kernel, like "
-                    "the reference; value counts rays x triangles decided, executed_tests_per_s the "
-                    "Moller-Trumbore evaluations actually run",
-        "parallelism": f"candidate shards x{world}, one all-gather of valid paths",
+        "candidates": int(wl["cand_global"]), "candidate_pairs": pairs,
+        "algorithmic_tests_per_step": pairs * (wl["order"] + 1) * T,
+        "blockage": "dense: every segment of every candidate is decided by the any-hit test, like the "
+                    "reference; value counts rays x triangles decided, executed_tests_per_s the "
+                    "Moller-Trumbore evaluations actually run (a candidate stops at its first blocker; "
+                    "pairs the exact cull proves to be misses are skipped)",
+        "parallelism": f"the workload's candidates in {world} contiguous shards, one all-gather of valid paths",
         "l2_policy": "no flush: each step writes >1.3 GB of path vertices/objects (L2 is 126 MB); "
                      "the 0.5 MB packed mesh is L2/shared-memory resident by design",
     }
@@ -305,6 +369,40 @@ def workload_config(wl: dict, world: int, **extra) -> dict:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+
+
+def parity_check(wl: dict, paths, max_pairs: int = 16384) -> dict:
+    """Compare a strided sub-block of the LAST timed step's outputs (this rank's shard) with the C
+    oracle: the validity mask, the vertices (bits) and the objects of `max_pairs` (rx, candidate) pairs."""
+    from oracle import c_oracle as co
+
+    import torch
+
+    nrx, nc = wl["rx"].shape[0], wl["cand"].shape[0]
+    n_r = max(1, min(nrx, 32))
+    n_c = max(1, min(nc, max_pairs // n_r))
+    sel_r = np.linspace(0, nrx - 1, n_r).astype(np.int64)
+    sel_c = np.linspace(0, nc - 1, n_c).astype(np.int64)
+    # plus the receivers / candidates of (up to 8) paths the GPU reports valid, so that the oracle
+    # confirms valid paths too and not only rejections
+    valid = paths.mask[0].nonzero()[:8].cpu().numpy()
+    sel_r = np.unique(np.concatenate([sel_r, valid[:, 0]]))
+    sel_c = np.unique(np.concatenate([sel_c, valid[:, 1]]))
+    tx0 = wl["tx"][:1]  # first transmitter
+    ev, eo, em = co.trace_path_candidates(wl["vertices"], wl["triangles"], tx0, wl["rx"][sel_r],
+                                          wl["cand"][sel_c], early_exit=2)
+    eo[..., -1] = sel_r[eo[..., -1]].astype(np.int32)  # the oracle numbered the sub-sampled receivers
+    ir = torch.from_numpy(sel_r).to(paths.mask.device)
+    ic = torch.from_numpy(sel_c).to(paths.mask.device)
+    gm = paths.mask[:1].index_select(1, ir).index_select(2, ic).cpu().numpy()
+    gv = paths.vertices.detach()[:1].index_select(1, ir).index_select(2, ic).cpu().numpy()
+    go = paths.objects[:1].index_select(1, ir).index_select(2, ic).cpu().numpy()
+    bad = int((gm != em).sum())
+    bad_v = int((gv.view(np.uint32) != ev.view(np.uint32)).any(axis=(-1, -2)).sum())
+    bad_o = int((go != eo).any(axis=-1).sum())
+    return {"checked_pairs": int(em.size), "mismatches": bad + bad_v + bad_o, "mask_mismatches": bad,
+            "vertex_bit_mismatches": bad_v, "object_mismatches": bad_o, "oracle_valid": int(em.sum()),
+            "against": "oracle/oracle.c on a strided block of the last timed step (rank 0's shard)"}
 
 
 def run_ours(args, rank: int, local_rank: int, world: int) -> None:
@@ -323,15 +421,18 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.cand is not None:  # BASELINE config 5's sweep over the number of candidates
+        WORKLOADS[args.workload]["cand"] = args.cand
     wl = build_workload(args.workload, rank, world)
     k = wl["order"]
-    capacity = 1 << 14
+    capacity = 1 << 10  # valid paths per rank in the gather record (overflow → the API's retry path)
 
     # host buffers (pinned) for the e2e leg; device-resident copies for the kernel-level leg
     host = {n: torch.from_numpy(wl[n]).pin_memory() for n in ("vertices", "triangles", "tx", "rx", "cand")}
     mesh = drt.Mesh.from_numpy(wl["vertices"], wl["triangles"])
     tx_d, rx_d, cand_d = (host[n].to(dev) for n in ("tx", "rx", "cand"))
     record = GatherRecord(capacity, k, dev)
+    gathered = torch.empty(world * record.nbytes, dtype=torch.uint8, device=dev)  # preallocated receive buffer
     stats_acc = torch.zeros(4, dtype=torch.int64, device=dev)
 
     # reverse mode every step (BASELINE config 3 is "with VJP"; SURVEY §8d: VJP of vertices.sum() w.r.t.
@@ -351,7 +452,6 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             torch.autograd.grad(paths.vertices, (mesh.vertices, tx_d, rx_d), cot)
         fill_record(record, paths, wl["cand_global"], wl["cand_start"])
         if world > 1:
-            gathered = torch.empty(world * record.nbytes, dtype=torch.uint8, device=dev)
             dist.all_gather_into_tensor(gathered, record.buffer)
         return paths
 
@@ -381,6 +481,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             grad_host[i].copy_(g, non_blocking=True)
             grads_h.append(grad_host[i])
         valid = gather_valid_paths(record)  # all-gather (N>1) + counts to host
+        assert valid is not None, "gather record overflow: raise `capacity` in bench.py"
         out = (valid.index.cpu(), valid.vertices.cpu(), valid.objects.cpu(), mask_host, *grads_h)
         torch.cuda.current_stream().synchronize()
         return out
@@ -389,6 +490,31 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        r = None
+        for i in range(n):
+            r = fn(i)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), r
+
+    if args.profile_only:
+        # for `ncu`: exactly K steps of the timed loop's body and nothing else, so that per-step kernel
+        # and instruction counts are the capture's totals divided by K (tools/inst_counts.py)
+        keep = None
+        for _ in range(args.steps):
+            keep = step_resident(False)
+        barrier()
+        if rank == 0:
+            emit({"profile_only": True, "steps": args.steps, "workload": wl["name"], "n_gpus": world,
+                  "valid_paths": int(keep.mask.sum().item())})
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- kernel-level leg: inputs resident in HBM ------------------------------------------------
     if sampler:
@@ -404,17 +530,10 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     barrier()
     stats_acc.zero_()
     _lib.check(_lib.lib.drt_profile_reset())
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     if sampler:
         sampler.mark_start()
-    ev0.record()
-    for i in range(args.steps):
-        paths = step_resident(i < 64)
-    ev1.record()
-    barrier()
+    ms, paths = timed(lambda i: step_resident(i < 64), args.steps)
     clocks = sampler.stop() if sampler else None
-    ms = ev0.elapsed_time(ev1)
     tests_local = int(stats_acc[0].item())
     valid_local = int(paths.mask.sum().item())
     import ctypes as C
@@ -424,119 +543,171 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         f = C.c_float()
         _lib.check(_lib.lib.drt_profile_elapsed_ms(slot, C.byref(f)))
         kern_ms.append(f.value)
+
+    # ---- parity: the last timed step against the oracle; the gathered records against the ranks' masks --
+    parity = parity_check(wl, paths) if rank == 0 and not args.no_cpu else None
+    torch.cuda.synchronize()
+    parts = [GatherRecord.views(gathered[r * record.nbytes:(r + 1) * record.nbytes], capacity, k) for r in range(world)] \
+        if world > 1 else [record.fields()]
+    counts = [int(p_[0].item()) for p_ in parts]
+    gather_ok = counts[rank] == valid_local and all(c <= capacity for c in counts)
+    if gather_ok and valid_local > 0:  # this rank's own record inside the gathered buffer: right paths, right bits
+        mine = parts[rank]
+        idx_local = paths.mask.reshape(-1).nonzero().squeeze(-1)
+        pair = torch.div(idx_local, cand_d.shape[0], rounding_mode="floor")
+        idx_global = pair * wl["cand_global"] + (idx_local - pair * cand_d.shape[0]) + wl["cand_start"]
+        gather_ok = bool(torch.equal(mine[1][:valid_local], idx_global)) and bool(
+            torch.equal(mine[2][:valid_local], paths.vertices.detach().reshape(-1, k + 2, 3)[idx_local]))
     del paths
+
+    # ---- sustained: the same step for at least 5 s (the K timed steps above can be a short burst) ---------
+    n_sus = max(args.steps, int(np.ceil(args.sustain_seconds * 1e3 / max(ms / args.steps, 1e-3)))) if args.sustain_seconds > 0 else 0
+    ms_sus = None
+    if n_sus:
+        if world > 1:  # every rank must run the same number of steps
+            t = torch.tensor([n_sus], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            n_sus = int(t.item())
+        ms_sus, _ = timed(lambda i: step_resident(False), n_sus)
 
     # ---- the API's default (pruned) mode: blockage only for candidates that pass the cheap tests -----
     for _ in range(2):
         drt.trace_path_candidates(mesh, tx_d, rx_d, cand_d)
-    evp0, evp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    evp0.record()
-    for _ in range(10):
-        drt.trace_path_candidates(mesh, tx_d, rx_d, cand_d)
-    evp1.record()
-    barrier()
-    ms_pruned = evp0.elapsed_time(evp1) / 10
+    ms_pruned, _ = timed(lambda i: drt.trace_path_candidates(mesh, tx_d, rx_d, cand_d), 10)
+    ms_pruned /= 10
 
-    # ---- end-to-end leg: host buffers through the public API ---------------------------------------
-    e2e_steps = max(1, min(args.steps, 3)) if args.e2e_steps is None else args.e2e_steps
+    # ---- end-to-end leg: host buffers through the public API, as many steps as the timed region ---------
+    e2e_steps = args.steps if args.e2e_steps is None else args.e2e_steps
     step_e2e()
     barrier()
     stats_acc.zero_()
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev2.record()
-    for _ in range(e2e_steps):
-        out = step_e2e()
-    ev3.record()
-    barrier()
-    ms_e2e = ev2.elapsed_time(ev3)
+    ms_e2e, out = timed(lambda i: step_e2e(), e2e_steps)
     tests_e2e_local = int(stats_acc[0].item())
     h2d = sum(int(h.numel() * h.element_size()) for h in host.values())
     d2h = sum(int(o.numel() * o.element_size()) for o in out) + 8 * world
     num_valid_global = int(out[0].shape[0])
 
+    # ---- weak-scaling leg (N > 1): every rank traces a full-size shard of its own ------------------------
+    weak = None
+    if world > 1 and args.weak_steps > 0:
+        wlw = build_workload(args.workload, rank, world, weak=True)
+        cand_w = torch.from_numpy(wlw["cand"]).to(dev)
+        cot_w = torch.ones((tx_d.shape[0], rx_d.shape[0], cand_w.shape[0], k + 2, 3), dtype=torch.float32, device=dev) \
+            if with_vjp else None
+
+        def step_weak(_i):
+            p_ = drt.trace_path_candidates(mesh, tx_d, rx_d, cand_w, dense_blockage=True)
+            if with_vjp:
+                torch.autograd.grad(p_.vertices, (mesh.vertices, tx_d, rx_d), cot_w)
+            fill_record(record, p_, wlw["cand_global"], wlw["cand_start"])
+            dist.all_gather_into_tensor(gathered, record.buffer)
+            return p_
+
+        keep = [step_weak(0), step_weak(1)]
+        ms_weak, _ = timed(step_weak, args.weak_steps)
+        del keep
+        weak = ms_weak
+
     # ---- reduce over ranks: max time, summed work ----------------------------------------------------
-    red = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    tot = torch.tensor([tests_local, tests_e2e_local, valid_local], dtype=torch.int64, device=dev)
+    red = torch.tensor([ms, ms_e2e, ms_sus or 0.0, weak or 0.0], dtype=torch.float64, device=dev)
+    tot = torch.tensor([tests_local, tests_e2e_local, valid_local, int(gather_ok)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms, ms_e2e = red.tolist()
-    tests, tests_e2e, valid_total = tot.tolist()
+    ms, ms_e2e, ms_sus, ms_weak = red.tolist()
+    tests, tests_e2e, valid_total, gather_ok_ranks = tot.tolist()
 
     if rank == 0:
-        peaks_file = ROOT / "MEASURED_PEAKS.json"
-        if peaks_file.exists():
-            peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
-        else:
-            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        cfg = workload_config(wl, world)
+        algo_step = cfg["algorithmic_tests_per_step"]
+        pairs_step = cfg["candidate_pairs"]
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         kms = float(np.mean(kern_ms)) if kern_ms else None
         tests_per_launch = tests_local / max(args.steps, 1)
-        achieved = BYTES_PER_TEST * tests_per_launch / (kms * 1e-3) / 1e9 if kms else None
-        roofline = {
-            "kernel": "blockage pass = drt::path_head_kernel<order+1> (head tiles, ~3/4 of the time) + "
-                      "drt::intersect_kernel<order+1, ANY, PATH> (ring pass over the survivors)",
-            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak if achieved else None, "traffic": None,
-            "peak_source": peak_src, "bytes_per_test": BYTES_PER_TEST,
-            "tests_per_launch": tests_per_launch, "kernel_ms": kms,
-            "kernel_share_of_step": kms * args.steps / ms if kms else None,
-            # what actually bounds the kernel: issue slots; 63 = SASS instructions per
-            # test (cuobjdump of the inner loop), peak = 148 SMs x 4 schedulers x SM clock
-            "fp32_issue": {
-                "sass_instructions_per_test": 63,
-                "achieved_warp_instructions_per_s": 63 * tests_per_launch / 32 / (kms * 1e-3) if kms else None,
-                "peak_warp_instructions_per_s": 148 * 4 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else None,
-            },
-            "note": "streamed-operand model (36 B per executed test); the packed mesh is on-chip "
-                    "resident so DRAM traffic is far below it and the binding limit is FP32 issue — "
-                    "see DESIGN.md and profiles/",
-        }
-        fi = roofline["fp32_issue"]
-        if fi["achieved_warp_instructions_per_s"] and fi["peak_warp_instructions_per_s"]:
-            fi["frac"] = fi["achieved_warp_instructions_per_s"] / fi["peak_warp_instructions_per_s"]
+        # what bounds the blockage kernels: instruction issue (no tensor cores, operands on chip).  The
+        # warp-instruction count per step comes from the committed ncu launch list of this very command
+        # (profiles/inst_counts.json, written by tools/inst_counts.py), never from a literal.
+        inst = None
+        inst_file = ROOT / "profiles" / "inst_counts.json"
+        if inst_file.exists():
+            inst = json.loads(inst_file.read_text()).get(f"{wl['name']}@{world}")
+        issue_peak = 148 * 4 * sm_mhz * 1e6
+        achieved = inst["blockage_warp_instructions_per_step"] / (kms * 1e-3) if inst and kms else None
+        peaks_file = ROOT / "MEASURED_PEAKS.json"
+        hbm_peak = float(json.loads(peaks_file.read_text())["hbm_gbs"]) if peaks_file.exists() else 6650.0
         traffic_file = ROOT / "profiles" / "traffic.json"
-        if traffic_file.exists():
-            roofline["traffic"] = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch")
-        algo_step = world * workload_config(wl, world)["algorithmic_tests_per_gpu_step"]
+        traffic = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch") if traffic_file.exists() else None
+        roofline = {
+            "kernel": "blockage pass = drt::path_head_kernel<order+1> (resident head tiles, every candidate) + "
+                      "drt::path_cull_kernel<order+1> (exact culled pass over the whole mesh, undecided candidates) "
+                      "+ the ordering pass (drt::hit_count_kernel)",
+            "bound": "fp32_issue", "achieved": achieved, "peak": issue_peak, "unit": "warp-inst/s",
+            "frac": achieved / issue_peak if achieved else None, "traffic": traffic,
+            "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (SM clock sampled during the timed region)",
+            "instructions_source": (inst or {}).get("source", "profiles/inst_counts.json has no entry for this "
+                                                              "workload: run tools/inst_counts.py on the ncu launch list"),
+            "warp_instructions_per_executed_test": (inst["blockage_warp_instructions_per_step"] * 32 / tests_per_launch
+                                                     if inst and tests_per_launch else None),
+            "kernel_ms": kms, "kernel_share_of_step": kms * args.steps / ms if kms else None,
+            "executed_tests_per_launch": tests_per_launch,
+            "hbm_model": {
+                "note": "INAPPLICABLE as a roofline (kept because BASELINE.json asks for %HBM): 36 B of triangle "
+                        "operand per executed test against the measured copy bandwidth; the packed mesh is resident "
+                        "on chip, so the real DRAM traffic (`traffic`, ncu) is the path vertices only",
+                "bytes_per_test": BYTES_PER_TEST,
+                "model_gbs": BYTES_PER_TEST * tests_per_launch / (kms * 1e-3) / 1e9 if kms else None,
+                "hbm_peak_gbs": hbm_peak,
+                "dram_gbs_measured": traffic / (ms / args.steps * 1e-3) / 1e9 if traffic else None,
+            },
+        }
         line = {
             "metric": METRIC, "value": algo_step * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": workload_config(
                 wl, world,
                 reverse_mode=("every step also runs the VJP of vertices.sum() w.r.t. tx, rx and mesh.vertices "
-                              "(all-ones cotangent, 1 ms); not counted in value's tests") if with_vjp else "off"),
-            "candidate_pairs_per_s": world * wl["tx"].shape[0] * wl["rx"].shape[0] * wl["cand"].shape[0]
-            * args.steps / (ms * 1e-3),
+                              "(all-ones cotangent); not counted in value's tests") if with_vjp else "off"),
+            "candidate_pairs_per_s": pairs_step * args.steps / (ms * 1e-3),
             "valid_paths_per_s": valid_total * args.steps / (ms * 1e-3),
-            "default_mode": {"what": "trace_path_candidates() as the API runs it by default: identical outputs, "
-                                     "blockage only for candidates that pass the cheap tests (rank 0, not "
-                                     "part of value)",
-                             "ms_per_step": ms_pruned,
-                             "candidate_pairs_per_s": wl["tx"].shape[0] * wl["rx"].shape[0] * wl["cand"].shape[0]
-                             / (ms_pruned * 1e-3)},
             "valid_paths_per_step": valid_total,
             "executed_tests_per_s": tests / (ms * 1e-3),
             "executed_fraction_of_algorithmic": tests / max(args.steps * algo_step, 1),
+            "sustained": {"steps": n_sus, "ms_per_step": ms_sus / n_sus, "seconds": ms_sus * 1e-3,
+                          "value": algo_step * n_sus / (ms_sus * 1e-3)} if n_sus else None,
+            "default_mode": {"what": "trace_path_candidates() as the API runs it by default: identical outputs, "
+                                     "blockage only for candidates that pass the cheap tests (rank 0's shard, "
+                                     "not part of value)",
+                             "ms_per_step": ms_pruned,
+                             "candidate_pairs_per_s": wl["tx"].shape[0] * wl["rx"].shape[0] * wl["cand"].shape[0]
+                             / (ms_pruned * 1e-3)},
             "e2e": {"value": algo_step * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "executed_tests_per_s": tests_e2e / (ms_e2e * 1e-3), "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                     "valid_paths_gathered": num_valid_global},
-            # our kernels per step: pack, area keys + gather, stage A, ordering pass (hit count, iota,
-            # gather, sample list, then per greedy round: resident pass on the samples, hit count, iota,
-            # gather), ceil(tiles / 8) resident passes of the cascade, 3 compaction kernels, the VJP
-            # (CUB's radix-sort kernels are not counted as ours)
-            "gpu_launches": args.steps * launches_per_step(wl, with_vjp),
+            "parity": parity,
+            "gather_check": {"ranks_ok": gather_ok_ranks, "ranks": world, "valid_paths_per_rank": counts,
+                             "what": "after the timed loop every rank reads the all-gathered buffer back: the "
+                                     "counts match its mask and its own record holds its valid paths bit for bit"},
+            "gpu_launches": args.steps * ((inst or {}).get("our_launches_per_step") or launches_per_step(wl, with_vjp)),
             "clocks": clocks, "roofline": roofline,
         }
+        if world > 1 and ms_weak:
+            wcfg = workload_config(build_workload(args.workload, 0, world, weak=True), world)
+            line["weak_scaling"] = {"what": "extra leg: every rank traces a full-size shard of its own "
+                                            f"({wl['cand_global']} candidates per GPU)",
+                                    "steps": args.weak_steps, "ms_per_step": ms_weak / args.weak_steps,
+                                    "value": wcfg["algorithmic_tests_per_step"] * args.weak_steps / (ms_weak * 1e-3)}
         if world == 1 and not args.no_cpu:
-            cores = cpu_threads()
-            cand, rx, sample = cpu_calibrate(wl, args.cpu_seconds)
-            n, dt, _ = cpu_step(wl, cand, rx)
-            line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": sample, "seconds": dt, "host_cpus": os.cpu_count()}
+            cb = cpu_baseline_block(wl, args.cpu_seconds)
+            line["cpu_baseline"] = cb
+            line["vs_cpu"] = {
+                "e2e_decided_pairs_ratio": line["e2e"]["value"] / cb["value"],
+                "executed_tests_ratio": line["executed_tests_per_s"] / cb["executed_tests_per_s"],
+                "note": "both arms stop a candidate at its first blocker; the first ratio is a ratio of times "
+                        "for the same job, the second compares Moller-Trumbore evaluations per second",
+            }
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -573,7 +744,13 @@ def main() -> None:
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per bounded sample")
-    ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--e2e-steps", type=int, default=None, help="default: as many as --steps")
+    ap.add_argument("--sustain-seconds", type=float, default=5.0,
+                    help="extra leg: repeat the step for at least this long (0 = skip)")
+    ap.add_argument("--weak-steps", type=int, default=5, help="extra weak-scaling leg for N > 1 (0 = skip)")
+    ap.add_argument("--cand", type=int, default=None, help="override the workload's number of candidates")
+    ap.add_argument("--profile-only", action="store_true",
+                    help="run exactly --steps steps of the timed loop's body and nothing else (for ncu)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-vjp", action="store_true", help="forward only (default: forward + VJP every step)")
     args = ap.parse_args()

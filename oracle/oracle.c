@@ -265,6 +265,8 @@ static inline float sgnf(float x) { return (x > 0.0f) - (x < 0.0f); } /* NaN →
 
 /* a9: _solvers.py:514-770, non-smoothing branch, blockage = pure-JAX any-hit over the whole mesh
  * for every segment of every candidate (dense, as the reference evaluates it).
+ * early_exit: 0 = dense like the reference's fori_loop; 1 = a ray stops at the first 512-triangle span that
+ * hits; 2 = in addition a candidate stops at its first blocked segment.  Same outputs in all three.
  * tri_mask may be NULL.  stage_out (may be NULL) receives 5 flag bytes per path:
  * inside, same_side, blocked, too_small, finite.  tests_done (may be NULL) receives the number of
  * ray-triangle tests evaluated. */
@@ -331,6 +333,10 @@ ORC_API void orc_trace_path_candidates(int64_t V, int64_t T, const float *verts,
                     if (any && early_exit) break;
                 }
                 blocked |= any;
+                /* early_exit >= 2: a blocked candidate is invalid whatever its other segments do, so a
+                 * tuned CPU implementation stops here (mask identical; the per-stage flags would not be,
+                 * so this level is only honoured when they are not requested) */
+                if (blocked && early_exit >= 2 && !stage_out) break;
             }
         }
         for (int i = 0; i < k + 2; ++i) finite &= isfinite(full[i].x) && isfinite(full[i].y) && isfinite(full[i].z);

@@ -12,10 +12,15 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    import os
+
+    # the reference arm must not load the product: with the library path pointing nowhere, importing
+    # the package would raise
+    env = dict(os.environ, DIFFERT_B200_LIB="/nonexistent/libdiffert_b200.so")
     res = subprocess.run(
         [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
          "--cpu-seconds", "0.3", "--workload", "urban10k_small"],
-        capture_output=True, text=True, timeout=600, cwd=ROOT,
+        capture_output=True, text=True, timeout=600, cwd=ROOT, env=env,
     )
     assert res.returncode == 0, res.stderr
     lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
@@ -29,6 +34,9 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["value"] > 1e6 and "workload" in d["config"]
+    # same unit as the GPU arm: decided pairs per second with the same early exit, executed rate beside it
+    assert d["executed_tests_per_s"] <= d["value"] and 0 < d["executed_fraction_of_algorithmic"] <= 1
+    assert d["dense_no_early_exit_tests_per_s"] > 0
 
 
 def test_non_zero_ranks_of_the_reference_arm_do_nothing():
