@@ -139,9 +139,11 @@ __global__ void cull_keys_kernel(int64_t n, const Tri48 *__restrict__ pack, cons
             const float c[3] = {t.v0.x + (t.e1.x + t.e2.x) * (1.0f / 3.0f), t.v0.y + (t.e1.y + t.e2.y) * (1.0f / 3.0f),
                                 t.v0.z + (t.e1.z + t.e2.z) * (1.0f / 3.0f)};
             uint32_t q[3];
+            // ONE scale for the three axes (the largest extent): a city is 20 x wider than tall, and cells
+            // that are cubes in space keep the triangles of a building together
+            const float ext = fmaxf(fmaxf(bounds[3] - bounds[0], bounds[4] - bounds[1]), bounds[5] - bounds[2]);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float ext = bounds[3 + k] - bounds[k];
                 float x = ext > 0.0f ? (c[k] - bounds[k]) / ext : 0.0f;
                 x = fminf(fmaxf(x * 1024.0f, 0.0f), 1023.0f);  // NaN → 0
                 q[k] = uint32_t(x);
@@ -205,7 +207,7 @@ __global__ void cull_group_nodes_kernel(int64_t num_groups, const Tri48 *__restr
 // groups' axes (a normal within asin(sa_g) of a group axis that is within asin(x) of a tile axis is
 // within asin(x) + asin(sa_g) of it, and sin(p + q) <= sin p + sin q)
 __global__ void cull_tile_nodes_kernel(int64_t num_tiles, int64_t num_groups, const CullNode *__restrict__ groups,
-                                       CullNode *__restrict__ tiles) {
+                                       CullNode *__restrict__ tiles, const int fan) {
     const int64_t tidx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     if (tidx >= num_tiles) return;
     float3 lo = make_float3(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
@@ -213,8 +215,8 @@ __global__ void cull_tile_nodes_kernel(int64_t num_tiles, int64_t num_groups, co
     float r = 0.0f, e = 0.0f, st = 1.0f;
     bool any = false, cullable = true;
     AxisSet axes;
-    for (int k = 0; k < kCullFan; ++k) {
-        const int64_t gidx = tidx * kCullFan + k;
+    for (int k = 0; k < fan; ++k) {
+        const int64_t gidx = tidx * fan + k;
         if (gidx >= num_groups) break;
         const CullNode g = groups[gidx];
         if (g.half.x < 0.0f) continue;  // empty group
@@ -263,8 +265,25 @@ CullLayout cull_layout(int64_t records) {
     l.num_groups = (n + kCullGroup - 1) / kCullGroup;
     l.num_tiles = (l.num_groups + kCullFan - 1) / kCullFan;
     size_t off = 0;
+    // levels of the 8-ary hierarchy, bottom-up sizes, stored top-first
+    int sizes[kWalkMaxLevels], nb = 0;
+    int64_t cur = l.num_groups;
+    sizes[nb++] = int(cur);
+    while (cur > kWalkFan && nb < kWalkMaxLevels) {
+        cur = (cur + kWalkFan - 1) / kWalkFan;
+        sizes[nb++] = int(cur);
+    }
+    l.levels.num_levels = nb;
+    int64_t walk_nodes = 0;
+    for (int i = 0; i < nb; ++i) {
+        l.levels.size[i] = sizes[nb - 1 - i];
+        l.levels.offset[i] = int(walk_nodes);
+        walk_nodes += sizes[nb - 1 - i];
+    }
+    for (int i = nb; i < kWalkMaxLevels; ++i) l.levels.size[i] = l.levels.offset[i] = 0;
     l.pack = off, off += a256(size_t(n) * sizeof(Tri48));
-    l.groups = off, off += a256(size_t(l.num_groups) * sizeof(CullNode));
+    l.walk = off, off += a256(size_t(walk_nodes) * sizeof(CullNode));
+    l.groups = l.walk + size_t(l.levels.offset[nb - 1]) * sizeof(CullNode);  // the last level
     l.tiles = off, off += a256(size_t(l.num_tiles) * sizeof(CullNode));
     l.bounds = off, off += 256;
     l.keys = off, off += a256(size_t(n) * sizeof(uint32_t));
@@ -288,7 +307,13 @@ int cull_build(cudaStream_t s, int64_t records, const Tri48 *pack_in, unsigned c
     const int rc = drt_sort_records_by_keys(s, records, pack_in, keys, sort_ws, sort_bytes, pack);
     if (rc != DRT_OK) return rc;
     cull_group_nodes_kernel<<<unsigned((l.num_groups + 127) / 128), 128, 0, s>>>(l.num_groups, pack, groups);
-    cull_tile_nodes_kernel<<<unsigned((l.num_tiles + 63) / 64), 64, 0, s>>>(l.num_tiles, l.num_groups, groups, tiles);
+    cull_tile_nodes_kernel<<<unsigned((l.num_tiles + 63) / 64), 64, 0, s>>>(l.num_tiles, l.num_groups, groups, tiles,
+                                                                              kCullFan);
+    CullNode *walk = reinterpret_cast<CullNode *>(ws + l.walk);
+    for (int lev = l.levels.num_levels - 2; lev >= 0; --lev)  // bottom-up: level lev from level lev + 1
+        cull_tile_nodes_kernel<<<unsigned((l.levels.size[lev] + 63) / 64), 64, 0, s>>>(
+            l.levels.size[lev], l.levels.size[lev + 1], walk + l.levels.offset[lev + 1], walk + l.levels.offset[lev],
+            kWalkFan);
     return cudaGetLastError() == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
 }
 

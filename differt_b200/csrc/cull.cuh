@@ -108,12 +108,24 @@ __device__ __forceinline__ bool node_culled(const SegCull &s, const CullNode &n)
     return tmin > tmax + 1e-5f;
 }
 
+// The 8-ary hierarchy of the per-thread traversal (path_walk_kernel): level 0 is the top (<= 8 nodes,
+// children of a virtual root), the last level holds the groups; node i of level l has the children
+// 8i .. 8i+7 of level l+1.  Offsets are in nodes from the start of the `walk` array.
+constexpr int kWalkFan = 8;
+constexpr int kWalkMaxLevels = 8;
+struct WalkLevels {
+    int num_levels;
+    int offset[kWalkMaxLevels];
+    int size[kWalkMaxLevels];
+};
+
 size_t cull_workspace_bytes(int64_t records);
-// Builds the spatially ordered pack and its two node levels from a packed mesh of `records` records
+// Builds the spatially ordered pack and its node levels from a packed mesh of `records` records
 // (a multiple of kTile).  Layout inside `ws`: see CullLayout.
 struct CullLayout {
-    size_t pack, groups, tiles, bounds, keys, total;
+    size_t pack, groups, tiles, walk, bounds, keys, total;
     int64_t num_groups, num_tiles;
+    WalkLevels levels;  // groups are ALSO the last level of `walk` (stored once, inside `walk`)
 };
 CullLayout cull_layout(int64_t records);
 int cull_build(cudaStream_t s, int64_t records, const Tri48 *pack_in, unsigned char *ws, const CullLayout &l,

@@ -199,7 +199,7 @@ def trace_path_candidates(
     if with_stats:
         s = stats.cpu().tolist()
         paths.stats = {"tests_done": s[0], "candidates_blockage_tested": s[1], "head_pass_survivors": s[2],
-                       "ordering_pass": s[3]}
+                       "ordering_pass": s[3] & 255, "culled_pass": bool(s[3] & 256)}
     return paths
 
 

@@ -195,8 +195,9 @@ DRT_API int drt_consecutive_vertices_are_on_same_side_of_mirror(
  *       vertices [Ntx,Nrx,C,k+2,3] f32, objects [Ntx,Nrx,C,k+2] i32, mask [Ntx,Nrx,C] u8.
  *     `stats` (nullable, device int64[4]): [0] ray–triangle tests evaluated, [1] candidates that
  *     passed the cheap tests (the only ones blockage-tested unless DRT_TRACE_DENSE_BLOCKAGE),
- *     [2] candidates still unblocked after the first resident pass (8 tiles), [3] 0 if the
- *     batch-specific ordering pass did not run (small or pruned batches), else 1 + its greedy rounds.
+ *     [2] candidates still unblocked after the first resident pass (8 tiles), [3] bit field: low byte =
+ *     1 + greedy rounds of the batch-specific ordering pass (0 if it did not run), bit 8 = the exactly
+ *     culled blockage pass (csrc/cull.cuh) ran.
  *     The callee zero-fills it.
  * K6b reverse mode of `vertices` w.r.t. tx, rx and Mesh.vertices (mask carries no cotangent,
  *     reference: _mesh.py:3087-3094).  g_* outputs are zero-filled by the callee.
