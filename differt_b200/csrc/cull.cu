@@ -1,6 +1,6 @@
 // Builds the structure behind the exact conservative cull of the blockage test (cull.cuh): the packed
 // triangles in Morton order of their centroids, one CullNode per group of 8 consecutive triangles and
-// one per tile of 32 groups.  Stateless like everything else in the library: rebuilt per call from the
+// the levels of an 8-ary hierarchy above them.  Stateless like everything else in the library: rebuilt per call from the
 // packed mesh (three tiny kernels + one CUB radix sort; ~30 µs for 10 000 triangles).
 #include "cull.cuh"
 
@@ -203,8 +203,8 @@ __global__ void cull_group_nodes_kernel(int64_t num_groups, const Tri48 *__restr
     nodes[gidx] = node;
 }
 
-// one thread per tile of kCullFan consecutive groups: union of the boxes, axes re-clustered from the
-// groups' axes (a normal within asin(sa_g) of a group axis that is within asin(x) of a tile axis is
+// one thread per parent of `fan` consecutive nodes of the level below: union of the boxes, axes
+// re-clustered from the children's axes (a normal within asin(sa_g) of a group axis that is within asin(x) of a tile axis is
 // within asin(x) + asin(sa_g) of it, and sin(p + q) <= sin p + sin q)
 __global__ void cull_tile_nodes_kernel(int64_t num_tiles, int64_t num_groups, const CullNode *__restrict__ groups,
                                        CullNode *__restrict__ tiles, const int fan) {
@@ -263,7 +263,6 @@ CullLayout cull_layout(int64_t records) {
     CullLayout l{};
     const int64_t n = records > 0 ? records : 1;
     l.num_groups = (n + kCullGroup - 1) / kCullGroup;
-    l.num_tiles = (l.num_groups + kCullFan - 1) / kCullFan;
     size_t off = 0;
     // levels of the 8-ary hierarchy, bottom-up sizes, stored top-first
     int sizes[kWalkMaxLevels], nb = 0;
@@ -284,7 +283,6 @@ CullLayout cull_layout(int64_t records) {
     l.pack = off, off += a256(size_t(n) * sizeof(Tri48));
     l.walk = off, off += a256(size_t(walk_nodes) * sizeof(CullNode));
     l.groups = l.walk + size_t(l.levels.offset[nb - 1]) * sizeof(CullNode);  // the last level
-    l.tiles = off, off += a256(size_t(l.num_tiles) * sizeof(CullNode));
     l.bounds = off, off += 256;
     l.keys = off, off += a256(size_t(n) * sizeof(uint32_t));
     l.total = off;
@@ -300,15 +298,12 @@ int cull_build(cudaStream_t s, int64_t records, const Tri48 *pack_in, unsigned c
     uint32_t *keys = reinterpret_cast<uint32_t *>(ws + l.keys);
     Tri48 *pack = reinterpret_cast<Tri48 *>(ws + l.pack);
     CullNode *groups = reinterpret_cast<CullNode *>(ws + l.groups);
-    CullNode *tiles = reinterpret_cast<CullNode *>(ws + l.tiles);
     cull_bounds_kernel<<<1, 1024, 0, s>>>(records, pack_in, bounds);
     cull_keys_kernel<<<unsigned((records + 255) / 256), 256, 0, s>>>(records, pack_in, bounds, keys);
     if (cudaGetLastError() != cudaSuccess) return DRT_ERR_CUDA;
     const int rc = drt_sort_records_by_keys(s, records, pack_in, keys, sort_ws, sort_bytes, pack);
     if (rc != DRT_OK) return rc;
     cull_group_nodes_kernel<<<unsigned((l.num_groups + 127) / 128), 128, 0, s>>>(l.num_groups, pack, groups);
-    cull_tile_nodes_kernel<<<unsigned((l.num_tiles + 63) / 64), 64, 0, s>>>(l.num_tiles, l.num_groups, groups, tiles,
-                                                                              kCullFan);
     CullNode *walk = reinterpret_cast<CullNode *>(ws + l.walk);
     for (int lev = l.levels.num_levels - 2; lev >= 0; --lev)  // bottom-up: level lev from level lev + 1
         cull_tile_nodes_kernel<<<unsigned((l.levels.size[lev] + 63) / 64), 64, 0, s>>>(

@@ -27,7 +27,7 @@
 // violated by overflow; underflow needs products below 2^-126, excluded by the guards below.
 //
 // ---- The test ---------------------------------------------------------------------------------------
-// A NODE (8 triangles, or 32 such groups) stores its bounding box (centre, half extent), up to three
+// A NODE (a group of 8 triangles, or 8 nodes of the level below) stores its bounding box (centre, half extent), up to three
 // unit axes such that every triangle normal is within angle alpha of ±one axis (sin/cos alpha), the
 // smallest sin(theta), E >= |e1|+|e2| and R >= every |coordinate|.  For a segment (o, d):
 //     g  = sin_theta_min (min_k |d^.c_k| cos_alpha - sin_alpha) - 2e-5      <= rho - 8u for every triangle
@@ -49,9 +49,7 @@
 
 namespace drt {
 
-constexpr int kCullGroup = 8;                     // triangles per leaf node
-constexpr int kCullFan = 32;                      // leaf nodes per tile node (one per lane)
-constexpr int kCullTile = kCullGroup * kCullFan;  // 256 triangles per tile node
+constexpr int kCullGroup = 8;  // triangles per leaf node (group)
 
 struct __align__(16) CullNode {  // 80 bytes
     float4 ctr;   // xyz = box centre,      w = cos(alpha)   (lower bound)
@@ -123,8 +121,8 @@ size_t cull_workspace_bytes(int64_t records);
 // Builds the spatially ordered pack and its node levels from a packed mesh of `records` records
 // (a multiple of kTile).  Layout inside `ws`: see CullLayout.
 struct CullLayout {
-    size_t pack, groups, tiles, walk, bounds, keys, total;
-    int64_t num_groups, num_tiles;
+    size_t pack, groups, walk, bounds, keys, total;
+    int64_t num_groups;
     WalkLevels levels;  // groups are ALSO the last level of `walk` (stored once, inside `walk`)
 };
 CullLayout cull_layout(int64_t records);

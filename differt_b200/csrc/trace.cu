@@ -212,16 +212,10 @@ int drt_sort_records_by_keys(drt_stream_t stream, int64_t n, const void *pack_in
 #ifndef DRT_PATH_HEAD_CTAS
 #define DRT_PATH_HEAD_CTAS 1
 #endif
-#ifndef DRT_BLOCKAGE_WALK
-#define DRT_BLOCKAGE_WALK 1  // 0: resident head pass + warp-per-candidate culled pass instead of the traversal
+#ifndef DRT_WALK_MIN_TILES
+#define DRT_WALK_MIN_TILES 4
 #endif
-#ifndef DRT_CULL_HEAD_TILES
-#define DRT_CULL_HEAD_TILES 4
-#endif
-#ifndef DRT_CULL_CTAS
-#define DRT_CULL_CTAS 4
-#endif
-constexpr int kCullHead = DRT_CULL_HEAD_TILES;  // head tiles in front of the culled pass (<= kPathHead)
+constexpr int kCullHead = DRT_WALK_MIN_TILES;  // meshes with more tiles than this take the culled traversal
 constexpr int kPathHead = DRT_PATH_HEAD_TILES;
 constexpr int kPathHeadWarps = DRT_PATH_HEAD_WARPS;
 constexpr size_t kPathHeadSmem = size_t(kPathHead) * kTile * sizeof(Tri48) + 16;
@@ -337,130 +331,6 @@ path_head_kernel(const Tri48 *__restrict__ pack, const int num_head_tiles, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// Blockage, culled pass (cull.cuh): the candidates the resident passes over the head tiles left
-// undecided — mostly UNBLOCKED ones, which would otherwise have to be tested against every triangle —
-// against the whole mesh in spatial order.  One warp per candidate.  Level 1: the lanes test 32 tile
-// nodes (256 triangles each) at a time against the candidate's segments; level 2: for every tile that
-// some segment may touch, the 32 lanes test its 32 groups (8 triangles each); level 3: the surviving
-// groups are evaluated four at a time with the exact Möller–Trumbore test (lane = triangle, only the
-// segments that survived for that group).  A (segment, triangle) pair is skipped only when node_culled
-// PROVES the reference's fp32 test reports no hit, so the mask is bit-identical to the dense evaluation.
-// Nodes and triangles are read through L1/L2 (the working set of a candidate is a few KB).
-// ------------------------------------------------------------------------------------------------
-
-constexpr int kCullWarps = 8;
-
-template <int NSEG>
-__global__ void __launch_bounds__(kCullWarps * 32)
-path_cull_kernel(const Tri48 *__restrict__ pack, const CullNode *__restrict__ tiles, const int num_tile_nodes,
-                 const CullNode *__restrict__ groups, const int64_t num_units_host,
-                 const int64_t *__restrict__ num_units_dev, const float *__restrict__ vertices,
-                 const uint32_t *__restrict__ list, const float eps, const float thr,
-                 uint8_t *__restrict__ mask, int64_t *tests_done) {
-    __shared__ uint8_t sel_all[kCullWarps][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *sel = sel_all[warp];
-    const int64_t num_units = num_units_dev ? *num_units_dev : num_units_host;
-    const int64_t total_warps = int64_t(gridDim.x) * kCullWarps;
-    constexpr int NV = NSEG + 1;
-    static_assert(3 * NV <= 32, "one float per lane prefetch");
-    auto path_of = [&](int64_t u) -> int64_t { return list != nullptr ? int64_t(list[u]) : u; };
-    auto fetch = [&](int64_t path) -> float { return lane < 3 * NV ? vertices[path * (3 * NV) + lane] : 0.0f; };
-
-    int64_t unit = int64_t(blockIdx.x) * kCullWarps + warp;
-    int64_t path_cur = unit < num_units ? path_of(unit) : 0;
-    float pf = unit < num_units ? fetch(path_cur) : 0.0f;
-    int64_t path_next = unit + total_warps < num_units ? path_of(unit + total_warps) : 0;
-    int64_t tests = 0;
-    for (; unit < num_units; unit += total_warps) {
-        float3 o[NSEG], d[NSEG];
-        SegCull sc[NSEG];
-        uint32_t alive = 0;
-        {
-            float3 prev = make_float3(__shfl_sync(kFull, pf, 0), __shfl_sync(kFull, pf, 1), __shfl_sync(kFull, pf, 2));
-#pragma unroll
-            for (int sgm = 0; sgm < NSEG; ++sgm) {
-                const float3 next = make_float3(__shfl_sync(kFull, pf, 3 * sgm + 3), __shfl_sync(kFull, pf, 3 * sgm + 4),
-                                                __shfl_sync(kFull, pf, 3 * sgm + 5));
-                o[sgm] = prev;
-                d[sgm] = sub3(next, prev);  // jnp.diff (_solvers.py:593)
-                // d = 0 → a = 0 → no hit; a non-finite origin or direction → NaN/inf comparisons → no hit
-                const bool dead = (d[sgm].x == 0.0f && d[sgm].y == 0.0f && d[sgm].z == 0.0f) || !finite3(prev) ||
-                                  !finite3(d[sgm]);
-                if (!dead) alive |= 1u << sgm;
-                sc[sgm] = make_seg_cull(o[sgm], d[sgm]);
-                prev = next;
-            }
-        }
-        const int64_t path = path_cur;
-        path_cur = path_next;
-        if (unit + total_warps < num_units) pf = fetch(path_cur);
-        path_next = unit + 2 * total_warps < num_units ? path_of(unit + 2 * total_warps) : 0;
-        if (alive == 0) continue;
-
-        bool blocked = false;
-        for (int tb = 0; tb < num_tile_nodes && !blocked; tb += 32) {
-            uint32_t tmask = 0;
-            if (tb + lane < num_tile_nodes) {
-                const CullNode node = tiles[tb + lane];
-#pragma unroll
-                for (int sgm = 0; sgm < NSEG; ++sgm)
-                    if ((alive >> sgm) & 1u) tmask |= node_culled(sc[sgm], node) ? 0u : (1u << sgm);
-            }
-            uint32_t tballot = __ballot_sync(kFull, tmask != 0);
-            while (tballot != 0 && !blocked) {
-                const int tl = __ffs(tballot) - 1;
-                tballot &= tballot - 1;
-                const uint32_t tm = __shfl_sync(kFull, tmask, tl);
-                const int64_t g0 = int64_t(tb + tl) * kCullFan;  // first group of the tile
-                uint32_t gmask = 0;
-                {
-                    const CullNode node = groups[g0 + lane];
-#pragma unroll
-                    for (int sgm = 0; sgm < NSEG; ++sgm)
-                        if ((tm >> sgm) & 1u) gmask |= node_culled(sc[sgm], node) ? 0u : (1u << sgm);
-                }
-                const uint32_t gballot = __ballot_sync(kFull, gmask != 0);
-                const int ng = __popc(gballot);
-                if (gmask != 0) sel[__popc(gballot & ((1u << lane) - 1u))] = uint8_t(lane);
-                __syncwarp();
-                for (int b = 0; b < ng && !blocked; b += 32 / kCullGroup) {
-                    const int which = b + lane / kCullGroup;
-                    const int gl = which < ng ? int(sel[which]) : 0;
-                    uint32_t gm = __shfl_sync(kFull, gmask, gl);
-                    if (which >= ng) gm = 0;
-                    const Tri48 *rec = pack + (g0 + gl) * kCullGroup + (lane % kCullGroup);
-                    const float4 ta = rec->a, tb4 = rec->b, tc = rec->c;
-                    const Tri tr = unpack(ta, tb4, tc);
-                    bool hit = false, weird = false;
-#pragma unroll
-                    for (int sgm = 0; sgm < NSEG; ++sgm)
-                        if ((gm >> sgm) & 1u) hit = mt_any_fast(o[sgm], d[sgm], tr, eps, thr, weird) || hit;
-                    if (__any_sync(kFull, weird)) {  // |a| outside the fast reciprocal's range: exact redo
-                        hit = false;
-#pragma unroll
-                        for (int sgm = 0; sgm < NSEG; ++sgm)
-                            if ((gm >> sgm) & 1u) {
-                                float t;
-                                hit = (mt_exact(o[sgm], d[sgm], tr, eps, t) && t < thr) || hit;
-                            }
-                    }
-                    tests += __popc(gm);
-                    blocked = __any_sync(kFull, hit);
-                }
-                __syncwarp();
-            }
-        }
-        if (blocked && lane == 0) mask[path] = 0;
-    }
-    if (tests_done != nullptr) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) tests += __shfl_xor_sync(kFull, tests, off);
-        if (lane == 0 && tests) atomicAdd(reinterpret_cast<unsigned long long *>(tests_done), (unsigned long long)tests);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Blockage, culled traversal (cull.cuh): ONE WARP per candidate walks the 8-ary hierarchy over the
 // Morton-ordered pack, one segment at a time — the LAST segment first: it ends at the receiver, at
 // street level, and is the likeliest to be blocked — with all 32 lanes busy on that segment:
@@ -485,7 +355,14 @@ path_cull_kernel(const Tri48 *__restrict__ pack, const CullNode *__restrict__ ti
 #ifndef DRT_WALK_CTAS
 #define DRT_WALK_CTAS 4
 #endif
+#ifndef DRT_WALK_CHUNK
+#define DRT_WALK_CHUNK 16
+#endif
+#ifndef DRT_WALK_HEAD_ROWS
+#define DRT_WALK_HEAD_ROWS 1
+#endif
 constexpr int kWalkWarps = DRT_WALK_WARPS;
+constexpr int kWalkHeadRows = DRT_WALK_HEAD_ROWS;  // rows of 32 largest triangles tested before the walk
 constexpr int kWalkStack = 256;      // node stack: a step pops <= 4 and pushes <= 32, depth-first: <= 7 x 28 + 32
 constexpr int kWalkGroupStack = 64;  // group stack: drained 4 at a time as soon as it holds 4: <= 3 + 32
 
@@ -519,11 +396,14 @@ path_walk_kernel(const Tri48 *__restrict__ pack, const CullNode *__restrict__ no
     // the 32 largest triangles (first row of the area-sorted pack), one per lane: every candidate is
     // tested against them before it walks the hierarchy — a random segment is blocked by a triangle
     // with a probability proportional to its area (the ground alone blocks a third of the bench batch)
-    const Tri head_tri = unpack(head_row[lane].a, head_row[lane].b, head_row[lane].c);
+    Tri head_tri[kWalkHeadRows];
+#pragma unroll
+    for (int h = 0; h < kWalkHeadRows; ++h)
+        head_tri[h] = unpack(head_row[32 * h + lane].a, head_row[32 * h + lane].b, head_row[32 * h + lane].c);
 
     // Work distribution: chunks of kChunk consecutive candidates from a global cursor (the cost of a
     // candidate varies by two orders of magnitude; a static stride would leave most warps idle at the end)
-    constexpr int kChunk = 16;
+    constexpr int kChunk = DRT_WALK_CHUNK;
     int64_t tests = 0;
     while (true) {
         unsigned long long base = 0;
@@ -538,14 +418,15 @@ path_walk_kernel(const Tri48 *__restrict__ pack, const CullNode *__restrict__ no
         if (unit + 1 < unit1) pf = fetch(path_of(unit + 1));
 
         bool blocked = false;
-        {   // head row: every segment against the 32 largest triangles
+#pragma unroll
+        for (int h = 0; h < kWalkHeadRows && !blocked; ++h) {  // head rows: every segment against the largest triangles
             bool hit = false, weird = false;
             float3 prev = make_float3(__shfl_sync(kFull, pv, 0), __shfl_sync(kFull, pv, 1), __shfl_sync(kFull, pv, 2));
 #pragma unroll
             for (int sgm = 0; sgm < NSEG; ++sgm) {
                 const float3 next = make_float3(__shfl_sync(kFull, pv, 3 * sgm + 3), __shfl_sync(kFull, pv, 3 * sgm + 4),
                                                 __shfl_sync(kFull, pv, 3 * sgm + 5));
-                hit = mt_any_fast(prev, sub3(next, prev), head_tri, eps, thr, weird) || hit;
+                hit = mt_any_fast(prev, sub3(next, prev), head_tri[h], eps, thr, weird) || hit;
                 prev = next;
             }
             if (__any_sync(kFull, weird)) {  // re-evaluate with the general test
@@ -557,7 +438,7 @@ path_walk_kernel(const Tri48 *__restrict__ pack, const CullNode *__restrict__ no
                                                     __shfl_sync(kFull, pv, 3 * sgm + 4),
                                                     __shfl_sync(kFull, pv, 3 * sgm + 5));
                     float t;
-                    hit = (mt_exact(prev, sub3(next, prev), head_tri, eps, t) && t < thr) || hit;
+                    hit = (mt_exact(prev, sub3(next, prev), head_tri[h], eps, t) && t < thr) || hit;
                     prev = next;
                 }
             }
@@ -645,7 +526,6 @@ path_walk_kernel(const Tri48 *__restrict__ pack, const CullNode *__restrict__ no
 // ------------------------------------------------------------------------------------------------
 
 __global__ void set_i64_kernel(int64_t *p, int64_t v) { *p = v; }
-__global__ void or_i64_kernel(int64_t *p, int64_t v) { *p |= v; }
 
 __global__ void sample_list_kernel(int64_t n, int64_t stride, uint32_t *__restrict__ list) {
     const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
@@ -1143,7 +1023,6 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
         cudaEventRecord(g_profile.start[slot], s);
     }
     if constexpr (NSEG <= 6) {
-#if DRT_BLOCKAGE_WALK
         // Meshes with more tiles than a resident pass holds: per-thread traversal of the culled
         // hierarchy for every candidate (cull.cuh; its proof needs FLT_MIN <= eps and 0 < thr <= 1,
         // other parameters keep the row-per-warp passes below).
@@ -1164,7 +1043,6 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
             if (slot >= 0) cudaEventRecord(g_profile.stop[slot], s);
             return e == cudaSuccess ? DRT_OK : DRT_ERR_CUDA;
         }
-#endif
         // ordering pass (dense batches only: a pruned work list is too short to pay for it)
         constexpr int64_t kSamples = 32768;
         if (dense && !compact && a.P >= 8 * kSamples && p.eps >= 1.17549435e-38f) {
@@ -1258,27 +1136,8 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
         uint32_t *out_list = list2;
         int64_t *out_count = list2_count;  // counters[2]; counters[3] is list3's
         e = cudaSuccess;
-        // With more tiles than the head holds, ONE resident pass over the first kCullHead tiles of the
-        // ordered pack (the likeliest blockers) decides most blocked candidates, and the rest — mostly
-        // unblocked ones — goes to the culled pass over the whole mesh in spatial order (cull.cuh).  The
-        // cull's proof needs FLT_MIN <= eps and 0 < thr <= 1; other parameters keep the plain cascade.
-        const bool use_cull = cull_ws != nullptr && NT > kCullHead && p.eps >= 1.17549435e-38f && p.thr > 0.0f &&
-                              p.thr <= 1.0f;
-        const int head_step = use_cull ? kCullHead : kPathHead;
+        const int head_step = kPathHead;
         for (int t0 = 0; t0 < NT && e == cudaSuccess; t0 += head_step) {
-            if (use_cull && t0 > 0) {
-                auto ck = path_cull_kernel<NSEG>;
-                const int64_t cblocks2 = (bound + kCullWarps - 1) / kCullWarps;
-                const int64_t cres = int64_t(sms) * DRT_CULL_CTAS;
-                ck<<<unsigned(cblocks2 < cres ? cblocks2 : cres), kCullWarps * 32, 0, s>>>(
-                    reinterpret_cast<const Tri48 *>(cull_ws + cull.pack),
-                    reinterpret_cast<const CullNode *>(cull_ws + cull.tiles), int(cull.num_tiles),
-                    reinterpret_cast<const CullNode *>(cull_ws + cull.groups), bound, in_count, a.out_vertices, in_list,
-                    a.eps, p.thr, a.out_mask, tests_done);
-                e = cudaGetLastError();
-                if (e == cudaSuccess && tests_done != nullptr) or_i64_kernel<<<1, 1, 0, s>>>(tests_done + 3, 256);
-                break;
-            }
             const int nh = NT - t0 < head_step ? NT - t0 : head_step;
             hk<<<unsigned(hblocks < hres ? hblocks : hres), kPathHeadWarps * 32, kPathHeadSmem, s>>>(
                 pack_active + size_t(t0) * kTile, nh, bound, in_count, a.out_vertices, in_list, a.eps, p.thr,
