@@ -53,10 +53,12 @@ PROTOTYPES: dict[str, tuple] = {
         C.c_int,
         [ptr, i64, i64, ptr, ptr, ptr, i32, i64, ptr, i64, ptr, i64, i32, ptr, f32, f32, f32, u32,
          ptr, size_t, ptr, ptr, ptr, ptr]),
+    "drt_trace_prepared_bytes": (size_t, [i64]),
+    "drt_trace_prepare": (C.c_int, [ptr, i64, i64, ptr, ptr, ptr, ptr, size_t]),
     "drt_trace_valid_workspace_bytes": (size_t, [i64, i64]),
     "drt_trace_valid_path_candidates": (
         C.c_int,
-        [ptr, i64, i64, ptr, ptr, ptr, i32, i64, ptr, i64, ptr, i64, i32, ptr, f32, f32, f32, i64, ptr, size_t,
+        [ptr, i64, i64, ptr, ptr, ptr, i32, i64, ptr, i64, ptr, i64, i32, ptr, f32, f32, f32, u32, i64, ptr, size_t,
          ptr, ptr, ptr, ptr, ptr]),
     "drt_trace_path_candidates_vjp": (
         C.c_int, [ptr, i64, i64, ptr, ptr, i64, ptr, i64, ptr, i64, i32, ptr, ptr, ptr, ptr, ptr]),
@@ -104,6 +106,7 @@ PROTOTYPES: dict[str, tuple] = {
 
 DRT_TRACE_DENSE_BLOCKAGE = 1
 DRT_TRACE_PROFILE = 2
+DRT_TRACE_PREPARED = 4
 DRT_MAX_ORDER = 8
 DRT_MAX_BATCH_DIMS = 4
 DRT_TILE_TRIANGLES = 512
@@ -120,7 +123,7 @@ def _load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the library does not export the ABI
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.drt_abi_version() != 1:
+    if lib.drt_abi_version() != 2:
         raise ImportError("libdiffert_b200.so ABI version mismatch; rebuild the library")
     return lib
 

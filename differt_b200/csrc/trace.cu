@@ -920,9 +920,12 @@ __global__ void complete_graph_candidates_kernel(int64_t n, int order, int64_t s
     }
 }
 
+// Workspace of the trace entry points.  The first `prefix` bytes depend on the mesh only (geometry pack,
+// masked pack, area-sorted pack, the culled hierarchy, the sort scratch): drt_trace_prepare fills them
+// once and a call flagged DRT_TRACE_PREPARED finds them already in place.
 struct TraceWorkspace {
-    size_t pack_geom, pack_active, pack_sorted, pack_sorted2, hit_counts, sort_ws, sort_bytes, list, list2, list3, counters,
-        cull, total;
+    size_t pack_geom, pack_active, pack_sorted, cull, sort_ws, sort_bytes, prefix;
+    size_t pack_sorted2, pack_sorted3, hit_counts, list, list2, list3, counters, total;
     CullLayout cull_layout;
 };
 
@@ -938,13 +941,19 @@ inline TraceWorkspace trace_workspace_layout(int64_t T, int64_t P) {
     off += align256(pack);
     w.pack_sorted = off;  // blockage pack: active triangles in descending area order (pack_sort.cu)
     off += align256(pack);
-    w.pack_sorted2 = off;  // ... re-sorted by the hit counts of a sample of this batch
-    off += align256(pack);
-    w.hit_counts = off;
-    off += align256(pack / sizeof(Tri48) * sizeof(uint32_t));
+    w.cull = off;  // spatially ordered pack + its node levels (cull.cuh)
+    w.cull_layout = cull_layout(int64_t(pack / sizeof(Tri48)));
+    off += align256(w.cull_layout.total);
     w.sort_ws = off;
     w.sort_bytes = drt_mesh_pack_sort_workspace_bytes(T);
     off += align256(w.sort_bytes);
+    w.prefix = off;
+    w.pack_sorted2 = off;  // ordering pass: the pack re-sorted by the hit counts of a sample of this batch,
+    off += align256(pack);
+    w.pack_sorted3 = off;  // ... and its ping-pong partner during the greedy rounds
+    off += align256(pack);
+    w.hit_counts = off;
+    off += align256(pack / sizeof(Tri48) * sizeof(uint32_t));
     w.counters = off;
     off += 256;
     w.list = off;  // candidates that reach the blockage test (stage A → head pass)
@@ -953,11 +962,32 @@ inline TraceWorkspace trace_workspace_layout(int64_t T, int64_t P) {
     off += align256(size_t(P > 0 ? P : 1) * sizeof(uint32_t));
     w.list3 = off;
     off += align256(size_t(P > 0 ? P : 1) * sizeof(uint32_t));
-    w.cull = off;  // spatially ordered pack + its node levels (cull.cuh)
-    w.cull_layout = cull_layout(int64_t(pack / sizeof(Tri48)));
-    off += align256(w.cull_layout.total);
     w.total = off;
     return w;
+}
+
+// Mesh-only part of the trace: packs, area order, culled hierarchy → the prefix of `ws`.
+inline int trace_prepare_mesh(drt_stream_t stream, int64_t V, int64_t T, const float *vertices,
+                              const int32_t *triangles, const uint8_t *triangle_mask, unsigned char *ws,
+                              const TraceWorkspace &w) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Tri48 *pack_geom = reinterpret_cast<Tri48 *>(ws + w.pack_geom);
+    Tri48 *pack_active = reinterpret_cast<Tri48 *>(ws + w.pack_active);
+    int rc = drt_mesh_pack(stream, V, T, vertices, triangles, nullptr, pack_geom);
+    if (rc != DRT_OK) return rc;
+    rc = drt_mesh_pack(stream, V, T, vertices, triangles, triangle_mask, pack_active);  // null mask: a second copy
+    if (rc != DRT_OK) return rc;
+    if (T > 0) {
+        Tri48 *pack_sorted = reinterpret_cast<Tri48 *>(ws + w.pack_sorted);
+        rc = drt_mesh_pack_sort_by_area(stream, T, pack_active, ws + w.sort_ws, w.sort_bytes, pack_sorted);
+        if (rc != DRT_OK) return rc;
+        const int64_t records = int64_t(drt_mesh_pack_bytes(T) / sizeof(Tri48));
+        if (records > int64_t(kCullHead) * kTile) {
+            rc = cull_build(s, records, pack_sorted, ws + w.cull, w.cull_layout, ws + w.sort_ws, w.sort_bytes);
+            if (rc != DRT_OK) return rc;
+        }
+    }
+    return DRT_OK;
 }
 
 // per-thread profile ring (DRT_TRACE_PROFILE): event pairs around the blockage kernel
@@ -981,8 +1011,8 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
                  const Tri48 *pack_active, float hit_tol, int64_t *tests_done,
                  int64_t *units_scratch, uint32_t *list2, uint32_t *list3, int64_t *list2_count,
                  uint32_t *hit_counts,
-                 Tri48 *pack_sorted2, void *sort_ws, size_t sort_bytes, const unsigned char *cull_ws,
-                 const CullLayout &cull) {
+                 Tri48 *pack_sorted2, Tri48 *pack_sorted3, void *sort_ws, size_t sort_bytes,
+                 const unsigned char *cull_ws, const CullLayout &cull) {
     // candidates along x, receiver chunks along y (enough of them to fill the GPU), transmitters along z
     const int threads = 128;
     const int64_t cblocks = (a.C + threads - 1) / threads;
@@ -1062,7 +1092,7 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
             int rc = drt_mesh_pack_sort_by_keys(s, a.T, pack_active, hit_counts, sort_ws, sort_bytes, pack_sorted2);
             if (rc != DRT_OK) return rc;
             Tri48 *cur = pack_sorted2;
-            Tri48 *other = const_cast<Tri48 *>(pack_active);  // the area-sorted copy is no longer needed
+            Tri48 *other = pack_sorted3;  // (the area-sorted pack stays intact: it may belong to a prepared prefix)
 #if DRT_GREEDY_TILES > 0
             // Greedy refinement (set-cover heuristic): raw hit counts are redundant — the triangles
             // that block the most samples tend to block the SAME samples.  Tile by tile: keep the
@@ -1203,27 +1233,15 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
     if (workspace_bytes < w.total) return DRT_ERR_WORKSPACE;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     Tri48 *pack_geom = reinterpret_cast<Tri48 *>(ws + w.pack_geom);
-    Tri48 *pack_active = pack_geom;
-    int rc = drt_mesh_pack(stream, V, T, vertices, triangles, nullptr, pack_geom);
-    if (rc != DRT_OK) return rc;
-    if (triangle_mask != nullptr) {
-        pack_active = reinterpret_cast<Tri48 *>(ws + w.pack_active);
-        rc = drt_mesh_pack(stream, V, T, vertices, triangles, triangle_mask, pack_active);
+    int rc = DRT_OK;
+    if ((flags & DRT_TRACE_PREPARED) == 0) {
+        rc = trace_prepare_mesh(stream, V, T, vertices, triangles, triangle_mask, ws, w);
         if (rc != DRT_OK) return rc;
     }
-    if (T > 0) {
-        Tri48 *pack_sorted = reinterpret_cast<Tri48 *>(ws + w.pack_sorted);
-        rc = drt_mesh_pack_sort_by_area(stream, T, pack_active, ws + w.sort_ws, w.sort_bytes, pack_sorted);
-        if (rc != DRT_OK) return rc;
-        pack_active = pack_sorted;
-    }
+    const Tri48 *pack_active = reinterpret_cast<const Tri48 *>(ws + (T > 0 ? w.pack_sorted : w.pack_active));
     const unsigned char *cull_ws = nullptr;
-    if (order + 1 <= 6 && int64_t(drt_mesh_pack_bytes(T) / sizeof(Tri48)) > int64_t(kCullHead) * kTile) {
-        rc = cull_build(s, int64_t(drt_mesh_pack_bytes(T) / sizeof(Tri48)), pack_active, ws + w.cull, w.cull_layout,
-                        ws + w.sort_ws, w.sort_bytes);
-        if (rc != DRT_OK) return rc;
+    if (order + 1 <= 6 && int64_t(drt_mesh_pack_bytes(T) / sizeof(Tri48)) > int64_t(kCullHead) * kTile)
         cull_ws = ws + w.cull;
-    }
     int64_t *counters = reinterpret_cast<int64_t *>(ws + w.counters);
     if (cudaMemsetAsync(counters, 0, 256, s) != cudaSuccess) return DRT_ERR_CUDA;
     const bool dense = (flags & DRT_TRACE_DENSE_BLOCKAGE) != 0;
@@ -1257,7 +1275,8 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
         rc = trace_launch<K>(s, a, quads, dense, profile, pack_active, hit_tol, tests_done,        \
                              units_scratch, list2, list3, counters + 2,                           \
                              reinterpret_cast<uint32_t *>(ws + w.hit_counts),                      \
-                             reinterpret_cast<Tri48 *>(ws + w.pack_sorted2), ws + w.sort_ws,      \
+                             reinterpret_cast<Tri48 *>(ws + w.pack_sorted2),                      \
+                             reinterpret_cast<Tri48 *>(ws + w.pack_sorted3), ws + w.sort_ws,      \
                              w.sort_bytes, cull_ws, w.cull_layout);                               \
         break;
     switch (order) {
@@ -1274,6 +1293,20 @@ int drt_trace_path_candidates(drt_stream_t stream, int64_t V, int64_t T, const f
     return DRT_OK;
 }
 
+size_t drt_trace_prepared_bytes(int64_t T) {
+    if (T < 0) return 0;
+    return trace_workspace_layout(T, 0).prefix;
+}
+
+int drt_trace_prepare(drt_stream_t stream, int64_t V, int64_t T, const float *vertices, const int32_t *triangles,
+                      const uint8_t *triangle_mask, void *prepared, size_t prepared_bytes) {
+    if (V < 0 || T < 0) return DRT_ERR_BAD_EXTENT;
+    if (!prepared) return DRT_ERR_NULL_POINTER;
+    const TraceWorkspace w = trace_workspace_layout(T, 0);
+    if (prepared_bytes < w.prefix) return DRT_ERR_WORKSPACE;
+    return trace_prepare_mesh(stream, V, T, vertices, triangles, triangle_mask, static_cast<unsigned char *>(prepared), w);
+}
+
 size_t drt_trace_valid_workspace_bytes(int64_t T, int64_t capacity) {
     if (T < 0 || capacity < 0) return 0;
     return trace_workspace_layout(T, capacity).total;
@@ -1283,8 +1316,8 @@ int drt_trace_valid_path_candidates(drt_stream_t stream, int64_t V, int64_t T, c
                                     const int32_t *triangles, const uint8_t *triangle_mask,
                                     int32_t assume_quads, int64_t ntx, const float *tx, int64_t nrx,
                                     const float *rx, int64_t C, int32_t order, const int32_t *cand,
-                                    float epsilon, float hit_tol, float min_len, int64_t capacity,
-                                    void *workspace, size_t workspace_bytes, int64_t *out_count,
+                                    float epsilon, float hit_tol, float min_len, uint32_t flags,
+                                    int64_t capacity, void *workspace, size_t workspace_bytes, int64_t *out_count,
                                     int64_t *out_index, float *out_vertices, int32_t *out_objects,
                                     uint8_t *out_valid) {
     if (V < 0 || T < 0 || ntx < 0 || nrx < 0 || C < 0 || order < 0 || capacity <= 0) return DRT_ERR_BAD_EXTENT;
@@ -1303,28 +1336,15 @@ int drt_trace_valid_path_candidates(drt_stream_t stream, int64_t V, int64_t T, c
     if (workspace_bytes < w.total) return DRT_ERR_WORKSPACE;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     Tri48 *pack_geom = reinterpret_cast<Tri48 *>(ws + w.pack_geom);
-    const Tri48 *pack_active = pack_geom;
-    int rc = drt_mesh_pack(stream, V, T, vertices, triangles, nullptr, pack_geom);
-    if (rc != DRT_OK) return rc;
-    if (triangle_mask != nullptr) {
-        Tri48 *pm = reinterpret_cast<Tri48 *>(ws + w.pack_active);
-        rc = drt_mesh_pack(stream, V, T, vertices, triangles, triangle_mask, pm);
+    int rc = DRT_OK;
+    if ((flags & DRT_TRACE_PREPARED) == 0) {
+        rc = trace_prepare_mesh(stream, V, T, vertices, triangles, triangle_mask, ws, w);
         if (rc != DRT_OK) return rc;
-        pack_active = pm;
     }
-    if (T > 0) {
-        Tri48 *pack_sorted = reinterpret_cast<Tri48 *>(ws + w.pack_sorted);
-        rc = drt_mesh_pack_sort_by_area(stream, T, pack_active, ws + w.sort_ws, w.sort_bytes, pack_sorted);
-        if (rc != DRT_OK) return rc;
-        pack_active = pack_sorted;
-    }
+    const Tri48 *pack_active = reinterpret_cast<const Tri48 *>(ws + (T > 0 ? w.pack_sorted : w.pack_active));
     const unsigned char *cull_ws = nullptr;
-    if (int64_t(drt_mesh_pack_bytes(T) / sizeof(Tri48)) > int64_t(kCullHead) * kTile) {
-        rc = cull_build(s, int64_t(drt_mesh_pack_bytes(T) / sizeof(Tri48)), pack_active, ws + w.cull, w.cull_layout,
-                        ws + w.sort_ws, w.sort_bytes);
-        if (rc != DRT_OK) return rc;
+    if (int64_t(drt_mesh_pack_bytes(T) / sizeof(Tri48)) > int64_t(kCullHead) * kTile)
         cull_ws = ws + w.cull;
-    }
     int64_t *counters = reinterpret_cast<int64_t *>(ws + w.counters);
     if (cudaMemsetAsync(counters, 0, 256, s) != cudaSuccess) return DRT_ERR_CUDA;
     TraceArgs a{};
@@ -1354,7 +1374,8 @@ int drt_trace_valid_path_candidates(drt_stream_t stream, int64_t V, int64_t T, c
                              reinterpret_cast<uint32_t *>(ws + w.list2),                                 \
                              reinterpret_cast<uint32_t *>(ws + w.list3), counters + 2,                   \
                              reinterpret_cast<uint32_t *>(ws + w.hit_counts),                            \
-                             reinterpret_cast<Tri48 *>(ws + w.pack_sorted2), ws + w.sort_ws,            \
+                             reinterpret_cast<Tri48 *>(ws + w.pack_sorted2),                            \
+                             reinterpret_cast<Tri48 *>(ws + w.pack_sorted3), ws + w.sort_ws,            \
                              w.sort_bytes, cull_ws, w.cull_layout);                                     \
         break;
     switch (order) {

@@ -97,6 +97,26 @@ class Mesh:
     def _mask_u8(self) -> torch.Tensor | None:
         return None if self.mask is None else self.mask.to(torch.uint8)
 
+    def _trace_prepared(self) -> torch.Tensor:
+        """The mesh-only part of the trace (packed mesh, area order, culled hierarchy:
+        ``drt_trace_prepare``), built once per mesh STATE and copied to the front of every trace
+        call's workspace.  The key is the storage and version counter of ``vertices`` / ``triangles`` /
+        ``mask`` — an in-place update (an optimizer step) bumps the version and the next call rebuilds,
+        so the bytes can never describe another mesh (the staleness the reference's process-global
+        ``_WARP_MESHES_CACHE`` has, ``_mesh.py:48-55``).  The library itself keeps no state."""
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) if t is not None else None
+                    for t in (self.vertices, self.triangles, self.mask))
+        cached = self.__dict__.get("_prepared_cache")
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        T = self.num_triangles
+        blob = torch.empty(max(lib.drt_trace_prepared_bytes(T), 1), dtype=torch.uint8, device=self.vertices.device)
+        mask_u8 = self._mask_u8()
+        check(lib.drt_trace_prepare(stream_ptr(), self.vertices.shape[0], T, ptr(self.vertices.detach()),
+                                    ptr(self.triangles), ptr(mask_u8), ptr(blob), blob.numel()))
+        self.__dict__["_prepared_cache"] = (key, blob)
+        return blob
+
     def build_bvh(self, relative_pad: float = 1e-4) -> torch.Tensor:
         """Linear BVH over the (masked) triangles for the opt-in ``accel="bvh"`` queries
         (``drt_bvh_build``): a caller-owned blob, rebuilt in ~0.1 ms — nothing is cached, so it can

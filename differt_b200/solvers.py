@@ -173,6 +173,9 @@ def trace_path_candidates(
     stats = torch.zeros(4, dtype=torch.int64, device=dev) if want_stats else None
     flags = (_lib.DRT_TRACE_DENSE_BLOCKAGE if dense_blockage else 0) | (_lib.DRT_TRACE_PROFILE if _profile else 0)
     ws = torch.empty(max(lib.drt_trace_workspace_bytes(T, ntx, nrx, C), 1), dtype=torch.uint8, device=dev)
+    prepared = mesh._trace_prepared()  # mesh-only work, cached per mesh state: one D2D copy per call
+    ws[:prepared.numel()].copy_(prepared)
+    flags |= _lib.DRT_TRACE_PREPARED
     mask_u8 = mesh._mask_u8()  # named: must outlive the call
     check(
         lib.drt_trace_path_candidates(
@@ -226,6 +229,7 @@ def trace_valid_path_candidates(
         raise NotImplementedError("the compact trace supports orders up to 5; use trace_path_candidates")
     T = mesh.num_triangles
     mask_u8 = mesh._mask_u8()
+    prepared = mesh._trace_prepared()
     while True:
         out_i = torch.empty(capacity, dtype=torch.int64, device=dev)
         out_v = torch.empty((capacity, k + 2, 3), dtype=torch.float32, device=dev)
@@ -233,6 +237,7 @@ def trace_valid_path_candidates(
         out_ok = torch.empty(capacity, dtype=torch.uint8, device=dev)
         count = torch.zeros(1, dtype=torch.int64, device=dev)
         ws = torch.empty(max(lib.drt_trace_valid_workspace_bytes(T, capacity), 1), dtype=torch.uint8, device=dev)
+        ws[:prepared.numel()].copy_(prepared)
         check(
             lib.drt_trace_valid_path_candidates(
                 stream_ptr(), mesh.vertices.shape[0], T, ptr(mesh.vertices.detach()), ptr(mesh.triangles),
@@ -240,7 +245,8 @@ def trace_valid_path_candidates(
                 10.0 * F32_EPS if epsilon is None else float(epsilon),
                 100.0 * F32_EPS if hit_tol is None else float(hit_tol),
                 10.0 * F32_EPS if min_len is None else float(min_len),
-                capacity, ptr(ws), ws.numel(), ptr(count), ptr(out_i), ptr(out_v), ptr(out_o), ptr(out_ok),
+                _lib.DRT_TRACE_PREPARED, capacity, ptr(ws), ws.numel(), ptr(count), ptr(out_i), ptr(out_v), ptr(out_o),
+                ptr(out_ok),
             )
         )
         n = int(count.item())  # the one host read

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define DRT_ABI_VERSION 1
+#define DRT_ABI_VERSION 2
 
 #define DRT_OK 0
 #define DRT_ERR_NULL_POINTER (-1)     /* a required pointer is NULL */
@@ -50,6 +50,9 @@ extern "C" {
                                          reference does; default (0) skips candidates that already
                                          failed a cheaper test — same outputs, less work */
 
+#define DRT_TRACE_PREPARED 4u         /* the first drt_trace_prepared_bytes(T) bytes of `workspace` already hold
+                                         what drt_trace_prepare wrote for THIS mesh and mask (the caller
+                                         copied them there): skip the mesh-only work of the call */
 #define DRT_TRACE_PROFILE 2u          /* record a CUDA-event pair around the blockage (all-pairs)
                                          kernel of this call into the calling thread's profile
                                          ring (drt_profile_*); measurement hook for bench.py */
@@ -204,6 +207,15 @@ DRT_API int drt_consecutive_vertices_are_on_same_side_of_mirror(
  * ------------------------------------------------------------------------------------------- */
 DRT_API size_t drt_trace_workspace_bytes(int64_t num_triangles, int64_t num_tx, int64_t num_rx,
                                  int64_t num_candidates);
+/* The mesh-only part of K6 / K6c (packed mesh, area order, the culled hierarchy of csrc/cull.cuh),
+ * hoisted for callers that trace many batches against one mesh (chunked searches, per-rank shards,
+ * training steps between two mesh updates): drt_trace_prepare writes it into caller-owned memory;
+ * a later call copies those bytes to the start of its workspace and passes DRT_TRACE_PREPARED.
+ * The library still keeps no state — the caller owns the bytes and knows when its mesh changed. */
+DRT_API size_t drt_trace_prepared_bytes(int64_t num_triangles);
+DRT_API int drt_trace_prepare(drt_stream_t stream, int64_t num_vertices, int64_t num_triangles,
+                      const float *vertices, const int32_t *triangles,
+                      const uint8_t *triangle_mask /*nullable*/, void *prepared, size_t prepared_bytes);
 DRT_API int drt_trace_path_candidates(drt_stream_t stream, int64_t num_vertices, int64_t num_triangles,
                               const float *vertices, const int32_t *triangles,
                               const uint8_t *triangle_mask /*nullable*/, int32_t assume_quads,
@@ -227,7 +239,7 @@ DRT_API int drt_trace_valid_path_candidates(drt_stream_t stream, int64_t num_ver
                                     int64_t num_tx, const float *tx, int64_t num_rx, const float *rx,
                                     int64_t num_candidates, int32_t order,
                                     const int32_t *path_candidates, float epsilon, float hit_tol,
-                                    float min_len, int64_t capacity, void *workspace,
+                                    float min_len, uint32_t flags, int64_t capacity, void *workspace,
                                     size_t workspace_bytes, int64_t *out_count, int64_t *out_index,
                                     float *out_vertices, int32_t *out_objects, uint8_t *out_valid);
 DRT_API int drt_trace_path_candidates_vjp(drt_stream_t stream, int64_t num_vertices, int64_t num_triangles,

@@ -207,7 +207,7 @@ static ffi::Error TraceValidImpl(cudaStream_t stream, ffi::ScratchAllocator scra
         stream, V, T, vertices.typed_data(), triangles.typed_data(), m, assume_quads ? 1 : 0,
         tx.dimensions()[0], tx.typed_data(), rx.dimensions()[0], rx.typed_data(), candidates.dimensions()[0],
         static_cast<int32_t>(candidates.dimensions()[1]), candidates.typed_data(), epsilon, hit_tol, min_len,
-        capacity, *ws, ws_bytes, out_count->typed_data(), out_index->typed_data(), out_vertices->typed_data(),
+        /*flags=*/0u, capacity, *ws, ws_bytes, out_count->typed_data(), out_index->typed_data(), out_vertices->typed_data(),
         out_objects->typed_data(), reinterpret_cast<uint8_t *>(out_valid->typed_data())));
 }
 

@@ -58,7 +58,7 @@ def test_python_prototypes_cover_the_header(lib):
 
 def test_host_only_helpers(lib):
     L = lib.lib
-    assert L.drt_abi_version() == 1
+    assert L.drt_abi_version() == 2
     assert L.drt_error_string(0) == b"ok"
     assert b"NULL" in L.drt_error_string(-1)
     # 48 bytes per triangle, padded to 512-triangle tiles, at least one tile

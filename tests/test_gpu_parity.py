@@ -1219,6 +1219,36 @@ def test_cull_parameter_ranges(drt, rng, hit_tol, epsilon):
     assert st["blocked"].any() and (~st["blocked"]).any()
 
 
+def test_prepared_mesh_cache_follows_in_place_updates(drt, rng):
+    """The mesh-only part of the trace is cached per mesh STATE (storage + version counter): an
+    in-place update of the vertices (what an optimizer step does) or of the mask must be seen by the
+    next call, and a cached call must equal an uncached one."""
+    v, t = scenes.urban_grid(16, 16)  # 3074 triangles: takes the culled traversal
+    tx = np.array([[230.0, 230.0, 45.0]], np.float32)
+    rx = scenes.receivers_grid(v, 6, 6)
+    cand = scenes.sampled_candidates(t.shape[0], 1, 2000)
+    mask = rng.uniform(size=t.shape[0]) < 0.8
+    mesh = drt.Mesh.from_numpy(v, t, mask=mask)
+    for step in range(3):
+        vv = mesh.vertices.cpu().numpy()
+        mm = mesh.mask.cpu().numpy()
+        ev, eo, em = co.trace_path_candidates(vv, t, tx, rx, cand, mask=mm, early_exit=True)
+        for dense in (True, False, True):  # the second and third calls hit the cache
+            got = drt.trace_path_candidates(mesh, tx, rx, cand, dense_blockage=dense)
+            np.testing.assert_array_equal(got.mask.cpu().numpy(), em)
+            np.testing.assert_array_equal(bits(got.vertices.cpu().numpy()), bits(ev))
+        comp = drt.trace_valid_path_candidates(mesh, tx, rx, cand)
+        np.testing.assert_array_equal(comp.index.cpu().numpy(), np.flatnonzero(em.reshape(-1)))
+        assert em.any() and not em.all()
+        if step == 0:  # raise every other building by 15 m, in place
+            with torch.no_grad():
+                sel = (mesh.vertices[:, 2] > 0) & ((mesh.vertices[:, 0] // 30).long() % 2 == 0)
+                mesh.vertices[sel, 2] += 15.0
+        else:          # flip a third of the mask, in place
+            flip = torch.from_numpy(rng.uniform(size=t.shape[0]) < 0.33).to(mesh.mask.device)
+            mesh.mask ^= flip
+
+
 @pytest.mark.parametrize("solver", ["exhaustive", "hybrid"])
 def test_chunked_trace_equals_one_shot_masked(drt, two_buildings, kats, solver):
     """Scene.trace_paths(chunk_size=...) semantics (_scene.py:738-751) and the merged valid paths:

@@ -19,7 +19,7 @@ import json
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-BLOCKAGE = ("path_head_kernel", "path_cull_kernel", "hit_count_kernel", "path_bvh_kernel", "intersect_kernel")
+BLOCKAGE = ("path_head_kernel", "path_walk_kernel", "hit_count_kernel", "intersect_kernel")
 
 
 def main() -> None:
