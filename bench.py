@@ -530,9 +530,28 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     barrier()
     stats_acc.zero_()
     _lib.check(_lib.lib.drt_profile_reset())
+    paths = None  # timed() binds its own results: with this one still alive a THIRD generation of the 1.4 GB
+    #               outputs would be allocated (cudaMalloc, a 0.25 s host stall) inside the timed region
     if sampler:
         sampler.mark_start()
-    ms, paths = timed(lambda i: step_resident(i < 64), args.steps)
+    diag = os.environ.get("DRT_BENCH_DIAG")
+    if diag:
+        s0 = torch.cuda.memory_stats()
+        host_ms = []
+
+        def probe(i):
+            h0 = time.perf_counter()
+            r = step_resident(i < 64)
+            host_ms.append(1e3 * (time.perf_counter() - h0))
+            return r
+
+        ms, paths = timed(probe, args.steps)
+        s1 = torch.cuda.memory_stats()
+        sys.stderr.write(f"[diag] ms/step {ms / args.steps:.3f} host enqueue ms {host_ms} cudaMalloc "
+                         f"{s1['num_device_alloc'] - s0['num_device_alloc']} cudaFree "
+                         f"{s1['num_device_free'] - s0['num_device_free']}\n")
+    else:
+        ms, paths = timed(lambda i: step_resident(i < 64), args.steps)
     clocks = sampler.stop() if sampler else None
     tests_local = int(stats_acc[0].item())
     valid_local = int(paths.mask.sum().item())
