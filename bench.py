@@ -431,8 +431,13 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     host = {n: torch.from_numpy(wl[n]).pin_memory() for n in ("vertices", "triangles", "tx", "rx", "cand")}
     mesh = drt.Mesh.from_numpy(wl["vertices"], wl["triangles"])
     tx_d, rx_d, cand_d = (host[n].to(dev) for n in ("tx", "rx", "cand"))
-    record = GatherRecord(capacity, k, dev)
-    gathered = torch.empty(world * record.nbytes, dtype=torch.uint8, device=dev)  # preallocated receive buffer
+    # two records / receive buffers (preallocated): the all-gather of step i runs on NCCL's own stream
+    # while step i + 1 computes, and is only waited for when its buffers are about to be reused
+    records = [GatherRecord(capacity, k, dev) for _ in range(2)]
+    record = records[0]
+    gathered_bufs = [torch.empty(world * record.nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    in_flight: list = [None, None]
+    step_no = [0]
     stats_acc = torch.zeros(4, dtype=torch.int64, device=dev)
 
     # reverse mode every step (BASELINE config 3 is "with VJP"; SURVEY §8d: VJP of vertices.sum() w.r.t.
@@ -450,10 +455,20 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         )
         if with_vjp:
             torch.autograd.grad(paths.vertices, (mesh.vertices, tx_d, rx_d), cot)
-        fill_record(record, paths, wl["cand_global"], wl["cand_start"])
+        slot = step_no[0] & 1
+        step_no[0] += 1
+        if in_flight[slot] is not None:  # the gather that used these buffers two steps ago
+            in_flight[slot].wait()
+        fill_record(records[slot], paths, wl["cand_global"], wl["cand_start"])
         if world > 1:
-            dist.all_gather_into_tensor(gathered, record.buffer)
+            in_flight[slot] = dist.all_gather_into_tensor(gathered_bufs[slot], records[slot].buffer, async_op=True)
         return paths
+
+    def drain():
+        """Every gather issued so far has completed on the current stream."""
+        for w_ in in_flight:
+            if w_ is not None:
+                w_.wait()
 
     mask_host = torch.empty((tx_d.shape[0], rx_d.shape[0], cand_d.shape[0]), dtype=torch.bool, pin_memory=True)
     grad_host: list = []
@@ -470,7 +485,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         grads = ()
         if with_vjp:
             grads = torch.autograd.grad(paths.vertices, (m.vertices, tx_e, rx_e), cot)
-        fill_record(record, paths, wl["cand_global"], wl["cand_start"])
+        fill_record(records[0], paths, wl["cand_global"], wl["cand_start"])
         # device → host: the mask and the gradients into pinned buffers (asynchronous), then the gather,
         # whose count read is the synchronisation point
         mask_host.copy_(paths.mask, non_blocking=True)
@@ -480,7 +495,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                 grad_host.append(torch.empty(g.shape, dtype=g.dtype, pin_memory=True))
             grad_host[i].copy_(g, non_blocking=True)
             grads_h.append(grad_host[i])
-        valid = gather_valid_paths(record)  # all-gather (N>1) + counts to host
+        valid = gather_valid_paths(records[0])  # all-gather (N>1) + counts to host
         assert valid is not None, "gather record overflow: raise `capacity` in bench.py"
         out = (valid.index.cpu(), valid.vertices.cpu(), valid.objects.cpu(), mask_host, *grads_h)
         torch.cuda.current_stream().synchronize()
@@ -498,6 +513,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         r = None
         for i in range(n):
             r = fn(i)
+        drain()  # the last gathers are part of the work
         e1.record()
         barrier()
         return e0.elapsed_time(e1), r
@@ -566,6 +582,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     # ---- parity: the last timed step against the oracle; the gathered records against the ranks' masks --
     parity = parity_check(wl, paths) if rank == 0 and not args.no_cpu else None
     torch.cuda.synchronize()
+    last = (step_no[0] - 1) & 1
+    gathered, record = gathered_bufs[last], records[last]
     parts = [GatherRecord.views(gathered[r * record.nbytes:(r + 1) * record.nbytes], capacity, k) for r in range(world)] \
         if world > 1 else [record.fields()]
     counts = [int(p_[0].item()) for p_ in parts]
@@ -618,8 +636,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             p_ = drt.trace_path_candidates(mesh, tx_d, rx_d, cand_w, dense_blockage=True)
             if with_vjp:
                 torch.autograd.grad(p_.vertices, (mesh.vertices, tx_d, rx_d), cot_w)
-            fill_record(record, p_, wlw["cand_global"], wlw["cand_start"])
-            dist.all_gather_into_tensor(gathered, record.buffer)
+            fill_record(records[0], p_, wlw["cand_global"], wlw["cand_start"])
+            dist.all_gather_into_tensor(gathered_bufs[0], records[0].buffer)
             return p_
 
         keep = [step_weak(0), step_weak(1)]
@@ -628,12 +646,13 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         weak = ms_weak
 
     # ---- reduce over ranks: max time, summed work ----------------------------------------------------
-    red = torch.tensor([ms, ms_e2e, ms_sus or 0.0, weak or 0.0], dtype=torch.float64, device=dev)
+    kms_local = float(np.mean(kern_ms)) if kern_ms else 0.0
+    red = torch.tensor([ms, ms_e2e, ms_sus or 0.0, weak or 0.0, kms_local, -kms_local], dtype=torch.float64, device=dev)
     tot = torch.tensor([tests_local, tests_e2e_local, valid_local, int(gather_ok)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms, ms_e2e, ms_sus, ms_weak = red.tolist()
+    ms, ms_e2e, ms_sus, ms_weak, kms_max, kms_min_neg = red.tolist()
     tests, tests_e2e, valid_total, gather_ok_ranks = tot.tolist()
 
     if rank == 0:
@@ -668,6 +687,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             "warp_instructions_per_executed_test": (inst["blockage_warp_instructions_per_step"] * 32 / tests_per_launch
                                                      if inst and tests_per_launch else None),
             "kernel_ms": kms, "kernel_share_of_step": kms * args.steps / ms if kms else None,
+            "kernel_ms_over_ranks": {"max": kms_max, "min": -kms_min_neg,
+                                     "note": "blockage kernel time of the slowest / fastest rank: the shards hold "
+                                             "different candidates, the step ends with the slowest"},
             "executed_tests_per_launch": tests_per_launch,
             "hbm_model": {
                 "note": "INAPPLICABLE as a roofline (kept because BASELINE.json asks for %HBM): 36 B of triangle "
