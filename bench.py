@@ -76,17 +76,13 @@ def load_scenes():
     return _SCENES
 
 
-def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
-    """Same contiguous split as differt_b200.distributed.shard_bounds (restated: see load_scenes)."""
-    base, extra = divmod(int(n), world)
-    start = rank * base + min(rank, extra)
-    return start, start + base + (1 if rank < extra else 0)
-
-
 def build_workload(name: str, rank: int, world: int, *, weak: bool = False):
-    """Seeded synthetic inputs (host, NumPy).  The workload is FIXED (strong scaling): its `cand`
-    candidates are split into `world` contiguous shards and rank r traces shard r.  `weak=True` gives
-    every rank `cand` candidates of its own instead (the extra weak-scaling leg)."""
+    """Seeded synthetic inputs (host, NumPy).  The workload is FIXED (strong scaling): its receivers
+    are dealt round-robin to the ranks (differt_b200.distributed.receiver_shard) and rank r traces
+    receivers r, r + world, ... against EVERY candidate — every shard then costs the same to within a
+    percent, which contiguous shards of a few hundred candidates do not.  `weak=True`
+    gives every rank the full receiver set and `cand` candidates of its own instead (the extra
+    weak-scaling leg)."""
     scenes = load_scenes()
 
     w = WORKLOADS[name]
@@ -114,11 +110,15 @@ def build_workload(name: str, rank: int, world: int, *, weak: bool = False):
         n = min(known.shape[0], total // 4)
         slots = (np.arange(n) * (total // max(n, 1))).astype(np.int64)
         cand_all[slots] = known[:n]
-    start, stop = (rank * w["cand"], (rank + 1) * w["cand"]) if weak else shard_bounds(total, world, rank)
-    cand = np.ascontiguousarray(cand_all[start:stop])
+    if weak:
+        start, stop = rank * w["cand"], (rank + 1) * w["cand"]
+        return dict(name=name, vertices=v, triangles=t, tx=tx, rx=rx, order=w["order"],
+                    cand=np.ascontiguousarray(cand_all[start:stop]), cand_global=total, cand_start=start,
+                    rx_global=int(rx.shape[0]), receivers=None)
     return dict(
-        name=name, vertices=v, triangles=t, tx=tx, rx=rx, order=w["order"], cand=cand,
-        cand_global=total, cand_start=start,
+        name=name, vertices=v, triangles=t, tx=tx, rx=np.ascontiguousarray(rx[rank::world]), order=w["order"],
+        cand=cand_all, cand_global=total, cand_start=0, rx_global=int(rx.shape[0]),
+        receivers=(int(rx.shape[0]), rank, world),
     )
 
 
@@ -348,17 +348,18 @@ def launches_per_step(wl: dict, with_vjp: bool) -> int:
 
 def workload_config(wl: dict, world: int, **extra) -> dict:
     T = int(wl["triangles"].shape[0])
-    pairs = int(wl["tx"].shape[0] * wl["rx"].shape[0] * wl["cand_global"])
+    pairs = int(wl["tx"].shape[0] * wl["rx_global"] * wl["cand_global"])
     cfg = {
         "workload": wl["name"], "triangles": T, "num_tx": int(wl["tx"].shape[0]),
-        "num_rx": int(wl["rx"].shape[0]), "order": int(wl["order"]),
+        "num_rx": int(wl["rx_global"]), "order": int(wl["order"]),
         "candidates": int(wl["cand_global"]), "candidate_pairs": pairs,
         "algorithmic_tests_per_step": pairs * (wl["order"] + 1) * T,
         "blockage": "dense: every segment of every candidate is decided by the any-hit test, like the "
                     "reference; value counts rays x triangles decided, executed_tests_per_s the "
                     "Moller-Trumbore evaluations actually run (a candidate stops at its first blocker; "
                     "pairs the exact cull proves to be misses are skipped)",
-        "parallelism": f"the workload's candidates in {world} contiguous shards, one all-gather of valid paths",
+        "parallelism": f"the workload's receivers dealt round-robin to {world} rank(s), every candidate on every "
+                       "rank, one all-gather of valid paths",
         "l2_policy": "no flush: each step writes >1.3 GB of path vertices/objects (L2 is 126 MB); "
                      "the 0.5 MB packed mesh is L2/shared-memory resident by design",
     }
@@ -459,7 +460,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         step_no[0] += 1
         if in_flight[slot] is not None:  # the gather that used these buffers two steps ago
             in_flight[slot].wait()
-        fill_record(records[slot], paths, wl["cand_global"], wl["cand_start"])
+        fill_record(records[slot], paths, wl["cand_global"], wl["cand_start"], receivers=wl["receivers"])
         if world > 1:
             in_flight[slot] = dist.all_gather_into_tensor(gathered_bufs[slot], records[slot].buffer, async_op=True)
         return paths
@@ -485,7 +486,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         grads = ()
         if with_vjp:
             grads = torch.autograd.grad(paths.vertices, (m.vertices, tx_e, rx_e), cot)
-        fill_record(records[0], paths, wl["cand_global"], wl["cand_start"])
+        fill_record(records[0], paths, wl["cand_global"], wl["cand_start"], receivers=wl["receivers"])
         # device → host: the mask and the gradients into pinned buffers (asynchronous), then the gather,
         # whose count read is the synchronisation point
         mask_host.copy_(paths.mask, non_blocking=True)
@@ -590,9 +591,10 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     gather_ok = counts[rank] == valid_local and all(c <= capacity for c in counts)
     if gather_ok and valid_local > 0:  # this rank's own record inside the gathered buffer: right paths, right bits
         mine = parts[rank]
+        from differt_b200.distributed import global_path_index_receivers
+
         idx_local = paths.mask.reshape(-1).nonzero().squeeze(-1)
-        pair = torch.div(idx_local, cand_d.shape[0], rounding_mode="floor")
-        idx_global = pair * wl["cand_global"] + (idx_local - pair * cand_d.shape[0]) + wl["cand_start"]
+        idx_global = global_path_index_receivers(idx_local, cand_d.shape[0], rx_d.shape[0], wl["rx_global"], rank, world)
         gather_ok = bool(torch.equal(mine[1][:valid_local], idx_global)) and bool(
             torch.equal(mine[2][:valid_local], paths.vertices.detach().reshape(-1, k + 2, 3)[idx_local]))
     del paths
@@ -629,13 +631,14 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     if world > 1 and args.weak_steps > 0:
         wlw = build_workload(args.workload, rank, world, weak=True)
         cand_w = torch.from_numpy(wlw["cand"]).to(dev)
-        cot_w = torch.ones((tx_d.shape[0], rx_d.shape[0], cand_w.shape[0], k + 2, 3), dtype=torch.float32, device=dev) \
+        rx_w = torch.from_numpy(wlw["rx"]).to(dev).requires_grad_(with_vjp)  # ALL receivers on every rank
+        cot_w = torch.ones((tx_d.shape[0], rx_w.shape[0], cand_w.shape[0], k + 2, 3), dtype=torch.float32, device=dev) \
             if with_vjp else None
 
         def step_weak(_i):
-            p_ = drt.trace_path_candidates(mesh, tx_d, rx_d, cand_w, dense_blockage=True)
+            p_ = drt.trace_path_candidates(mesh, tx_d, rx_w, cand_w, dense_blockage=True)
             if with_vjp:
-                torch.autograd.grad(p_.vertices, (mesh.vertices, tx_d, rx_d), cot_w)
+                torch.autograd.grad(p_.vertices, (mesh.vertices, tx_d, rx_w), cot_w)
             fill_record(records[0], p_, wlw["cand_global"], wlw["cand_start"])
             dist.all_gather_into_tensor(gathered_bufs[0], records[0].buffer)
             return p_
@@ -723,6 +726,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                              "ms_per_step": ms_pruned,
                              "candidate_pairs_per_s": wl["tx"].shape[0] * wl["rx"].shape[0] * wl["cand"].shape[0]
                              / (ms_pruned * 1e-3)},
+            "shard": {"receivers_per_rank": int(wl["rx"].shape[0]), "candidates_per_rank": int(wl["cand"].shape[0])},
             "e2e": {"value": algo_step * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "executed_tests_per_s": tests_e2e / (ms_e2e * 1e-3), "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,

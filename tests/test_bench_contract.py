@@ -57,7 +57,16 @@ def test_workload_is_deterministic_and_sharded_per_rank():
     a = bench.build_workload("urban10k_small", 0, 2)
     b = bench.build_workload("urban10k_small", 1, 2)
     a2 = bench.build_workload("urban10k_small", 0, 2)
+    one = bench.build_workload("urban10k_small", 0, 1)
     np.testing.assert_array_equal(a["cand"], a2["cand"])
-    assert a["cand_start"] == 0 and b["cand_start"] == a["cand"].shape[0] and a["cand_global"] == 2 * a["cand"].shape[0]
-    assert not np.array_equal(a["cand"], b["cand"])
+    # strong scaling: ONE fixed problem, its receivers dealt round-robin, every candidate on every rank
+    np.testing.assert_array_equal(a["cand"], b["cand"])
+    np.testing.assert_array_equal(a["cand"], one["cand"])
+    np.testing.assert_array_equal(a["rx"], one["rx"][0::2])
+    np.testing.assert_array_equal(b["rx"], one["rx"][1::2])
+    assert a["rx_global"] == one["rx"].shape[0] and a["receivers"] == (one["rx"].shape[0], 0, 2)
     assert (a["cand"][:, 1:] != a["cand"][:, :-1]).all()
+    # the weak-scaling leg: every rank its own candidates, all receivers
+    wa, wb = bench.build_workload("urban10k_small", 0, 2, weak=True), bench.build_workload("urban10k_small", 1, 2, weak=True)
+    assert wa["cand_start"] == 0 and wb["cand_start"] == wa["cand"].shape[0] and wa["cand_global"] == 2 * wa["cand"].shape[0]
+    assert not np.array_equal(wa["cand"], wb["cand"]) and wa["rx"].shape == one["rx"].shape

@@ -121,6 +121,23 @@ def test_global_path_index_roundtrip():
     np.testing.assert_array_equal(g.numpy(), pair * C + c + start)
 
 
+def test_receiver_sharding_index_roundtrip():
+    from differt_b200.distributed import global_path_index_receivers, receiver_shard
+
+    ntx, nrx, C = 3, 11, 5
+    full = np.arange(ntx * nrx * C).reshape(ntx, nrx, C)
+    seen = []
+    for world in (1, 2, 4):
+        seen.clear()
+        for rank in range(world):
+            mine = receiver_shard(nrx, world, rank).numpy()
+            local = torch.arange(ntx * len(mine) * C)
+            g = global_path_index_receivers(local, C, len(mine), nrx, rank, world).numpy()
+            np.testing.assert_array_equal(g, full[:, mine, :].reshape(-1))
+            seen.append(g)
+        np.testing.assert_array_equal(np.sort(np.concatenate(seen)), full.reshape(-1))  # a partition
+
+
 def test_record_layout_is_aligned_and_disjoint():
     from differt_b200.distributed import GatherRecord
 

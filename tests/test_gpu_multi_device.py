@@ -108,6 +108,10 @@ def _nccl_worker(rank: int, world: int, port: int, out_dir: str) -> None:
             out[f"vertices{capacity}"] = valid.vertices.cpu().numpy()
             out[f"objects{capacity}"] = valid.objects.cpu().numpy()
             out[f"counts{capacity}"] = np.array(valid.counts)
+        _, valid = trace_path_candidates_sharded(mesh, tx, rx, cand, shard="receivers", dense_blockage=True)
+        out["rx_index"] = valid.index.cpu().numpy()
+        out["rx_vertices"] = valid.vertices.cpu().numpy()
+        out["rx_objects"] = valid.objects.cpu().numpy()
         single = drt.trace_path_candidates(mesh, tx, rx, cand).masked()  # this rank alone, all candidates
         out["single_vertices"] = single.vertices.cpu().numpy()
         out["single_objects"] = single.objects.cpu().numpy()
@@ -143,5 +147,8 @@ def test_nccl_world_size_two_sharded_trace_equals_single_gpu_and_oracle(tmp_path
             assert int(got[f"counts{capacity}"].sum()) == exp.size and got[f"counts{capacity}"].size == world
         np.testing.assert_array_equal(got["single_vertices"].view(np.uint32), got["vertices4096"].view(np.uint32))
         np.testing.assert_array_equal(got["single_objects"], got["objects4096"])
+        np.testing.assert_array_equal(got["rx_index"], exp)  # receivers dealt round-robin: same merged list
+        np.testing.assert_array_equal(got["rx_vertices"].view(np.uint32), got["vertices4096"].view(np.uint32))
+        np.testing.assert_array_equal(got["rx_objects"], got["objects4096"])
         np.testing.assert_array_equal(got["search_index"], exp)
         np.testing.assert_array_equal(got["search_vertices"].view(np.uint32), got["vertices4096"].view(np.uint32))
