@@ -61,6 +61,7 @@ DEFAULT_WORKLOAD = "urban10k_1tx_4096rx_order3"
 
 
 _SCENES = None
+RX_BLOCK = int(os.environ.get("DRT_RX_BLOCK", "16"))  # = differt_b200.distributed.RX_BLOCK
 
 
 def load_scenes():
@@ -115,10 +116,12 @@ def build_workload(name: str, rank: int, world: int, *, weak: bool = False):
         return dict(name=name, vertices=v, triangles=t, tx=tx, rx=rx, order=w["order"],
                     cand=np.ascontiguousarray(cand_all[start:stop]), cand_global=total, cand_start=start,
                     rx_global=int(rx.shape[0]), receivers=None)
+    idx = np.arange(rx.shape[0])
+    mine = idx[(idx // RX_BLOCK) % world == rank]  # differt_b200.distributed.receiver_shard, restated (see load_scenes)
     return dict(
-        name=name, vertices=v, triangles=t, tx=tx, rx=np.ascontiguousarray(rx[rank::world]), order=w["order"],
-        cand=cand_all, cand_global=total, cand_start=0, rx_global=int(rx.shape[0]),
-        receivers=(int(rx.shape[0]), rank, world),
+        name=name, vertices=v, triangles=t, tx=tx, rx=np.ascontiguousarray(rx[mine]), order=w["order"],
+        cand=cand_all, cand_global=total, cand_start=0, rx_global=int(rx.shape[0]), rx_index=mine,
+        receivers=(int(rx.shape[0]), mine),
     )
 
 
@@ -425,6 +428,10 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     if args.cand is not None:  # BASELINE config 5's sweep over the number of candidates
         WORKLOADS[args.workload]["cand"] = args.cand
     wl = build_workload(args.workload, rank, world)
+    if args.emulate_shard:  # one process traces the shard rank r of w would get (no collective)
+        r_, w_ = (int(x) for x in args.emulate_shard.split("/"))
+        wl = build_workload(args.workload, r_, w_)
+        wl["receivers"] = None
     k = wl["order"]
     capacity = 1 << 10  # valid paths per rank in the gather record (overflow → the API's retry path)
 
@@ -440,6 +447,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     in_flight: list = [None, None]
     step_no = [0]
     stats_acc = torch.zeros(4, dtype=torch.int64, device=dev)
+    rx_shard = None if wl["receivers"] is None else (wl["receivers"][0], torch.from_numpy(wl["receivers"][1]).to(dev))
 
     # reverse mode every step (BASELINE config 3 is "with VJP"; SURVEY §8d: VJP of vertices.sum() w.r.t.
     # tx, rx and mesh.vertices): an all-ones cotangent, resident like the other inputs
@@ -460,7 +468,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         step_no[0] += 1
         if in_flight[slot] is not None:  # the gather that used these buffers two steps ago
             in_flight[slot].wait()
-        fill_record(records[slot], paths, wl["cand_global"], wl["cand_start"], receivers=wl["receivers"])
+        fill_record(records[slot], paths, wl["cand_global"], wl["cand_start"], receivers=rx_shard)
         if world > 1:
             in_flight[slot] = dist.all_gather_into_tensor(gathered_bufs[slot], records[slot].buffer, async_op=True)
         return paths
@@ -486,7 +494,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         grads = ()
         if with_vjp:
             grads = torch.autograd.grad(paths.vertices, (m.vertices, tx_e, rx_e), cot)
-        fill_record(records[0], paths, wl["cand_global"], wl["cand_start"], receivers=wl["receivers"])
+        fill_record(records[0], paths, wl["cand_global"], wl["cand_start"], receivers=rx_shard)
         # device → host: the mask and the gradients into pinned buffers (asynchronous), then the gather,
         # whose count read is the synchronisation point
         mask_host.copy_(paths.mask, non_blocking=True)
@@ -594,7 +602,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         from differt_b200.distributed import global_path_index_receivers
 
         idx_local = paths.mask.reshape(-1).nonzero().squeeze(-1)
-        idx_global = global_path_index_receivers(idx_local, cand_d.shape[0], rx_d.shape[0], wl["rx_global"], rank, world)
+        idx_global = global_path_index_receivers(idx_local, cand_d.shape[0], rx_shard[1], wl["rx_global"]) \
+            if rx_shard is not None else idx_local
         gather_ok = bool(torch.equal(mine[1][:valid_local], idx_global)) and bool(
             torch.equal(mine[2][:valid_local], paths.vertices.detach().reshape(-1, k + 2, 3)[idx_local]))
     del paths
@@ -794,6 +803,7 @@ def main() -> None:
                     help="extra leg: repeat the step for at least this long (0 = skip)")
     ap.add_argument("--weak-steps", type=int, default=5, help="extra weak-scaling leg for N > 1 (0 = skip)")
     ap.add_argument("--cand", type=int, default=None, help="override the workload's number of candidates")
+    ap.add_argument("--emulate-shard", default=None, help="r/w: single process, the shard of rank r of w (diagnostic)")
     ap.add_argument("--profile-only", action="store_true",
                     help="run exactly --steps steps of the timed loop's body and nothing else (for ncu)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -356,7 +356,7 @@ path_head_kernel(const Tri48 *__restrict__ pack, const int num_head_tiles, const
 #define DRT_WALK_CTAS 4
 #endif
 #ifndef DRT_WALK_CHUNK
-#define DRT_WALK_CHUNK 16
+#define DRT_WALK_CHUNK 4
 #endif
 #ifndef DRT_WALK_HEAD_ROWS
 #define DRT_WALK_HEAD_ROWS 1
@@ -402,7 +402,10 @@ path_walk_kernel(const Tri48 *__restrict__ pack, const CullNode *__restrict__ no
         head_tri[h] = unpack(head_row[32 * h + lane].a, head_row[32 * h + lane].b, head_row[32 * h + lane].c);
 
     // Work distribution: chunks of kChunk consecutive candidates from a global cursor (the cost of a
-    // candidate varies by two orders of magnitude; a static stride would leave most warps idle at the end)
+    // candidate varies by two orders of magnitude; a static stride would leave most warps idle at the
+    // end).  Small chunks: a warp that draws a run of unblocked candidates is busy for ~30 us each, and
+    // nothing may wait for it at the tail of a small batch (guided self-scheduling — reading the cursor to
+    // size the chunk — was measured slower: 28.5 vs 27.8 ms on the bench batch).
     constexpr int kChunk = DRT_WALK_CHUNK;
     int64_t tests = 0;
     while (true) {

@@ -62,9 +62,14 @@ def test_workload_is_deterministic_and_sharded_per_rank():
     # strong scaling: ONE fixed problem, its receivers dealt round-robin, every candidate on every rank
     np.testing.assert_array_equal(a["cand"], b["cand"])
     np.testing.assert_array_equal(a["cand"], one["cand"])
-    np.testing.assert_array_equal(a["rx"], one["rx"][0::2])
-    np.testing.assert_array_equal(b["rx"], one["rx"][1::2])
-    assert a["rx_global"] == one["rx"].shape[0] and a["receivers"] == (one["rx"].shape[0], 0, 2)
+    from differt_b200.distributed import RX_BLOCK, receiver_shard
+
+    assert bench.RX_BLOCK == RX_BLOCK
+    for w_, r_ in ((a, 0), (b, 1)):
+        mine = receiver_shard(one["rx"].shape[0], 2, r_).numpy()
+        np.testing.assert_array_equal(w_["rx"], one["rx"][mine])
+        np.testing.assert_array_equal(w_["rx_index"], mine)
+    assert a["rx_global"] == one["rx"].shape[0] and a["rx"].shape[0] + b["rx"].shape[0] == one["rx"].shape[0]
     assert (a["cand"][:, 1:] != a["cand"][:, :-1]).all()
     # the weak-scaling leg: every rank its own candidates, all receivers
     wa, wb = bench.build_workload("urban10k_small", 0, 2, weak=True), bench.build_workload("urban10k_small", 1, 2, weak=True)

@@ -127,13 +127,13 @@ def test_receiver_sharding_index_roundtrip():
     ntx, nrx, C = 3, 11, 5
     full = np.arange(ntx * nrx * C).reshape(ntx, nrx, C)
     seen = []
-    for world in (1, 2, 4):
+    for world, block in ((1, 16), (2, 1), (4, 1), (2, 3), (3, 4)):
         seen.clear()
         for rank in range(world):
-            mine = receiver_shard(nrx, world, rank).numpy()
+            mine = receiver_shard(nrx, world, rank, block)
             local = torch.arange(ntx * len(mine) * C)
-            g = global_path_index_receivers(local, C, len(mine), nrx, rank, world).numpy()
-            np.testing.assert_array_equal(g, full[:, mine, :].reshape(-1))
+            g = global_path_index_receivers(local, C, mine, nrx).numpy()
+            np.testing.assert_array_equal(g, full[:, mine.numpy(), :].reshape(-1))
             seen.append(g)
         np.testing.assert_array_equal(np.sort(np.concatenate(seen)), full.reshape(-1))  # a partition
 
