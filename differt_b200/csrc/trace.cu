@@ -675,33 +675,42 @@ __device__ __forceinline__ void warp_accumulate3(float *base, int64_t key, float
 // cotangent — is applied once.  Lanes of a warp hold consecutive candidates of the same receiver, so
 // the cotangent reads are coalesced and g_rx needs one shuffle reduction + one atomic per warp.
 template <int K>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (K <= 3 ? 4 : (K <= 5 ? 3 : 2)))
 trace_vjp_kernel(int64_t V, int64_t T, const float *__restrict__ verts,
                  const int32_t *__restrict__ tris, int64_t ntx, const float *__restrict__ tx,
                  int64_t nrx, const float *__restrict__ rx, int64_t C,
                  const int32_t *__restrict__ cand, const float *__restrict__ g_out,
                  int64_t rx_per_chunk, float *g_tx, float *g_rx, float *g_verts) {
     constexpr int KK = K > 0 ? K : 1;
+    constexpr int NV3 = (K + 2) * 3;  // floats of cotangent per path
+    // The cotangents of a warp's 32 consecutive paths are one contiguous block of 32 * NV3 floats.  It is
+    // copied into shared memory with 16-byte cp.async one receiver AHEAD (double buffer, no registers
+    // held), and each lane then reads its own NV3 floats from there (stride NV3 = 3 (K + 2) words:
+    // conflict-free for odd orders, 4-way at worst for even ones) — instead of NV3 scalar loads per lane
+    // at a 4 * NV3-byte stride, issued only once the previous receiver is done.
+    constexpr int NF4 = 8 * NV3;  // float4 per block
+    __shared__ __align__(16) float stage_all[4][2][32 * NV3];
     const int lane = threadIdx.x & 31;
+    float(*stage)[32 * NV3] = stage_all[threadIdx.x >> 5];
     const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     const int64_t itx = blockIdx.z;
     const int64_t rx0 = int64_t(blockIdx.y) * rx_per_chunk;
     const int64_t rx1 = rx0 + rx_per_chunk < nrx ? rx0 + rx_per_chunk : nrx;
     const bool have = c < C;
 
-    int64_t vi[KK][3];
-    float3 v0[KK], v1[KK], v2[KK], mn[KK];
+    // persistent per-thread state is kept small (the kernel is latency bound: registers buy warps):
+    // first vertex + unit normal of every mirror and the accumulated cotangents; the triangle's vertex
+    // numbers are re-read and the other two vertices re-loaded in the epilogue
+    float3 v0[KK], mn[KK];
     if (have) {
 #pragma unroll
         for (int i = 0; i < K; ++i) {
             const int64_t t = min(max(int64_t(cand[c * K + i]), int64_t(0)), T - 1);
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-                vi[i][q] = min(max(int64_t(tris[3 * t + q]), int64_t(0)), V - 1);
-            v0[i] = ld3(verts + 3 * vi[i][0]);
-            v1[i] = ld3(verts + 3 * vi[i][1]);
-            v2[i] = ld3(verts + 3 * vi[i][2]);
-            mn[i] = unit_normal(v0[i], v1[i], v2[i]);
+            const int64_t i0 = min(max(int64_t(tris[3 * t]), int64_t(0)), V - 1);
+            const int64_t i1 = min(max(int64_t(tris[3 * t + 1]), int64_t(0)), V - 1);
+            const int64_t i2 = min(max(int64_t(tris[3 * t + 2]), int64_t(0)), V - 1);
+            v0[i] = ld3(verts + 3 * i0);
+            mn[i] = unit_normal(v0[i], ld3(verts + 3 * i1), ld3(verts + 3 * i2));
         }
     }
     const float3 from = ld3(tx + 3 * itx);
@@ -710,11 +719,33 @@ trace_vjp_kernel(int64_t V, int64_t T, const float *__restrict__ verts,
 #pragma unroll
     for (int i = 0; i < KK; ++i) acc_mv[i] = acc_mn[i] = make_float3(0.f, 0.f, 0.f);
 
-    for (int64_t irx = rx0; irx < rx1; ++irx) {
+    const int64_t c0 = c - lane;      // first candidate of the warp
+    const bool whole = c0 + 32 <= C;  // a full warp of candidates
+    auto fetch_ahead = [&](int64_t irx, float *dst) {
+        const float *src = g_out + ((itx * nrx + irx) * C + c0) * NV3;
+        if (whole && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            for (int i = lane; i < NF4; i += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 4 * i)), "l"(src + 4 * i)
+                             : "memory");
+        } else if (c0 < C) {  // ragged or unaligned block: plain loads, same layout
+            const int n = int(C - c0 < 32 ? C - c0 : 32) * NV3;
+            for (int i = lane; i < n; i += 32) dst[i] = src[i];
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (rx0 < rx1) fetch_ahead(rx0, stage[0]);
+    int buf = 0;
+    for (int64_t irx = rx0; irx < rx1; ++irx, buf ^= 1) {
         float3 g_to = make_float3(0.f, 0.f, 0.f);
+        if (irx + 1 < rx1) {
+            fetch_ahead(irx + 1, stage[buf ^ 1]);  // in flight while this receiver is processed
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
         if (have) {
-            const int64_t p = (itx * nrx + irx) * C + c;
-            const float *g = g_out + p * (K + 2) * 3;
+            const float *g = stage[buf] + lane * NV3;
             float3 gp[KK];
             const float3 g0 = ld3(g), g1 = ld3(g + 3 * (K + 1));
             bool nz = (g0.x != 0.f) || (g0.y != 0.f) || (g0.z != 0.f) || (g1.x != 0.f) ||
@@ -741,6 +772,7 @@ trace_vjp_kernel(int64_t V, int64_t T, const float *__restrict__ verts,
                 }
             }
         }
+        __syncwarp();  // every lane is done with stage[buf] before the next iteration refills it
         // every lane of the warp works on the same receiver
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -760,8 +792,13 @@ trace_vjp_kernel(int64_t V, int64_t T, const float *__restrict__ verts,
     if (have) {
 #pragma unroll
         for (int i = 0; i < K; ++i) {
+            const int64_t t = min(max(int64_t(cand[c * K + i]), int64_t(0)), T - 1);
+            const int64_t i0 = min(max(int64_t(tris[3 * t]), int64_t(0)), V - 1);
+            const int64_t i1 = min(max(int64_t(tris[3 * t + 1]), int64_t(0)), V - 1);
+            const int64_t i2 = min(max(int64_t(tris[3 * t + 2]), int64_t(0)), V - 1);
+            const float3 v1 = ld3(verts + 3 * i1), v2 = ld3(verts + 3 * i2);
             // n = N / len, N = A × B, A = v1 - v0, B = v2 - v1
-            const float3 A = sub3(v1[i], v0[i]), B = sub3(v2[i], v1[i]);
+            const float3 A = sub3(v1, v0[i]), B = sub3(v2, v1);
             const float3 N = cross3(A, B);
             const float len = __fsqrt_rn(dot3(N, N));
             float3 gN;
@@ -772,9 +809,9 @@ trace_vjp_kernel(int64_t V, int64_t T, const float *__restrict__ verts,
                 gN = scale3(sub3(acc_mn[i], scale3(mn[i], proj)), __fdiv_rn(1.0f, len));
             }
             const float3 gA = cross3(B, gN), gB = cross3(gN, A);
-            atomic_add3(g_verts + 3 * vi[i][0], sub3(acc_mv[i], gA));
-            atomic_add3(g_verts + 3 * vi[i][1], sub3(gA, gB));
-            atomic_add3(g_verts + 3 * vi[i][2], gB);
+            atomic_add3(g_verts + 3 * i0, sub3(acc_mv[i], gA));
+            atomic_add3(g_verts + 3 * i1, sub3(gA, gB));
+            atomic_add3(g_verts + 3 * i2, gB);
         }
     }
 }
@@ -814,13 +851,33 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
     return before + x - v;
 }
 
+// bit i = mask[start + i] != 0 for the thread's kCompactItems (= 16) consecutive paths: one 16-byte load
+// when the span is whole and aligned (the mask base comes from an allocator: 256-byte aligned; start is a
+// multiple of 16), byte loads at the ragged end
+static_assert(kCompactItems == 16, "one uint4 of mask bytes per thread");
+__device__ __forceinline__ unsigned load_mask_bits(const uint8_t *__restrict__ mask, const int64_t start,
+                                                   const int64_t P) {
+    unsigned bits = 0;
+    if (start + kCompactItems <= P && (reinterpret_cast<uintptr_t>(mask + start) & 15) == 0) {
+        const uint4 w = *reinterpret_cast<const uint4 *>(mask + start);
+        const unsigned words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if ((words[q] >> (8 * b)) & 0xffu) bits |= 1u << (4 * q + b);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kCompactItems; ++i)
+            if (start + i < P && mask[start + i] != 0) bits |= 1u << i;
+    }
+    return bits;
+}
+
 __global__ void __launch_bounds__(kCompactThreads)
 compact_count_kernel(int64_t P, const uint8_t *__restrict__ mask, int32_t *__restrict__ block_counts) {
     const int64_t start = int64_t(blockIdx.x) * kCompactChunk + threadIdx.x * kCompactItems;
-    int n = 0;
-#pragma unroll
-    for (int i = 0; i < kCompactItems; ++i)
-        if (start + i < P) n += mask[start + i] != 0;
+    const int n = __popc(load_mask_bits(mask, start, P));
     int total;
     block_exclusive_scan(n, &total);
     if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
@@ -871,14 +928,8 @@ compact_scatter_kernel(int64_t P, int nvert, const float *__restrict__ vertices,
                        int64_t *__restrict__ out_index, float *__restrict__ out_vertices,
                        int32_t *__restrict__ out_objects) {
     const int64_t start = int64_t(blockIdx.x) * kCompactChunk + threadIdx.x * kCompactItems;
-    int n = 0;
-    unsigned bits = 0;
-#pragma unroll
-    for (int i = 0; i < kCompactItems; ++i)
-        if (start + i < P && mask[start + i] != 0) {
-            bits |= 1u << i;
-            ++n;
-        }
+    const unsigned bits = load_mask_bits(mask, start, P);
+    const int n = __popc(bits);
     int total;
     int64_t pos = block_offsets[blockIdx.x] + block_exclusive_scan(n, &total);
     for (int i = 0; i < kCompactItems; ++i) {
