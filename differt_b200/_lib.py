@@ -31,6 +31,9 @@ PROTOTYPES: dict[str, tuple] = {
     "drt_ray_intersect_triangle": (
         C.c_int, [ptr, i32, p_i64, ptr, p_i64, ptr, p_i64, ptr, p_i64, f32, ptr, ptr]),
     "drt_ray_intersect_any_triangle": (C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, f32, ptr, ptr]),
+    "drt_any_hit_workspace_bytes": (size_t, [i64]),
+    "drt_ray_intersect_any_triangle_culled": (
+        C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, f32, ptr, size_t, ptr, ptr]),
     "drt_first_triangle_hit_by_ray": (
         C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, i64, ptr, ptr, ptr]),
     "drt_first_triangle_hit_by_ray_vjp": (

@@ -2,6 +2,7 @@
 // Reference: differt/src/differt/geometry/_utils.py:1157-1960 and the Warp launchers
 // differt/src/differt/geometry/_mesh.py:142-223, 347-401.
 #include "intersect_core.cuh"
+#include "walk.cuh"
 
 namespace drt {
 
@@ -302,6 +303,44 @@ int drt_ray_intersect_any_triangle(drt_stream_t stream, int64_t R, const float *
         AnySink<RPW> sink{out};
         DRT_CHECK_CUDA((launch_intersect<RPW, MODE_ANY>(s, p, src, sink, p.num_units)));
     })
+    return DRT_OK;
+}
+
+size_t drt_any_hit_workspace_bytes(int64_t T) {
+    if (T < 0) return 0;
+    const int64_t records = padded_triangles(T);
+    return ((cull_layout(records).total + 255) & ~size_t(255)) + drt_mesh_pack_sort_workspace_bytes(T) + 256;
+}
+
+int drt_ray_intersect_any_triangle_culled(drt_stream_t stream, int64_t R, const float *o, const float *d,
+                                          const void *pack, int64_t T, float epsilon, float hit_tol,
+                                          void *workspace, size_t workspace_bytes, uint8_t *out,
+                                          int64_t *tests_done) {
+    if (R < 0 || T < 0) return DRT_ERR_BAD_EXTENT;
+    const int64_t records = padded_triangles(T);
+    const float thr = 1.0f - hit_tol;
+    // small meshes, or parameters outside the range the cull's proof covers: the plain all-pairs engine
+    if (R == 0 || T == 0 || workspace == nullptr || records <= int64_t(kCullHead) * kTile ||
+        !(epsilon >= 1.17549435e-38f) || !(thr > 0.0f && thr <= 1.0f))
+        return drt_ray_intersect_any_triangle(stream, R, o, d, pack, T, epsilon, hit_tol, out, tests_done);
+    if (out == nullptr || o == nullptr || d == nullptr || pack == nullptr) return DRT_ERR_NULL_POINTER;
+    if (workspace_bytes < drt_any_hit_workspace_bytes(T)) return DRT_ERR_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    const CullLayout l = cull_layout(records);
+    const size_t sort_off = (l.total + 255) & ~size_t(255);
+    const size_t sort_bytes = drt_mesh_pack_sort_workspace_bytes(T);
+    unsigned long long *cursor = reinterpret_cast<unsigned long long *>(ws + sort_off + sort_bytes);
+    int rc = cull_build(s, records, static_cast<const Tri48 *>(pack), ws, l, ws + sort_off, sort_bytes);
+    if (rc != DRT_OK) return rc;
+    DRT_CHECK_CUDA(cudaMemsetAsync(cursor, 0, 8, s));
+    DRT_CHECK_CUDA(cudaMemsetAsync(out, 0, size_t(R), s));
+    const int64_t wblocks = (R + kWalkWarps - 1) / kWalkWarps;
+    const int64_t wres = int64_t(device_sm_count()) * DRT_WALK_CTAS;
+    path_walk_kernel<1, true><<<unsigned(wblocks < wres ? wblocks : wres), kWalkWarps * 32, 0, s>>>(
+        reinterpret_cast<const Tri48 *>(ws + l.pack), reinterpret_cast<const CullNode *>(ws + l.walk), l.levels,
+        static_cast<const Tri48 *>(pack), R, nullptr, o, d, nullptr, epsilon, thr, out, cursor, tests_done);
+    DRT_CHECK_CUDA(cudaGetLastError());
     return DRT_OK;
 }
 

@@ -9,7 +9,7 @@
 //   TracedPaths fields and a work list of the candidates that still need the blockage test.
 // Stage B (all-pairs engine, one warp per candidate, its k+1 segments register-blocked): any-hit of
 //   every segment against the whole mesh; a hit on any segment retires the candidate.
-#include "cull.cuh"
+#include "walk.cuh"
 #include "image_core.cuh"
 #include "intersect_core.cuh"
 
@@ -212,10 +212,6 @@ int drt_sort_records_by_keys(drt_stream_t stream, int64_t n, const void *pack_in
 #ifndef DRT_PATH_HEAD_CTAS
 #define DRT_PATH_HEAD_CTAS 1
 #endif
-#ifndef DRT_WALK_MIN_TILES
-#define DRT_WALK_MIN_TILES 4
-#endif
-constexpr int kCullHead = DRT_WALK_MIN_TILES;  // meshes with more tiles than this take the culled traversal
 constexpr int kPathHead = DRT_PATH_HEAD_TILES;
 constexpr int kPathHeadWarps = DRT_PATH_HEAD_WARPS;
 constexpr size_t kPathHeadSmem = size_t(kPathHead) * kTile * sizeof(Tri48) + 16;
@@ -325,194 +321,6 @@ path_head_kernel(const Tri48 *__restrict__ pack, const int num_head_tiles, const
                                       (unsigned long long)nkeep);
         base = __shfl_sync(kFull, base, 0);
         if (lane < nkeep) out_list[base + lane] = keep;
-    }
-    if (tests_done != nullptr && lane == 0 && tests)
-        atomicAdd(reinterpret_cast<unsigned long long *>(tests_done), (unsigned long long)tests);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Blockage, culled traversal (cull.cuh): ONE WARP per candidate walks the 8-ary hierarchy over the
-// Morton-ordered pack, one segment at a time — the LAST segment first: it ends at the receiver, at
-// street level, and is the likeliest to be blocked — with all 32 lanes busy on that segment:
-//   * node step: up to four pending nodes are popped from a per-warp stack in shared memory and
-//     lane (j, c) tests child c of node j with node_culled (4 x 8 children, 80-byte nodes read as
-//     contiguous 640-byte blocks); the surviving children are pushed back — groups on a second stack;
-//   * group step: up to four pending groups are popped and lane (j, k) evaluates the exact
-//     Möller–Trumbore test of triangle k of group j.  The first hit retires the candidate.
-// Control flow is warp-uniform (ballots + popcounts, no divergence), the stacks hold at most a few
-// dozen entries (depth-first order), and a candidate only ever touches the nodes and triangles around
-// its own segments.
-//
-// Measured alternatives (profiles/README.md): a thread per candidate — the classic BVH traversal — runs
-// at 29 % SIMT efficiency with the L1 data pipe saturated by 32 lanes fetching 32 different nodes
-// (131 ms per bench step); all segments of a candidate walking together, lane = (segment, child),
-// visits every node ANY segment touches before the blocking one is found (153 ms).
-// ------------------------------------------------------------------------------------------------
-
-#ifndef DRT_WALK_WARPS
-#define DRT_WALK_WARPS 8
-#endif
-#ifndef DRT_WALK_CTAS
-#define DRT_WALK_CTAS 4
-#endif
-#ifndef DRT_WALK_CHUNK
-#define DRT_WALK_CHUNK 4
-#endif
-#ifndef DRT_WALK_HEAD_ROWS
-#define DRT_WALK_HEAD_ROWS 1
-#endif
-constexpr int kWalkWarps = DRT_WALK_WARPS;
-constexpr int kWalkHeadRows = DRT_WALK_HEAD_ROWS;  // rows of 32 largest triangles tested before the walk
-constexpr int kWalkStack = 256;      // node stack: a step pops <= 4 and pushes <= 32, depth-first: <= 7 x 28 + 32
-constexpr int kWalkGroupStack = 64;  // group stack: drained 4 at a time as soon as it holds 4: <= 3 + 32
-
-template <int NSEG>
-__global__ void __launch_bounds__(kWalkWarps * 32, DRT_WALK_CTAS)
-path_walk_kernel(const Tri48 *__restrict__ pack, const CullNode *__restrict__ nodes, const WalkLevels lv,
-                 const Tri48 *__restrict__ head_row, const int64_t num_units_host,
-                 const int64_t *__restrict__ num_units_dev, const float *__restrict__ vertices,
-                 const uint32_t *__restrict__ list, const float eps, const float thr, uint8_t *__restrict__ mask,
-                 unsigned long long *cursor, int64_t *tests_done) {
-    static_assert(kWalkFan == 8 && kCullGroup == 8, "lane = 8 x entry + child / triangle");
-    // entry = (L << 28) | index: node `index` of level L - 1 (L = 0: the virtual root); its children are
-    // the nodes 8 index .. 8 index + 7 of level L
-    __shared__ uint32_t node_stack_all[kWalkWarps][kWalkStack];
-    __shared__ uint32_t group_stack_all[kWalkWarps][kWalkGroupStack];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *node_stack = node_stack_all[warp], *group_stack = group_stack_all[warp];
-    __shared__ int level_offset[kWalkMaxLevels], level_size[kWalkMaxLevels];
-    if (threadIdx.x < kWalkMaxLevels) {
-        level_offset[threadIdx.x] = lv.offset[threadIdx.x];
-        level_size[threadIdx.x] = lv.size[threadIdx.x];
-    }
-    __syncthreads();
-    const int64_t num_units = num_units_dev ? *num_units_dev : num_units_host;
-    constexpr int NV = NSEG + 1;
-    static_assert(3 * NV <= 32, "one float per lane prefetch");
-    auto path_of = [&](int64_t u) -> int64_t { return list != nullptr ? int64_t(list[u]) : u; };
-    auto fetch = [&](int64_t path) -> float { return lane < 3 * NV ? vertices[path * (3 * NV) + lane] : 0.0f; };
-    const int leaf = lv.num_levels - 1;
-    const int sub = lane & 7, slot = lane >> 3;  // child / triangle, and which of the (up to) 4 popped entries
-    // the 32 largest triangles (first row of the area-sorted pack), one per lane: every candidate is
-    // tested against them before it walks the hierarchy — a random segment is blocked by a triangle
-    // with a probability proportional to its area (the ground alone blocks a third of the bench batch)
-    Tri head_tri[kWalkHeadRows];
-#pragma unroll
-    for (int h = 0; h < kWalkHeadRows; ++h)
-        head_tri[h] = unpack(head_row[32 * h + lane].a, head_row[32 * h + lane].b, head_row[32 * h + lane].c);
-
-    // Work distribution: chunks of kChunk consecutive candidates from a global cursor (the cost of a
-    // candidate varies by two orders of magnitude; a static stride would leave most warps idle at the
-    // end).  Small chunks: a warp that draws a run of unblocked candidates is busy for ~30 us each, and
-    // nothing may wait for it at the tail of a small batch (guided self-scheduling — reading the cursor to
-    // size the chunk — was measured slower: 28.5 vs 27.8 ms on the bench batch).
-    constexpr int kChunk = DRT_WALK_CHUNK;
-    int64_t tests = 0;
-    while (true) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kChunk);
-        const int64_t unit0 = int64_t(__shfl_sync(kFull, base, 0));
-        if (unit0 >= num_units) break;
-        const int64_t unit1 = unit0 + kChunk < num_units ? unit0 + kChunk : num_units;
-        float pf = fetch(path_of(unit0));
-    for (int64_t unit = unit0; unit < unit1; ++unit) {
-        const float pv = pf;  // this candidate's vertices, one float per lane
-        const int64_t path = path_of(unit);
-        if (unit + 1 < unit1) pf = fetch(path_of(unit + 1));
-
-        bool blocked = false;
-#pragma unroll
-        for (int h = 0; h < kWalkHeadRows && !blocked; ++h) {  // head rows: every segment against the largest triangles
-            bool hit = false, weird = false;
-            float3 prev = make_float3(__shfl_sync(kFull, pv, 0), __shfl_sync(kFull, pv, 1), __shfl_sync(kFull, pv, 2));
-#pragma unroll
-            for (int sgm = 0; sgm < NSEG; ++sgm) {
-                const float3 next = make_float3(__shfl_sync(kFull, pv, 3 * sgm + 3), __shfl_sync(kFull, pv, 3 * sgm + 4),
-                                                __shfl_sync(kFull, pv, 3 * sgm + 5));
-                hit = mt_any_fast(prev, sub3(next, prev), head_tri[h], eps, thr, weird) || hit;
-                prev = next;
-            }
-            if (__any_sync(kFull, weird)) {  // re-evaluate with the general test
-                hit = false;
-                prev = make_float3(__shfl_sync(kFull, pv, 0), __shfl_sync(kFull, pv, 1), __shfl_sync(kFull, pv, 2));
-#pragma unroll
-                for (int sgm = 0; sgm < NSEG; ++sgm) {
-                    const float3 next = make_float3(__shfl_sync(kFull, pv, 3 * sgm + 3),
-                                                    __shfl_sync(kFull, pv, 3 * sgm + 4),
-                                                    __shfl_sync(kFull, pv, 3 * sgm + 5));
-                    float t;
-                    hit = (mt_exact(prev, sub3(next, prev), head_tri[h], eps, t) && t < thr) || hit;
-                    prev = next;
-                }
-            }
-            tests += 32 * NSEG;
-            blocked = __any_sync(kFull, hit);
-        }
-        for (int sgm = NSEG - 1; sgm >= 0 && !blocked; --sgm) {
-            const float3 o = make_float3(__shfl_sync(kFull, pv, 3 * sgm), __shfl_sync(kFull, pv, 3 * sgm + 1),
-                                         __shfl_sync(kFull, pv, 3 * sgm + 2));
-            const float3 next = make_float3(__shfl_sync(kFull, pv, 3 * sgm + 3), __shfl_sync(kFull, pv, 3 * sgm + 4),
-                                            __shfl_sync(kFull, pv, 3 * sgm + 5));
-            const float3 d = sub3(next, o);  // jnp.diff (_solvers.py:593)
-            // d = 0 → a = 0 → no hit; a non-finite origin or direction → NaN/inf comparisons → no hit
-            if ((d.x == 0.0f && d.y == 0.0f && d.z == 0.0f) || !finite3(o) || !finite3(d)) continue;
-            const SegCull sc = make_seg_cull(o, d);
-
-            int nn = 1, ng = 0;  // stack heights (warp-uniform)
-            if (lane == 0) node_stack[0] = 0u;  // the virtual root
-            __syncwarp();
-            while (nn > 0 || ng > 0) {
-                if (ng >= 4 || nn == 0) {
-                    // ---- group step: up to 4 groups x 8 triangles
-                    const int take = ng < 4 ? ng : 4;
-                    ng -= take;
-                    bool hit = false;
-                    if (slot < take) {
-                        const uint32_t g = group_stack[ng + slot];
-                        const Tri48 *rec = pack + size_t(g) * kCullGroup + sub;
-                        const float4 ta = rec->a, tb = rec->b, tc = rec->c;
-                        const Tri tr = unpack(ta, tb, tc);
-                        bool weird = false;
-                        hit = mt_any_fast(o, d, tr, eps, thr, weird);
-                        if (weird) {  // |a| outside the fast reciprocal's range: the general test decides
-                            float t;
-                            hit = mt_exact(o, d, tr, eps, t) && t < thr;
-                        }
-                    }
-                    tests += take * kCullGroup;
-                    if (__any_sync(kFull, hit)) {
-                        blocked = true;
-                        break;
-                    }
-                } else {
-                    // ---- node step: up to 4 nodes x 8 children
-                    const int take = nn < 4 ? nn : 4;
-                    nn -= take;
-                    bool keep = false;
-                    uint32_t child = 0;
-                    int L = 0;
-                    if (slot < take) {
-                        const uint32_t e = node_stack[nn + slot];
-                        L = int(e >> 28);
-                        child = (e & 0x0fffffffu) * kWalkFan + sub;
-                        if (int(child) < level_size[L]) keep = !node_culled(sc, nodes[level_offset[L] + child]);
-                    }
-                    __syncwarp();  // every lane has read its entry before the stacks are overwritten
-                    const bool to_group = keep && L == leaf;
-                    const bool to_node = keep && L != leaf;
-                    const unsigned bg = __ballot_sync(kFull, to_group), bn = __ballot_sync(kFull, to_node);
-                    const unsigned below = (1u << lane) - 1u;
-                    if (to_group) group_stack[ng + __popc(bg & below)] = child;
-                    if (to_node) node_stack[nn + __popc(bn & below)] = (uint32_t(L + 1) << 28) | child;
-                    ng += __popc(bg);
-                    nn += __popc(bn);
-                    __syncwarp();
-                }
-            }
-        }
-        if (blocked && lane == 0) mask[path] = 0;
-        __syncwarp();
-    }
     }
     if (tests_done != nullptr && lane == 0 && tests)
         atomicAdd(reinterpret_cast<unsigned long long *>(tests_done), (unsigned long long)tests);
@@ -1116,11 +924,11 @@ int trace_launch(cudaStream_t s, const TraceArgs &a, bool quads, bool dense, boo
             if (compact) clamp_count_kernel<<<1, 1, 0, s>>>(a.list_count, a.capacity, units_scratch);
             const int64_t wblocks = (bound + kWalkWarps - 1) / kWalkWarps;
             const int64_t wres = int64_t(device_sm_count()) * DRT_WALK_CTAS;
-            path_walk_kernel<NSEG><<<unsigned(wblocks < wres ? wblocks : wres), kWalkWarps * 32, 0, s>>>(
+            path_walk_kernel<NSEG, false><<<unsigned(wblocks < wres ? wblocks : wres), kWalkWarps * 32, 0, s>>>(
                 reinterpret_cast<const Tri48 *>(cull_ws + cull.pack),
                 reinterpret_cast<const CullNode *>(cull_ws + cull.walk), cull.levels, pack_active, bound,
                 compact ? units_scratch : (dense ? nullptr : a.list_count), a.out_vertices,
-                compact ? nullptr : list, a.eps, p.thr, a.out_mask,
+                nullptr, compact ? nullptr : list, a.eps, p.thr, a.out_mask,
                 reinterpret_cast<unsigned long long *>(list2_count + 4), tests_done);
             e = cudaGetLastError();
             if (e == cudaSuccess && tests_done != nullptr) set_i64_kernel<<<1, 1, 0, s>>>(tests_done + 3, 256);

@@ -49,6 +49,8 @@ __all__ = [
 
 # below this many rays an any-hit call is launch-bound and sorting the pack first does not pay
 _SORT_MIN_RAYS = 4096
+_CULL_MIN_TRIANGLES = 2048  # above this the flat any-hit goes through the exact cull (csrc/cull.cuh)
+_CULL_MIN_RAYS = 1024       # ... when there are enough rays to pay for building its hierarchy (~0.1 ms)
 
 
 def _default(value, factor: float) -> float:
@@ -344,6 +346,7 @@ def ray_intersect_any_triangle(
     reference's memory use); ``epsilon`` may be passed through ``**kwargs`` like in the reference.
     """
     del batch_size
+    _tests_done = kwargs.pop("_tests_done", None)  # measurement hook: device int64 counter of executed tests
     pl = Placement()
     o = pl.put(ray_origins, torch.float32)
     d = pl.put(ray_directions, torch.float32)
@@ -390,11 +393,21 @@ def ray_intersect_any_triangle(
         if oi.shape[0] >= _SORT_MIN_RAYS:
             pack = sort_pack_by_area(pack, T)
         res = torch.empty(oi.shape[0], dtype=torch.uint8, device=o.device)
-        check(
-            lib.drt_ray_intersect_any_triangle(
-                stream_ptr(), oi.shape[0], ptr(oi), ptr(di), ptr(pack), T, eps, tol, ptr(res), None
+        if T > _CULL_MIN_TRIANGLES and oi.shape[0] >= _CULL_MIN_RAYS:
+            # same test, same results, behind the exact conservative cull (csrc/cull.cuh): O(log T) per ray
+            ws = torch.empty(lib.drt_any_hit_workspace_bytes(T), dtype=torch.uint8, device=o.device)
+            check(
+                lib.drt_ray_intersect_any_triangle_culled(
+                    stream_ptr(), oi.shape[0], ptr(oi), ptr(di), ptr(pack), T, eps, tol, ptr(ws), ws.numel(),
+                    ptr(res), ptr(_tests_done),
+                )
             )
-        )
+        else:
+            check(
+                lib.drt_ray_intersect_any_triangle(
+                    stream_ptr(), oi.shape[0], ptr(oi), ptr(di), ptr(pack), T, eps, tol, ptr(res), ptr(_tests_done)
+                )
+            )
         out[sel] = res.view(out[sel].shape)
     return pl.out(out.view(torch.bool))
 

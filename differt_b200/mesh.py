@@ -158,11 +158,19 @@ class Mesh:
         pack = geometry.pack_mesh(self.vertices.detach(), self.triangles, self._mask_u8())
         if R >= geometry._SORT_MIN_RAYS:
             pack = geometry.sort_pack_by_area(pack, self.num_triangles)
+        if self.num_triangles > geometry._CULL_MIN_TRIANGLES and R >= geometry._CULL_MIN_RAYS:
+            # same test, same results, behind the exact conservative cull (csrc/cull.cuh)
+            ws = torch.empty(lib.drt_any_hit_workspace_bytes(self.num_triangles), dtype=torch.uint8, device=o.device)
+            check(
+                lib.drt_ray_intersect_any_triangle_culled(
+                    stream_ptr(), R, ptr(o), ptr(d), ptr(pack), self.num_triangles, eps_, tol_, ptr(ws), ws.numel(),
+                    ptr(out), None,
+                )
+            )
+            return pl.out(out.view(torch.bool))
         check(
             lib.drt_ray_intersect_any_triangle(
-                stream_ptr(), R, ptr(o), ptr(d), ptr(pack), self.num_triangles,
-                10.0 * F32_EPS if epsilon is None else float(epsilon),
-                100.0 * F32_EPS if hit_tol is None else float(hit_tol), ptr(out), None,
+                stream_ptr(), R, ptr(o), ptr(d), ptr(pack), self.num_triangles, eps_, tol_, ptr(out), None,
             )
         )
         return pl.out(out.view(torch.bool))

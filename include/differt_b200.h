@@ -121,6 +121,18 @@ DRT_API int drt_ray_intersect_any_triangle(drt_stream_t stream, int64_t num_rays
                                    const float *ray_directions, const void *pack,
                                    int64_t num_triangles, float epsilon, float hit_tol,
                                    uint8_t *out, int64_t *tests_done /*nullable*/);
+/* K2 with the exact conservative cull of csrc/cull.cuh in front of the same Möller–Trumbore test: a warp
+ * per ray walks an 8-ary hierarchy over the Morton-ordered pack and only evaluates the triangles the
+ * cull cannot PROVE to be misses — identical results, O(log T) instead of O(T) per ray.  Falls back to
+ * the all-pairs engine for meshes of <= 2048 triangles and for epsilon < FLT_MIN or hit_tol outside
+ * [0, 1) (outside the proof).  `pack` as above (its first 32 records are tested first: pass an
+ * area-sorted pack when you have one).  workspace: drt_any_hit_workspace_bytes(num_triangles). */
+DRT_API size_t drt_any_hit_workspace_bytes(int64_t num_triangles);
+DRT_API int drt_ray_intersect_any_triangle_culled(drt_stream_t stream, int64_t num_rays, const float *ray_origins,
+                                          const float *ray_directions, const void *pack,
+                                          int64_t num_triangles, float epsilon, float hit_tol,
+                                          void *workspace, size_t workspace_bytes, uint8_t *out,
+                                          int64_t *tests_done /*nullable*/);
 
 /* ---------------------------------------------------------------------------------------------
  * K3  first_triangle_hit_by_ray (reference: _utils.py:1775-1960; launcher _mesh.py:202-223).

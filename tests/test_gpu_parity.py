@@ -170,6 +170,56 @@ def test_k2_counts_tests(drt, rng):
     assert int(cnt.item()) == 1000 * 512
 
 
+def test_k2_culled_any_hit_equals_all_pairs_and_oracle(drt, rng, bruxelles):
+    """The flat any-hit behind the exact cull: same bits as the all-pairs engine and the oracle, on the
+    urban grid, on the reference's bruxelles.obj (a general, non axis-aligned mesh) and on the coplanar
+    clusters that produce noise hits far from the triangles — with a fraction of the tests."""
+    from differt_b200 import _lib
+    from differt_b200._tensor import ptr, stream_ptr
+    from differt_b200.geometry import pack_triangle_vertices, sort_pack_by_area
+
+    cases = []
+    v, t = scenes.urban_grid(29, 29)
+    cases.append(("urban", orc.triangle_vertices(v, t), *scene_rays(rng, v, 60_000), None))
+    bv, bt = bruxelles
+    cases.append(("bruxelles", orc.triangle_vertices(bv, bt), *scene_rays(rng, bv, 40_000), rng.uniform(size=bt.shape[0]) < 0.5))
+    cv, ct, planes = _coplanar_clusters(np.random.default_rng(9))
+    c0, a, b, n, _ = planes[0]
+    uv0, uv1 = rng.uniform(-2500, 2500, (30_000, 2)), rng.uniform(-2500, 2500, (30_000, 2))
+    po = (c0 + uv0[:, 0:1] * a + uv0[:, 1:2] * b).astype(np.float32)
+    pe = (c0 + uv1[:, 0:1] * a + uv1[:, 1:2] * b).astype(np.float32)
+    cases.append(("coplanar", orc.triangle_vertices(cv, ct), po, (pe - po).astype(np.float32), None))
+    for name, tri, o, d, active in cases:
+        T = tri.shape[0]
+        exp = co.ray_intersect_any_triangle(o, d, tri, active)
+        got = drt.ray_intersect_any_triangle(o, d, tri, active)  # public API: culled for T > 2048
+        np.testing.assert_array_equal(got.numpy(), exp, err_msg=name)
+        assert exp.any() and not exp.all()
+        # through the C ABI, both engines, with their test counters
+        tc, oc, dc = (torch.from_numpy(x).cuda() for x in (tri, o, d))
+        act = None if active is None else torch.from_numpy(active.astype(np.uint8)).cuda()
+        pack = sort_pack_by_area(pack_triangle_vertices(tc, act), T)
+        res = [torch.empty(o.shape[0], dtype=torch.uint8, device="cuda") for _ in range(2)]
+        cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+        ws = torch.empty(_lib.lib.drt_any_hit_workspace_bytes(T), dtype=torch.uint8, device="cuda")
+        _lib.check(_lib.lib.drt_ray_intersect_any_triangle(
+            stream_ptr(), o.shape[0], ptr(oc), ptr(dc), ptr(pack), T, 10 * orc.EPS, 100 * orc.EPS, ptr(res[0]), ptr(cnt[0:1])))
+        _lib.check(_lib.lib.drt_ray_intersect_any_triangle_culled(
+            stream_ptr(), o.shape[0], ptr(oc), ptr(dc), ptr(pack), T, 10 * orc.EPS, 100 * orc.EPS, ptr(ws), ws.numel(),
+            ptr(res[1]), ptr(cnt[1:2])))
+        assert torch.equal(res[0], res[1]), name
+        np.testing.assert_array_equal(res[1].cpu().numpy().astype(bool), exp, err_msg=name)
+        brute, culled = cnt.cpu().tolist()
+        print(f"{name}: all-pairs engine {brute} tests, culled {culled} tests")
+        if name != "coplanar":  # (coplanar rays are exactly what the cull cannot prove anything about)
+            assert culled < 0.5 * brute, (name, brute, culled)
+    # parameters outside the proof fall back to the all-pairs engine (same results as the oracle)
+    name, tri, o, d, active = cases[0]
+    for kw in ({"hit_tol": -0.5}, {"epsilon": 0.0}, {"epsilon": -1.0}):
+        exp = co.ray_intersect_any_triangle(o[:5000], d[:5000], tri, **kw)
+        np.testing.assert_array_equal(drt.ray_intersect_any_triangle(o[:5000], d[:5000], tri, **kw).numpy(), exp)
+
+
 # ------------------------------------------------------------------------------------------------
 # K3 (+ K3b)
 # ------------------------------------------------------------------------------------------------
