@@ -36,6 +36,8 @@ PROTOTYPES: dict[str, tuple] = {
         C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, f32, ptr, size_t, ptr, ptr]),
     "drt_first_triangle_hit_by_ray": (
         C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, i64, ptr, ptr, ptr]),
+    "drt_first_triangle_hit_by_ray_culled": (
+        C.c_int, [ptr, i64, ptr, ptr, ptr, i64, f32, i64, ptr, size_t, ptr, ptr, ptr]),
     "drt_first_triangle_hit_by_ray_vjp": (
         C.c_int, [ptr, i64, i64, i64, ptr, ptr, ptr, ptr, ptr, ptr, ptr, ptr, ptr]),
     "drt_triangles_visible_from_vertex": (

@@ -81,8 +81,19 @@ __device__ __forceinline__ SegCull make_seg_cull(const float3 o, const float3 d)
     return s;
 }
 
-// true iff the node is PROVEN to contain no triangle the reference's test would report as hit by s
-__device__ __forceinline__ bool node_culled(const SegCull &s, const CullNode &n) {
+// The same for a RAY (first-hit queries: t > eps only, no upper bound).  (*) gains the term
+// 2.02u t̂ |d|, and t̂ |d| = |P1 - o| <= |P2 - o| + |P2 - P1| <= S + m, i.e. 2.02u (S + m): inside the
+// slack of the 6e-6 S / g term (100u S / g against the 37u S / g needed).  R_seg only has to bound the
+// coordinates of o (the slab arithmetic never forms o + d).
+__device__ __forceinline__ SegCull make_ray_cull(const float3 o, const float3 d) {
+    SegCull s = make_seg_cull(o, d);
+    s.rseg = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+    return s;
+}
+
+// true iff the node is PROVEN to contain no triangle the reference's test would report as hit by s at
+// a parameter t <= tmax (1 for a segment; the best distance so far, or +inf, for a first-hit ray)
+__device__ __forceinline__ bool node_culled(const SegCull &s, const CullNode &n, const float tmax_seg = 1.0f) {
     if (n.half.x < 0.0f) return true;  // empty node (only never-hit records)
     const float p0 = fabsf(__fmaf_rn(s.dhat.x, n.c0.x, __fmaf_rn(s.dhat.y, n.c0.y, s.dhat.z * n.c0.z)));
     const float p1 = fabsf(__fmaf_rn(s.dhat.x, n.c1.x, __fmaf_rn(s.dhat.y, n.c1.y, s.dhat.z * n.c1.z)));
@@ -102,8 +113,9 @@ __device__ __forceinline__ bool node_culled(const SegCull &s, const CullNode &n)
     const float ay = ((n.ctr.y - hy) - s.o.y) * s.inv.y, by = ((n.ctr.y + hy) - s.o.y) * s.inv.y;
     const float az = ((n.ctr.z - hz) - s.o.z) * s.inv.z, bz = ((n.ctr.z + hz) - s.o.z) * s.inv.z;
     const float tmin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-    const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), 1.0f));
-    return tmin > tmax + 1e-5f;
+    const float tmax = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax_seg));
+    // 1e-5 relative slack in t (the computed parameters carry a relative error of a few u)
+    return tmin > __fmaf_rn(tmax, 1e-5f, tmax) + 1e-30f;
 }
 
 // The 8-ary hierarchy of the per-thread traversal (path_walk_kernel): level 0 is the top (<= 8 nodes,

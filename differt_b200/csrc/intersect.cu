@@ -374,6 +374,40 @@ int drt_first_triangle_hit_by_ray(drt_stream_t stream, int64_t R, const float *o
     return DRT_OK;
 }
 
+int drt_first_triangle_hit_by_ray_culled(drt_stream_t stream, int64_t R, const float *o, const float *d,
+                                         const void *pack, int64_t T, float epsilon, int64_t batch_size,
+                                         void *workspace, size_t workspace_bytes, int32_t *out_index,
+                                         float *out_t, int64_t *tests_done) {
+    if (R < 0 || T < 0) return DRT_ERR_BAD_EXTENT;
+    const int64_t records = padded_triangles(T);
+    // small meshes, or an epsilon outside the range the cull's proof covers: the plain all-pairs engine
+    if (R == 0 || T == 0 || workspace == nullptr || records <= int64_t(kCullHead) * kTile ||
+        !(epsilon >= 1.17549435e-38f))
+        return drt_first_triangle_hit_by_ray(stream, R, o, d, pack, T, epsilon, batch_size, out_index, out_t,
+                                             tests_done);
+    if (out_index == nullptr || out_t == nullptr || o == nullptr || d == nullptr || pack == nullptr)
+        return DRT_ERR_NULL_POINTER;
+    if (workspace_bytes < drt_any_hit_workspace_bytes(T)) return DRT_ERR_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    const CullLayout l = cull_layout(records);
+    const size_t sort_off = (l.total + 255) & ~size_t(255);
+    const size_t sort_bytes = drt_mesh_pack_sort_workspace_bytes(T);
+    unsigned long long *cursor = reinterpret_cast<unsigned long long *>(ws + sort_off + sort_bytes);
+    int rc = cull_build(s, records, static_cast<const Tri48 *>(pack), ws, l, ws + sort_off, sort_bytes);
+    if (rc != DRT_OK) return rc;
+    DRT_CHECK_CUDA(cudaMemsetAsync(cursor, 0, 8, s));
+    const int64_t wblocks = (R + kWalkWarps - 1) / kWalkWarps;
+    const int64_t wres = int64_t(device_sm_count()) * DRT_WALK_CTAS;
+    ray_first_walk_kernel<<<unsigned(wblocks < wres ? wblocks : wres), kWalkWarps * 32, 0, s>>>(
+        reinterpret_cast<const Tri48 *>(ws + l.pack),
+        reinterpret_cast<const uint32_t *>(ws + sort_off + sort_indices_offset(records)),
+        reinterpret_cast<const CullNode *>(ws + l.walk), l.levels, R, o, d, epsilon, batch_size, T, out_index, out_t,
+        cursor, tests_done);
+    DRT_CHECK_CUDA(cudaGetLastError());
+    return DRT_OK;
+}
+
 int drt_triangles_visible_from_vertex(drt_stream_t stream, int64_t B, int64_t n_rays,
                                       const float *vertices, const float *dirs, const void *pack,
                                       int64_t T, float epsilon, uint8_t *out, int64_t *tests_done) {

@@ -53,7 +53,7 @@ inline SortLayout sort_layout(int64_t n) {
     l.keys_in = 0;
     l.keys_out = arr;
     l.idx_in = 2 * arr;
-    l.idx_out = 3 * arr;
+    l.idx_out = sort_indices_offset(n);  // = 3 * arr: read by the culled first-hit (walk.cuh)
     l.cub = 4 * arr;
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, static_cast<const uint32_t *>(nullptr),

@@ -209,4 +209,139 @@ path_walk_kernel(const Tri48 *__restrict__ pack, const CullNode *__restrict__ no
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// First hit (nearest triangle) with the same culled traversal: one warp per ray.  A node is skipped only
+// if node_culled proves that no triangle in it is reported as hit at a distance t <= the best found so
+// far (ties included: the reference's tie rule picks among EQUAL distances by index, tie_key), so the
+// winner and its distance are those of the all-pairs reduction bit for bit.  The bound shrinks as hits
+// are found; children are not ordered front to back (any order is exact; the Morton order of the
+// hierarchy is spatially coherent, which is most of the benefit).
+// `orig` maps a position in the Morton-ordered pack to the triangle's index in the caller's mesh.
+// ------------------------------------------------------------------------------------------------
+
+// tie key of the reference's first-hit reduction (_utils.py:1865-1868, 1886): smaller wins.
+__device__ __forceinline__ uint32_t first_hit_tie_key(int64_t j, int64_t bs, int64_t T) {
+    if (bs <= 0 || bs >= T) return static_cast<uint32_t>(j);
+    const int64_t nb = (T + bs - 1) / bs;  // batches incl. the remainder batch
+    const int64_t b = j / bs;
+    return static_cast<uint32_t>((nb - 1 - b) * bs + (j - b * bs));
+}
+
+static __global__ void __launch_bounds__(kWalkWarps * 32, DRT_WALK_CTAS)
+ray_first_walk_kernel(const Tri48 *__restrict__ pack, const uint32_t *__restrict__ orig,
+                      const CullNode *__restrict__ nodes, const WalkLevels lv, const int64_t num_rays,
+                      const float *__restrict__ origins, const float *__restrict__ directions, const float eps,
+                      const int64_t batch_size, const int64_t num_triangles, int32_t *__restrict__ out_index,
+                      float *__restrict__ out_t, unsigned long long *cursor, int64_t *tests_done) {
+    __shared__ uint32_t node_stack_all[kWalkWarps][kWalkStack];
+    __shared__ uint32_t group_stack_all[kWalkWarps][kWalkGroupStack];
+    __shared__ int level_offset[kWalkMaxLevels], level_size[kWalkMaxLevels];
+    if (threadIdx.x < kWalkMaxLevels) {
+        level_offset[threadIdx.x] = lv.offset[threadIdx.x];
+        level_size[threadIdx.x] = lv.size[threadIdx.x];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *node_stack = node_stack_all[warp], *group_stack = group_stack_all[warp];
+    const int leaf = lv.num_levels - 1;
+    const int sub = lane & 7, slot = lane >> 3;
+    const bool fast_ok = eps >= 1.17549435e-38f;
+    constexpr int kChunk = DRT_WALK_CHUNK;
+    int64_t tests = 0;
+    while (true) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kChunk);
+        const int64_t unit0 = int64_t(__shfl_sync(kFull, base, 0));
+        if (unit0 >= num_rays) break;
+        const int64_t unit1 = unit0 + kChunk < num_rays ? unit0 + kChunk : num_rays;
+        for (int64_t ray = unit0; ray < unit1; ++ray) {
+            const float pv = lane < 3 ? origins[ray * 3 + lane] : (lane < 6 ? directions[ray * 3 + lane - 3] : 0.0f);
+            const float3 o = make_float3(__shfl_sync(kFull, pv, 0), __shfl_sync(kFull, pv, 1), __shfl_sync(kFull, pv, 2));
+            const float3 d = make_float3(__shfl_sync(kFull, pv, 3), __shfl_sync(kFull, pv, 4), __shfl_sync(kFull, pv, 5));
+            // warp-uniform running minimum
+            float best_t = CUDART_INF_F;
+            uint32_t best_key = 0xffffffffu;
+            int32_t best_idx = -1;
+            const bool dead = (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f) || !finite3(o) || !finite3(d);
+            if (!dead) {
+                const SegCull sc = make_ray_cull(o, d);
+                int nn = 1, ng = 0;
+                if (lane == 0) node_stack[0] = 0u;
+                __syncwarp();
+                while (nn > 0 || ng > 0) {
+                    if (ng >= 4 || nn == 0) {
+                        const int take = ng < 4 ? ng : 4;
+                        ng -= take;
+                        float t = CUDART_INF_F;
+                        uint32_t key = 0xffffffffu;
+                        int32_t idx = -1;
+                        if (slot < take) {
+                            const uint32_t pos = group_stack[ng + slot] * kCullGroup + sub;
+                            const float4 ta = pack[pos].a, tb = pack[pos].b, tc = pack[pos].c;
+                            const Tri tr = unpack(ta, tb, tc);
+                            bool weird = !fast_ok, hit = false;
+                            float tt = 0.0f;
+                            if (fast_ok) hit = mt_first_fast(o, d, tr, eps, tt, weird);
+                            if (weird) hit = mt_exact(o, d, tr, eps, tt);
+                            if (hit && tt <= best_t) {
+                                t = tt + 0.0f;  // -0 and +0 are the same distance: canonicalise
+                                idx = int32_t(orig[pos]);
+                                key = first_hit_tie_key(idx, batch_size, num_triangles);
+                            }
+                        }
+                        tests += take * kCullGroup;
+                        // warp minimum of (t, key): ordered bits of t, then the tie key
+                        const uint32_t tb_ = idx >= 0 ? float_order_bits(t) : 0xffffffffu;
+                        const uint32_t tmin = __reduce_min_sync(kFull, tb_);
+                        if (tmin != 0xffffffffu) {
+                            const uint32_t k2 = (tb_ == tmin) ? key : 0xffffffffu;
+                            const uint32_t kmin = __reduce_min_sync(kFull, k2);
+                            const unsigned owner = __ballot_sync(kFull, tb_ == tmin && k2 == kmin);
+                            const int src = __ffs(owner) - 1;
+                            const float wt = __shfl_sync(kFull, t, src);
+                            const int32_t widx = __shfl_sync(kFull, idx, src);
+                            if (wt < best_t || (wt == best_t && kmin < best_key)) {
+                                best_t = wt;
+                                best_key = kmin;
+                                best_idx = widx;
+                            }
+                        }
+                    } else {
+                        const int take = nn < 4 ? nn : 4;
+                        nn -= take;
+                        bool keep = false;
+                        uint32_t child = 0;
+                        int L = 0;
+                        if (slot < take) {
+                            const uint32_t e = node_stack[nn + slot];
+                            L = int(e >> 28);
+                            child = (e & 0x0fffffffu) * kWalkFan + sub;
+                            if (int(child) < level_size[L])
+                                keep = !node_culled(sc, nodes[level_offset[L] + child], best_t);
+                        }
+                        __syncwarp();
+                        const bool to_group = keep && L == leaf;
+                        const bool to_node = keep && L != leaf;
+                        const unsigned bg = __ballot_sync(kFull, to_group), bn = __ballot_sync(kFull, to_node);
+                        const unsigned below = (1u << lane) - 1u;
+                        if (to_group) group_stack[ng + __popc(bg & below)] = child;
+                        if (to_node) node_stack[nn + __popc(bn & below)] = (uint32_t(L + 1) << 28) | child;
+                        ng += __popc(bg);
+                        nn += __popc(bn);
+                        __syncwarp();
+                    }
+                }
+            }
+            if (lane == 0) {  // a "hit" at a non-finite distance is a miss (_utils.py:1957-1959)
+                const bool fin = isfinite(best_t);
+                out_index[ray] = fin ? best_idx : -1;
+                out_t[ray] = fin ? best_t : CUDART_INF_F;
+            }
+            __syncwarp();
+        }
+    }
+    if (tests_done != nullptr && lane == 0 && tests)
+        atomicAdd(reinterpret_cast<unsigned long long *>(tests_done), (unsigned long long)tests);
+}
+
 }  // namespace drt

@@ -95,6 +95,21 @@ def sort_pack_by_area(pack: torch.Tensor, num_triangles: int) -> torch.Tensor:
     return out
 
 
+def first_hit_launch(pack: torch.Tensor, T: int, o: torch.Tensor, d: torch.Tensor, eps: float, batch_size: int,
+                     idx: torch.Tensor, t: torch.Tensor) -> None:
+    """Nearest hit of ``R`` flat rays against a packed mesh (in the mesh's own triangle order) into
+    ``idx`` / ``t``: behind the exact conservative cull (``csrc/cull.cuh``, identical results) when the
+    mesh and the batch are large enough to pay for its hierarchy, else the all-pairs engine."""
+    R = int(o.shape[0])
+    if T > _CULL_MIN_TRIANGLES and R >= _CULL_MIN_RAYS:
+        ws = torch.empty(lib.drt_any_hit_workspace_bytes(T), dtype=torch.uint8, device=o.device)
+        check(lib.drt_first_triangle_hit_by_ray_culled(stream_ptr(), R, ptr(o), ptr(d), ptr(pack), T, eps, batch_size,
+                                                       ptr(ws), ws.numel(), ptr(idx), ptr(t), None))
+    else:
+        check(lib.drt_first_triangle_hit_by_ray(stream_ptr(), R, ptr(o), ptr(d), ptr(pack), T, eps, batch_size,
+                                                ptr(idx), ptr(t), None))
+
+
 def pack_normals(pack: torch.Tensor, num_triangles: int) -> torch.Tensor:
     """Unit normals stored in the pack (``Mesh.normals``, reference ``_mesh.py:950-956``)."""
     return pack.view(torch.float32).view(-1, 12)[:num_triangles, 9:12]
@@ -449,11 +464,7 @@ def first_triangle_hit_by_ray(
         pack = pack_triangle_vertices(tvc.detach(), None if acti is None else acti.contiguous())
         ii = torch.empty(oi.shape[0], dtype=torch.int32, device=o.device)
         ti = torch.empty(oi.shape[0], dtype=torch.float32, device=o.device)
-        check(
-            lib.drt_first_triangle_hit_by_ray(
-                stream_ptr(), oi.shape[0], ptr(oi), ptr(di), ptr(pack), T, eps, bs, ptr(ii), ptr(ti), None
-            )
-        )
+        first_hit_launch(pack, T, oi, di, eps, bs, ii, ti)
         if needs_grad and single:
             tris = torch.arange(3 * T, dtype=torch.int32, device=o.device).view(T, 3)
             ti = _FirstHitDistanceGrad.apply(ti, tvc.reshape(3 * T, 3), tris, oi, di, ii)
@@ -615,10 +626,18 @@ def triangles_visible_from_vertex(
     dirs = dirs.reshape(B, num_rays, 3).contiguous()
     pack = pack_triangle_vertices(tv, None if act is None else act.contiguous())
     vflat = vx.reshape(B, 3).contiguous()
+    eps = _default(kwargs.get("epsilon"), 10.0)
+    if T > _CULL_MIN_TRIANGLES and B * num_rays >= _CULL_MIN_RAYS:
+        # nearest hits behind the exact cull (identical to the all-pairs reduction), then the scatter
+        origins = vflat[:, None, :].expand(B, num_rays, 3).reshape(-1, 3).contiguous()
+        idx = torch.empty(B * num_rays, dtype=torch.int32, device=vx.device)
+        tt = torch.empty(B * num_rays, dtype=torch.float32, device=vx.device)
+        first_hit_launch(pack, T, origins, dirs.reshape(-1, 3), eps, 512, idx, tt)
+        check(lib.drt_scatter_visible(stream_ptr(), B, num_rays, T, ptr(idx), ptr(out)))
+        return pl.out(out.view(torch.bool))
     check(
         lib.drt_triangles_visible_from_vertex(
-            stream_ptr(), B, num_rays, ptr(vflat), ptr(dirs), ptr(pack), T,
-            _default(kwargs.get("epsilon"), 10.0), ptr(out), None,
+            stream_ptr(), B, num_rays, ptr(vflat), ptr(dirs), ptr(pack), T, eps, ptr(out), None,
         )
     )
     return pl.out(out.view(torch.bool))

@@ -136,7 +136,7 @@ def _first_hit(pack, T, o, d, eps, faces, t, bvh=None):
     if bvh is not None:  # opt-in accel="bvh"
         check(lib.drt_bvh_first_triangle_hit_by_ray(stream_ptr(), n, ptr(o), ptr(d), ptr(bvh), T, eps, 512, ptr(faces), ptr(t)))
     else:
-        check(lib.drt_first_triangle_hit_by_ray(stream_ptr(), n, ptr(o), ptr(d), ptr(pack), T, eps, 512, ptr(faces), ptr(t), None))
+        geometry.first_hit_launch(pack, T, o.reshape(n, 3), d.reshape(n, 3), eps, 512, faces, t)
 
 
 def launch_paths(

@@ -203,12 +203,7 @@ class Mesh:
             )
         else:
             pack = geometry.pack_mesh(self.vertices.detach(), self.triangles, self._mask_u8())
-            check(
-                lib.drt_first_triangle_hit_by_ray(
-                    stream_ptr(), R, ptr(of), ptr(df), ptr(pack), self.num_triangles, eps_, bs_, ptr(idx),
-                    ptr(t), None,
-                )
-            )
+            geometry.first_hit_launch(pack, self.num_triangles, of.detach(), df.detach(), eps_, bs_, idx, t)
         if torch.is_grad_enabled() and any(x.requires_grad for x in (of, df, self.vertices)):
             t = geometry._FirstHitDistanceGrad.apply(t, self.vertices, self.triangles, of, df, idx)
         return pl.out(idx.view(batch)), pl.out(t.view(batch))

@@ -146,6 +146,15 @@ DRT_API int drt_first_triangle_hit_by_ray(drt_stream_t stream, int64_t num_rays,
                                   int64_t num_triangles, float epsilon, int64_t batch_size,
                                   int32_t *out_index, float *out_t,
                                   int64_t *tests_done /*nullable*/);
+/* K3 behind the same exact cull (one warp per ray; a node is skipped only if it provably holds no hit
+ * at a distance <= the best so far, ties included): index and distance identical to the all-pairs
+ * reduction.  Falls back to it for meshes of <= 2048 triangles and for epsilon < FLT_MIN.  `pack` must
+ * be in the mesh's own triangle order (indices are reported).  workspace: drt_any_hit_workspace_bytes. */
+DRT_API int drt_first_triangle_hit_by_ray_culled(drt_stream_t stream, int64_t num_rays, const float *ray_origins,
+                                         const float *ray_directions, const void *pack,
+                                         int64_t num_triangles, float epsilon, int64_t batch_size,
+                                         void *workspace, size_t workspace_bytes, int32_t *out_index,
+                                         float *out_t, int64_t *tests_done /*nullable*/);
 DRT_API int drt_first_triangle_hit_by_ray_vjp(drt_stream_t stream, int64_t num_rays, int64_t num_vertices,
                                       int64_t num_triangles, const float *vertices,
                                       const int32_t *triangles, const float *ray_origins,

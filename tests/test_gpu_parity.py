@@ -240,6 +240,44 @@ def test_k3_first_hit_bit_exact(drt, rng, grid, n_rays, batch_size):
     assert np.isinf(t0[i0 == -1]).all()
 
 
+@pytest.mark.parametrize("batch_size", [512, 7, None])
+def test_k3_culled_first_hit_ties_general_mesh_and_masks(drt, rng, bruxelles, batch_size):
+    """The nearest-hit query behind the exact cull (meshes > 2048 triangles): exact ties on an
+    integer-lattice city (the tie rule picks the index), the reference's bruxelles.obj with half the
+    triangles masked, and the visibility scatter built on it — index AND distance bits vs the oracle."""
+    parts = [scenes.box(4.0, 4.0, 6.0, with_top=True, center=(8.0 * i, 8.0 * j, 3.0)) for i in range(15) for j in range(15)]
+    v, t = scenes._merge(parts)  # 2700 triangles on integer coordinates
+    tri = orc.triangle_vertices(v, t)
+    g = np.arange(-4, 122, 2, dtype=np.float32)
+    pts = np.stack(np.meshgrid(g, g, np.array([0.0, 3.0, 6.0, 7.0], np.float32), indexing="ij"), -1).reshape(-1, 3)
+    a, b = pts[rng.integers(0, pts.shape[0], 20000)], pts[rng.integers(0, pts.shape[0], 20000)]
+    o, d = a, (b - a).astype(np.float32)
+    ei, et = co.first_triangle_hit_by_ray(o, d, tri, batch_size=batch_size)
+    gi, gt = drt.first_triangle_hit_by_ray(o, d, tri, batch_size=batch_size)
+    np.testing.assert_array_equal(gi.numpy(), ei)
+    np.testing.assert_array_equal(bits(gt.numpy()), bits(et))
+    assert (ei >= 0).sum() > 5000
+    bv, bt = bruxelles
+    btri = orc.triangle_vertices(bv, bt)
+    active = rng.uniform(size=bt.shape[0]) < 0.5
+    o, d = scene_rays(rng, bv, 30_000)
+    ei, et = co.first_triangle_hit_by_ray(o, d, btri, active, batch_size=batch_size)
+    gi, gt = drt.first_triangle_hit_by_ray(o, d, btri, active, batch_size=batch_size)
+    np.testing.assert_array_equal(gi.numpy(), ei)
+    np.testing.assert_array_equal(bits(gt.numpy()), bits(et))
+    mesh = drt.Mesh.from_numpy(bv, bt, mask=active)
+    mi, mt_ = mesh.first_triangle_hit_by_ray(o, d, batch_size=batch_size)
+    np.testing.assert_array_equal(mi.cpu().numpy(), ei)
+    np.testing.assert_array_equal(bits(mt_.cpu().numpy()), bits(et))
+    if batch_size == 512:  # visibility = nearest hits + scatter, with shared directions
+        vertex = np.array([[60.0, 60.0, 30.0], [10.0, 100.0, 2.0]], np.float32)
+        dirs = rng.normal(size=(2, 3000, 3)).astype(np.float32)
+        exp = co.triangles_visible_from_vertex_dirs(vertex, dirs, tri)
+        got = drt.triangles_visible_from_vertex(vertex, tri, ray_directions=dirs)
+        np.testing.assert_array_equal(got.numpy(), exp)
+        assert exp.any()
+
+
 def test_k3_tie_rule_and_empty(drt):
     tri = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]]] * 3, np.float32)
     o = np.array([[0.2, 0.2, 1.0]], np.float32)
