@@ -49,8 +49,13 @@ __all__ = [
 
 # below this many rays an any-hit call is launch-bound and sorting the pack first does not pay
 _SORT_MIN_RAYS = 4096
-_CULL_MIN_TRIANGLES = 2048  # above this the flat any-hit goes through the exact cull (csrc/cull.cuh)
-_CULL_MIN_RAYS = 1024       # ... when there are enough rays to pay for building its hierarchy (~0.1 ms)
+_CULL_MIN_TRIANGLES = 2048  # above this the flat queries can go through the exact cull (csrc/cull.cuh)
+_CULL_MIN_WORK = 1 << 30    # ... when rays x triangles is large enough to pay for building its hierarchy
+#                             (~0.3 ms: 10 000 rays x 14 206 triangles, the reference's harness, stay all-pairs)
+
+
+def use_cull(num_rays: int, num_triangles: int) -> bool:
+    return num_triangles > _CULL_MIN_TRIANGLES and num_rays * num_triangles >= _CULL_MIN_WORK
 
 
 def _default(value, factor: float) -> float:
@@ -101,7 +106,7 @@ def first_hit_launch(pack: torch.Tensor, T: int, o: torch.Tensor, d: torch.Tenso
     ``idx`` / ``t``: behind the exact conservative cull (``csrc/cull.cuh``, identical results) when the
     mesh and the batch are large enough to pay for its hierarchy, else the all-pairs engine."""
     R = int(o.shape[0])
-    if T > _CULL_MIN_TRIANGLES and R >= _CULL_MIN_RAYS:
+    if use_cull(R, T):
         ws = torch.empty(lib.drt_any_hit_workspace_bytes(T), dtype=torch.uint8, device=o.device)
         check(lib.drt_first_triangle_hit_by_ray_culled(stream_ptr(), R, ptr(o), ptr(d), ptr(pack), T, eps, batch_size,
                                                        ptr(ws), ws.numel(), ptr(idx), ptr(t), None))
@@ -408,7 +413,7 @@ def ray_intersect_any_triangle(
         if oi.shape[0] >= _SORT_MIN_RAYS:
             pack = sort_pack_by_area(pack, T)
         res = torch.empty(oi.shape[0], dtype=torch.uint8, device=o.device)
-        if T > _CULL_MIN_TRIANGLES and oi.shape[0] >= _CULL_MIN_RAYS:
+        if use_cull(oi.shape[0], T):
             # same test, same results, behind the exact conservative cull (csrc/cull.cuh): O(log T) per ray
             ws = torch.empty(lib.drt_any_hit_workspace_bytes(T), dtype=torch.uint8, device=o.device)
             check(
@@ -627,7 +632,7 @@ def triangles_visible_from_vertex(
     pack = pack_triangle_vertices(tv, None if act is None else act.contiguous())
     vflat = vx.reshape(B, 3).contiguous()
     eps = _default(kwargs.get("epsilon"), 10.0)
-    if T > _CULL_MIN_TRIANGLES and B * num_rays >= _CULL_MIN_RAYS:
+    if use_cull(B * num_rays, T):
         # nearest hits behind the exact cull (identical to the all-pairs reduction), then the scatter
         origins = vflat[:, None, :].expand(B, num_rays, 3).reshape(-1, 3).contiguous()
         idx = torch.empty(B * num_rays, dtype=torch.int32, device=vx.device)

@@ -158,7 +158,7 @@ class Mesh:
         pack = geometry.pack_mesh(self.vertices.detach(), self.triangles, self._mask_u8())
         if R >= geometry._SORT_MIN_RAYS:
             pack = geometry.sort_pack_by_area(pack, self.num_triangles)
-        if self.num_triangles > geometry._CULL_MIN_TRIANGLES and R >= geometry._CULL_MIN_RAYS:
+        if geometry.use_cull(R, self.num_triangles):
             # same test, same results, behind the exact conservative cull (csrc/cull.cuh)
             ws = torch.empty(lib.drt_any_hit_workspace_bytes(self.num_triangles), dtype=torch.uint8, device=o.device)
             check(

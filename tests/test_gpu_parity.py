@@ -170,11 +170,13 @@ def test_k2_counts_tests(drt, rng):
     assert int(cnt.item()) == 1000 * 512
 
 
-def test_k2_culled_any_hit_equals_all_pairs_and_oracle(drt, rng, bruxelles):
+def test_k2_culled_any_hit_equals_all_pairs_and_oracle(drt, rng, bruxelles, monkeypatch):
     """The flat any-hit behind the exact cull: same bits as the all-pairs engine and the oracle, on the
     urban grid, on the reference's bruxelles.obj (a general, non axis-aligned mesh) and on the coplanar
     clusters that produce noise hits far from the triangles — with a fraction of the tests."""
-    from differt_b200 import _lib
+    from differt_b200 import _lib, geometry
+
+    monkeypatch.setattr(geometry, "_CULL_MIN_WORK", 0)  # the public API takes the culled path at any size
     from differt_b200._tensor import ptr, stream_ptr
     from differt_b200.geometry import pack_triangle_vertices, sort_pack_by_area
 
@@ -241,10 +243,13 @@ def test_k3_first_hit_bit_exact(drt, rng, grid, n_rays, batch_size):
 
 
 @pytest.mark.parametrize("batch_size", [512, 7, None])
-def test_k3_culled_first_hit_ties_general_mesh_and_masks(drt, rng, bruxelles, batch_size):
+def test_k3_culled_first_hit_ties_general_mesh_and_masks(drt, rng, bruxelles, batch_size, monkeypatch):
     """The nearest-hit query behind the exact cull (meshes > 2048 triangles): exact ties on an
     integer-lattice city (the tie rule picks the index), the reference's bruxelles.obj with half the
     triangles masked, and the visibility scatter built on it — index AND distance bits vs the oracle."""
+    from differt_b200 import geometry
+
+    monkeypatch.setattr(geometry, "_CULL_MIN_WORK", 0)  # the public API takes the culled path at any size
     parts = [scenes.box(4.0, 4.0, 6.0, with_top=True, center=(8.0 * i, 8.0 * j, 3.0)) for i in range(15) for j in range(15)]
     v, t = scenes._merge(parts)  # 2700 triangles on integer coordinates
     tri = orc.triangle_vertices(v, t)
