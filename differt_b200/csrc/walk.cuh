@@ -38,7 +38,7 @@ namespace drt {
 #define DRT_WALK_HEAD_ROWS 1
 #endif
 #ifndef DRT_WALK_MIN_TILES
-#define DRT_WALK_MIN_TILES 4
+#define DRT_WALK_MIN_TILES 1
 #endif
 constexpr int kCullHead = DRT_WALK_MIN_TILES;  // meshes with more tiles than this take the culled traversal
 constexpr int kWalkWarps = DRT_WALK_WARPS;

@@ -124,7 +124,7 @@ DRT_API int drt_ray_intersect_any_triangle(drt_stream_t stream, int64_t num_rays
 /* K2 with the exact conservative cull of csrc/cull.cuh in front of the same Möller–Trumbore test: a warp
  * per ray walks an 8-ary hierarchy over the Morton-ordered pack and only evaluates the triangles the
  * cull cannot PROVE to be misses — identical results, O(log T) instead of O(T) per ray.  Falls back to
- * the all-pairs engine for meshes of <= 2048 triangles and for epsilon < FLT_MIN or hit_tol outside
+ * the all-pairs engine for meshes of <= 512 triangles and for epsilon < FLT_MIN or hit_tol outside
  * [0, 1) (outside the proof).  `pack` as above (its first 32 records are tested first: pass an
  * area-sorted pack when you have one).  workspace: drt_any_hit_workspace_bytes(num_triangles). */
 DRT_API size_t drt_any_hit_workspace_bytes(int64_t num_triangles);
@@ -148,7 +148,7 @@ DRT_API int drt_first_triangle_hit_by_ray(drt_stream_t stream, int64_t num_rays,
                                   int64_t *tests_done /*nullable*/);
 /* K3 behind the same exact cull (one warp per ray; a node is skipped only if it provably holds no hit
  * at a distance <= the best so far, ties included): index and distance identical to the all-pairs
- * reduction.  Falls back to it for meshes of <= 2048 triangles and for epsilon < FLT_MIN.  `pack` must
+ * reduction.  Falls back to it for meshes of <= 512 triangles and for epsilon < FLT_MIN.  `pack` must
  * be in the mesh's own triangle order (indices are reported).  workspace: drt_any_hit_workspace_bytes. */
 DRT_API int drt_first_triangle_hit_by_ray_culled(drt_stream_t stream, int64_t num_rays, const float *ray_origins,
                                          const float *ray_directions, const void *pack,
