@@ -21,7 +21,7 @@ __device__ __forceinline__ void store_tri(Tri48 *out, float3 v0, float3 v1, floa
 __device__ __forceinline__ void store_never_hit(Tri48 *out) {
     // NaN origin: every comparison of the intersection test is false
     const float q = CUDART_NAN_F;
-    out->a = make_float4(q, q, q, 0.f);
+    out->a = make_float4(__uint_as_float(kNeverHitBits), q, q, 0.f);
     out->b = make_float4(0.f, 0.f, 0.f, 0.f);
     out->c = make_float4(0.f, 0.f, 0.f, 0.f);
 }

@@ -91,7 +91,7 @@ any_smooth_kernel(int64_t R, int64_t T, const float *__restrict__ o, const float
     float acc = 0.0f;
     for (int64_t j = lane; j < T; j += 32) {
         const float4 a = pack[j].a, b = pack[j].b, c = pack[j].c;
-        if (a.x != a.x && a.y != a.y && a.z != a.z && a.w == 0.0f) continue;  // never-hit record: inactive
+        if (is_never_hit(a)) continue;  // never-hit record: inactive
         float t;
         acc += mt_smooth(oo, dd, unpack(a, b, c), eps, alpha, t, true, thr);
     }
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) trace_smooth_blocked_kernel(const SmoothT
         }
         for (int64_t j = lane; j < a.T; j += 32) {
             const float4 ra = a.pack_active[j].a, rb = a.pack_active[j].b, rc = a.pack_active[j].c;
-            if (ra.x != ra.x && ra.y != ra.y && ra.z != ra.z && ra.w == 0.0f) continue;  // inactive
+            if (is_never_hit(ra)) continue;  // inactive
             const Tri tr = unpack(ra, rb, rc);
 #pragma unroll
             for (int s = 0; s < NSEG; ++s) {
@@ -408,7 +408,7 @@ any_smooth_vjp_kernel(int64_t R, int64_t T, const float *__restrict__ o, const f
     float acc = 0.0f;
     for (int64_t j = lane; j < T; j += 32) {
         const float4 a = pack[j].a, b = pack[j].b, c = pack[j].c;
-        if (a.x != a.x && a.y != a.y && a.z != a.z && a.w == 0.0f) continue;
+        if (is_never_hit(a)) continue;
         float t;
         acc += mt_smooth(oo, dd, unpack(a, b, c), eps, alpha, t, true, thr);
     }
@@ -419,7 +419,7 @@ any_smooth_vjp_kernel(int64_t R, int64_t T, const float *__restrict__ o, const f
     if (acc < 1.0f && g != 0.0f && g == g) {
         for (int64_t j = lane; j < T; j += 32) {
             const float4 a = pack[j].a, b = pack[j].b, c = pack[j].c;
-            if (a.x != a.x && a.y != a.y && a.z != a.z && a.w == 0.0f) continue;
+            if (is_never_hit(a)) continue;
             MtGrad mg;
             if (mt_smooth_adjoint(oo, dd, unpack(a, b, c), eps, alpha, thr, 2, g, 0.0f, mg)) {
                 go = add3(go, mg.o);
@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(256) trace_smooth_vjp_blocked_kernel(const Smo
     }
     for (int64_t j = lane; j < fa.T; j += 32) {
         const float4 ra = fa.pack_active[j].a, rb = fa.pack_active[j].b, rc = fa.pack_active[j].c;
-        if (ra.x != ra.x && ra.y != ra.y && ra.z != ra.z && ra.w == 0.0f) continue;
+        if (is_never_hit(ra)) continue;
         const Tri tr = unpack(ra, rb, rc);
 #pragma unroll
         for (int s = 0; s < NSEG; ++s) {
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(256) trace_smooth_vjp_blocked_kernel(const Smo
     float3 go = make_float3(0.f, 0.f, 0.f), gd = make_float3(0.f, 0.f, 0.f);
     for (int64_t j = lane; j < fa.T; j += 32) {
         const float4 ra = fa.pack_active[j].a, rb = fa.pack_active[j].b, rc = fa.pack_active[j].c;
-        if (ra.x != ra.x && ra.y != ra.y && ra.z != ra.z && ra.w == 0.0f) continue;
+        if (is_never_hit(ra)) continue;
         MtGrad mg;
         if (mt_smooth_grad(os, ds, unpack(ra, rb, rc), fa.eps, fa.alpha, fa.thr, true, g, mg)) {
             go = add3(go, mg.o);

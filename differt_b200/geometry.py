@@ -463,6 +463,11 @@ def first_triangle_hit_by_ray(
     ob, db = o.expand(*batch, 3), d.expand(*batch, 3)
     needs_grad = torch.is_grad_enabled() and any(x.requires_grad for x in (o, d, tv))
     single = numel(torch.broadcast_shapes(tv.shape[:-3], () if act is None else act.shape[:-1])) == 1
+    if needs_grad and not single:
+        # the reference's t is differentiable in every case; dropping the gradient silently is worse
+        # than refusing (the relaxed any-hit does the same)
+        raise NotImplementedError("gradient of first_triangle_hit_by_ray over a BATCH of meshes is not built; "
+                                  "loop over the meshes or detach the inputs")
     for sel, tvi, acti in _mesh_batches(batch, tv, act):
         oi, di = ob[sel].reshape(-1, 3).contiguous(), db[sel].reshape(-1, 3).contiguous()
         tvc = tvi.contiguous()
