@@ -685,8 +685,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         achieved = inst["blockage_warp_instructions_per_step"] / (kms * 1e-3) if inst and kms else None
         peaks_file = ROOT / "MEASURED_PEAKS.json"
         hbm_peak = float(json.loads(peaks_file.read_text())["hbm_gbs"]) if peaks_file.exists() else 6650.0
-        traffic_file = ROOT / "profiles" / "traffic.json"
-        traffic = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch") if traffic_file.exists() else None
+        # DRAM bytes of the blockage kernels per step, from the same ncu launch list as the instruction counts
+        traffic = (inst or {}).get("blockage_dram_bytes_per_step") or None
         roofline = {
             "kernel": "blockage pass = drt::path_head_kernel<order+1> (resident head tiles, every candidate) + "
                       "drt::path_cull_kernel<order+1> (exact culled pass over the whole mesh, undecided candidates) "

@@ -344,7 +344,8 @@ def _mesh_batches(batch, tv, active):
     ab = None if active is None else active.expand(*mesh_batch, active.shape[-1])
     for idx in np.ndindex(*mesh_batch):
         sel = tuple(slice(None) for _ in range(lead)) + tuple(
-            slice(i, i + 1) if batch[lead + a] != 1 else slice(None) for a, i in enumerate(idx)
+            # a mesh-batch axis of size 1 broadcasts against the whole batch axis
+            slice(i, i + 1) if mesh_batch[a] != 1 else slice(None) for a, i in enumerate(idx)
         )
         yield sel, tvb[idx], None if ab is None else ab[idx]
 
@@ -619,37 +620,48 @@ def triangles_visible_from_vertex(
     vx = pl.put(vertex, torch.float32)
     tv = pl.put(triangle_vertices, torch.float32)
     act = None if active_triangles is None else pl.put(active_triangles, torch.uint8)
-    if tv.ndim != 3 or (act is not None and act.ndim != 1):
-        raise NotImplementedError("triangles_visible_from_vertex: one shared mesh [T,3,3] only")
-    T = int(tv.shape[0])
-    batch = tuple(vx.shape[:-1])
+    T = int(tv.shape[-3])
+    # reference broadcasting (_utils.py:1540-1548): vertex [*#b,3], triangles [*#b,T,3,3], active [*#b,T]
+    batch = tuple(torch.broadcast_shapes(vx.shape[:-1], tv.shape[:-3], () if act is None else act.shape[:-1]))
     B = numel(batch)
     out = torch.zeros((*batch, T), dtype=torch.uint8, device=vx.device)
     if T == 0 or B == 0:
         return pl.out(out.view(torch.bool))
-    tv = tv.contiguous()
-    if ray_directions is None:
-        dirs = visibility_directions(vx.reshape(B, 3), tv, act, num_rays)
-    else:
-        dirs = pl.put(ray_directions, torch.float32)
-        num_rays = int(dirs.shape[-2])
-    dirs = dirs.reshape(B, num_rays, 3).contiguous()
-    pack = pack_triangle_vertices(tv, None if act is None else act.contiguous())
-    vflat = vx.reshape(B, 3).contiguous()
+    vb = vx.expand(*batch, 3)
+    dirs_all = None
+    if ray_directions is not None:
+        dirs_all = pl.put(ray_directions, torch.float32)
+        num_rays = int(dirs_all.shape[-2])
+        dirs_all = dirs_all.expand(*batch, num_rays, 3)
     eps = _default(kwargs.get("epsilon"), 10.0)
-    if use_cull(B * num_rays, T):
-        # nearest hits behind the exact cull (identical to the all-pairs reduction), then the scatter
-        origins = vflat[:, None, :].expand(B, num_rays, 3).reshape(-1, 3).contiguous()
-        idx = torch.empty(B * num_rays, dtype=torch.int32, device=vx.device)
-        tt = torch.empty(B * num_rays, dtype=torch.float32, device=vx.device)
-        first_hit_launch(pack, T, origins, dirs.reshape(-1, 3), eps, 512, idx, tt)
-        check(lib.drt_scatter_visible(stream_ptr(), B, num_rays, T, ptr(idx), ptr(out)))
-        return pl.out(out.view(torch.bool))
-    check(
-        lib.drt_triangles_visible_from_vertex(
-            stream_ptr(), B, num_rays, ptr(vflat), ptr(dirs), ptr(pack), T, eps, ptr(out), None,
-        )
-    )
+    for sel, tvi, acti in _mesh_batches(batch, tv, act):  # one launch per distinct mesh of the batch
+        vi = vb[sel].reshape(-1, 3).contiguous()
+        Bi = int(vi.shape[0])
+        if Bi == 0:
+            continue
+        tvi = tvi.contiguous()
+        acti = None if acti is None else acti.contiguous()
+        if dirs_all is None:
+            dirs = visibility_directions(vi, tvi, acti, num_rays)
+        else:
+            dirs = dirs_all[sel]
+        dirs = dirs.reshape(Bi, num_rays, 3).contiguous()
+        pack = pack_triangle_vertices(tvi, acti)
+        res = torch.zeros((Bi, T), dtype=torch.uint8, device=vx.device)
+        if use_cull(Bi * num_rays, T):
+            # nearest hits behind the exact cull (identical to the all-pairs reduction), then the scatter
+            origins = vi[:, None, :].expand(Bi, num_rays, 3).reshape(-1, 3).contiguous()
+            idx = torch.empty(Bi * num_rays, dtype=torch.int32, device=vx.device)
+            tt = torch.empty(Bi * num_rays, dtype=torch.float32, device=vx.device)
+            first_hit_launch(pack, T, origins, dirs.reshape(-1, 3), eps, 512, idx, tt)
+            check(lib.drt_scatter_visible(stream_ptr(), Bi, num_rays, T, ptr(idx), ptr(res)))
+        else:
+            check(
+                lib.drt_triangles_visible_from_vertex(
+                    stream_ptr(), Bi, num_rays, ptr(vi), ptr(dirs), ptr(pack), T, eps, ptr(res), None,
+                )
+            )
+        out[sel] = res.view(out[sel].shape)
     return pl.out(out.view(torch.bool))
 
 

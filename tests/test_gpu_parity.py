@@ -403,6 +403,34 @@ def test_k4_bit_exact_with_shared_directions(drt, rng):
     assert exp.any() and not exp[:, ~active].any()
 
 
+def test_k4_batched_meshes_and_masks_follow_the_reference_broadcasting(drt, rng):
+    """`triangles_visible_from_vertex(vertex [*#b,3], triangles [*#b,T,3,3], active [*#b,T])`
+    (reference `_utils.py:1540-1548`): a batch of meshes / masks broadcast against a batch of vertices,
+    each batch element equal to the single-mesh call and to the oracle (shared ray directions)."""
+    v, t = scenes.street_canyon(3)
+    base = orc.triangle_vertices(v, t)
+    T = base.shape[0]
+    meshes = np.stack([base, base + np.float32([5.0, 0.0, 0.0]), base * np.float32(1.5)])      # [3,T,3,3]
+    masks = np.stack([np.ones(T, bool), rng.uniform(size=T) < 0.6])                              # [2,T]
+    vertices = rng.uniform([0, -8, 1], [25, 8, 30], size=(2, 1, 3)).astype(np.float32)          # [2,1,3]
+    dirs = rng.normal(size=(400, 3)).astype(np.float32)
+    # batch = broadcast([2,1], [3], [2,1]→masks as [2,1,T]) = [2,3]
+    got = drt.triangles_visible_from_vertex(vertices, meshes[None], masks[:, None, :], ray_directions=dirs)
+    assert tuple(got.shape) == (2, 3, T)
+    for i in range(2):
+        for j in range(3):
+            exp = co.triangles_visible_from_vertex_dirs(vertices[i, 0], dirs[None], meshes[j], masks[i])
+            np.testing.assert_array_equal(got[i, j].numpy(), exp[0])
+            one = drt.triangles_visible_from_vertex(vertices[i, 0], meshes[j], masks[i], ray_directions=dirs)
+            np.testing.assert_array_equal(one.numpy(), exp[0])
+    assert got.any() and not got.all()
+    # generated directions (frustum + Fibonacci lattice per mesh): batched call == per-mesh calls
+    gen = drt.triangles_visible_from_vertex(vertices, meshes[None], num_rays=2000)
+    for j in range(3):
+        np.testing.assert_array_equal(gen[:, j].numpy(),
+                                      drt.triangles_visible_from_vertex(vertices[:, 0], meshes[j], num_rays=2000).numpy())
+
+
 def test_ray_generation_matches_oracle(drt, rng):
     v, t = scenes.urban_grid(2, 2)
     tri = orc.triangle_vertices(v, t)

@@ -23,4 +23,22 @@ n5 = 1 << 22
 mv = tv[:n5].contiguous(); mn = torch.nn.functional.normalize(tv[n5:2 * n5], dim=-1).contiguous()
 for _ in range(2):
     drt.image_method(o[:n5], d[:n5], mv, mn)
+# flat queries at 2^18 rays x 10 094 triangles: the all-pairs engine (C ABI) and the culled traversal
+from differt_b200._lib import check, lib
+from differt_b200._tensor import ptr, stream_ptr
+from differt_b200.geometry import pack_mesh, sort_pack_by_area
+R, T = 1 << 18, wl["triangles"].shape[0]
+lo, hi = wl["vertices"].min(0), wl["vertices"].max(0)
+ro = rng.uniform(lo, hi, size=(R, 3)).astype(np.float32); re = rng.uniform(lo, hi, size=(R, 3)).astype(np.float32)
+ro[:, 2] = rng.uniform(0.5, 45.0, R); re[:, 2] = rng.uniform(0.5, 45.0, R)
+ro_d, rd_d = torch.from_numpy(ro).to(dev), torch.from_numpy((re - ro).astype(np.float32)).to(dev)
+pack = pack_mesh(mesh.vertices.detach(), mesh.triangles, None)
+spack = sort_pack_by_area(pack, T)
+hit = torch.empty(R, dtype=torch.uint8, device=dev); idx = torch.empty(R, dtype=torch.int32, device=dev); tt = torch.empty(R, device=dev)
+ws = torch.empty(lib.drt_any_hit_workspace_bytes(T), dtype=torch.uint8, device=dev)
+for _ in range(2):
+    check(lib.drt_ray_intersect_any_triangle(stream_ptr(), R, ptr(ro_d), ptr(rd_d), ptr(spack), T, 1.19e-6, 1.19e-5, ptr(hit), None))
+    check(lib.drt_first_triangle_hit_by_ray(stream_ptr(), R, ptr(ro_d), ptr(rd_d), ptr(pack), T, 1.19e-6, 512, ptr(idx), ptr(tt), None))
+    check(lib.drt_ray_intersect_any_triangle_culled(stream_ptr(), R, ptr(ro_d), ptr(rd_d), ptr(spack), T, 1.19e-6, 1.19e-5, ptr(ws), ws.numel(), ptr(hit), None))
+    check(lib.drt_first_triangle_hit_by_ray_culled(stream_ptr(), R, ptr(ro_d), ptr(rd_d), ptr(pack), T, 1.19e-6, 512, ptr(ws), ws.numel(), ptr(idx), ptr(tt), None))
 torch.cuda.synchronize()
