@@ -338,15 +338,13 @@ def run_reference(args, rank: int) -> None:
 
 
 def launches_per_step(wl: dict, with_vjp: bool) -> int:
-    """Kernels of OURS launched per step (CUB's radix-sort kernels are not counted): pack, area keys +
-    gather, the cull structure (bounds, keys, iota + gather, group nodes, tile nodes), stage A, the
-    ordering pass (hit count, iota + gather, sample list, set, then per greedy round: resident pass on
-    the samples, hit count, iota + gather), the stats marker, the resident head pass, the culled pass,
-    3 compaction kernels, the VJP.  profiles/inst_counts.json holds the ncu-counted figure."""
+    """Kernels of OURS launched per steady-state step when profiles/inst_counts.json (the ncu-counted
+    figure) has no entry for the workload: stage A, the culled traversal (meshes > 512 triangles; the
+    ordering pass + cascade of resident passes below that), the stats marker, 3 compaction kernels, the
+    VJP.  The mesh-only kernels (packs, sorts, hierarchy: ~14 launches) run once per mesh state."""
     tiles = -(-int(wl["triangles"].shape[0]) // 512)
-    rounds = min(4, tiles - 1)
-    cull = 6 if tiles > 4 else 0
-    return 1 + 2 + cull + 1 + (3 + 2 + 4 * rounds + 1) + 1 + (1 if cull else -(-tiles // 8) - 1) + 3 + (1 if with_vjp else 0)
+    blockage = 2 if tiles > 1 else 1 + 3 + 2
+    return 1 + blockage + 3 + (1 if with_vjp else 0)
 
 
 def workload_config(wl: dict, world: int, **extra) -> dict:
