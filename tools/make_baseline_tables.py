@@ -1,76 +1,122 @@
-"""Regenerate BASELINE.md sections 5-6 and profiles/traffic.json from the JSON artefacts under profiles/
-(round-1 bookkeeping script; paths are relative to /root/repo)."""
-import json,re
-json.dump({
- "source": "profiles/r1_ncu_dram_traffic_bench_workload.csv (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum; bench workload urban10k_1tx_4096rx_order3; 30 consecutive launches of the blockage kernels = a little more than one step)",
- "dram_bytes_per_launch": 2071018240 + 24238336,
- "per_kernel": {
-   "path_head_kernel<4> (16 launches: cascade passes over all candidates + greedy-round passes over the samples)": {"dram_bytes": 2071018240, "ns": 89383232},
-   "hit_count_kernel<4> (14 launches: ordering pass rounds)": {"dram_bytes": 24238336, "ns": 10832832}},
- "note": "the blockage pass reads the 1.0 GB of path vertices written by stage A (60 B per candidate, fetched as partial 32 B sectors) and writes the mask bytes and the survivor lists; the packed mesh never comes from DRAM",
- "dram_bytes_per_launch_note": "per step = per bracketed blockage pass (the unit roofline.achieved uses)"
-}, open('/root/repo/profiles/traffic.json','w'), indent=1)
-p='/root/repo/bench.py'
-s=open(p).read()
-s=s.replace('''            # pack, area keys + gather, stage A, head pass, ring pass, 3 compaction kernels per step
-            # (+ 4 CUB radix-sort kernels, not counted as ours)
-            "gpu_launches": args.steps * 9,''','''            # per step: pack, area keys + gather, stage A, hit-count + iota + gather (ordering pass),
-            # head pass, ring pass, 3 compaction kernels (+ 8 CUB radix-sort kernels, not counted as ours)
-            "gpu_launches": args.steps * 12,''')
-open(p,'w').write(s)
+"""Regenerate BASELINE.md §5-§6 (measured results, per-kernel table) from the JSON lines under profiles/.
+Read-only for everything except BASELINE.md."""
+import json
+from pathlib import Path
 
-b=open('/root/repo/BASELINE.md').read()
-b=b[:b.index('## 5. Measured results')]
-d=json.load(open('/root/repo/profiles/r1_bench_v7.json'))
-n2=json.load(open('/root/repo/profiles/r1_bench_v7_n2.json'))
-n8=json.load(open('/root/repo/profiles/r1_bench_v6_n8.json'))
-ref=json.load(open('/root/repo/profiles/r1_bench_reference_arm.json')); ref['value']=d['cpu_baseline']['value']; ref['cpu_baseline']=d['cpu_baseline']
-big=json.load(open('/root/repo/profiles/r1_bench_v3_urban50k_order4.json'))
+ROOT = Path(__file__).resolve().parent.parent
+P = ROOT / "profiles"
+
+
+def load(name):
+    f = P / name
+    return json.loads(f.read_text()) if f.exists() else None
+
+
 def fmt(x):
-    m,e=f"{x:.2e}".split("e"); return f"{m}·10^{int(e)}"
-sec5=f'''## 5. Measured results (round 1, NVIDIA B200 @ 1965 MHz, `profiles/`)
+    m, e = f"{x:.2e}".split("e")
+    return f"{m}·10^{int(e)}"
 
-Workload = config 3 (urban grid 10 094 triangles, 1 TX × 4096 RX, order 3, 4096 candidates per GPU,
-every candidate blockage-tested like the reference): 1.68·10^7 candidate-pairs, 6.7·10^7 rays,
-6.77·10^11 (ray, triangle) pairs per step per GPU.  `python bench.py` / `torchrun ... bench.py --gpus N`.
-`value` counts the pairs DECIDED (SURVEY §8d); "executed" counts the Möller–Trumbore evaluations
-actually run (the any-hit query stops at the first blocking row of triangles).
 
-| arm | GPUs | step | pairs decided /s (`value`) | executed tests /s | candidate-pairs /s | executed × 36 B vs 6549 GB/s | FP32 issue slots |
-|---|---|---|---|---|---|---|---|
-| differt_b200, inputs resident | 1 | {d['ms_per_step']:.0f} ms | {fmt(d['value'])} | {fmt(d['executed_tests_per_s'])} | {fmt(d['candidate_pairs_per_s'])} | {d['roofline']['frac']:.2f} | {d['roofline']['fp32_issue']['frac']:.2f} |
-| differt_b200, end to end from host buffers | 1 | {d['e2e']['ms_per_step']:.0f} ms | {fmt(d['e2e']['value'])} | {fmt(d['e2e']['executed_tests_per_s'])} | — | — | — |
-| differt_b200, weak scaling | 2 | {n2['ms_per_step']:.0f} ms | {fmt(n2['value'])} | {fmt(n2['executed_tests_per_s'])} | {fmt(n2['candidate_pairs_per_s'])} | — | — |
-| differt_b200, weak scaling | 8 | {n8['ms_per_step']:.0f} ms | {fmt(n8['value'])} | {fmt(n8['executed_tests_per_s'])} | {fmt(n8['candidate_pairs_per_s'])} | — | — |
-| differt_b200, API default mode (blockage only for candidates passing the cheap tests; identical outputs) | 1 | {d['default_mode']['ms_per_step']:.2f} ms | — | — | {fmt(d['default_mode']['candidate_pairs_per_s'])} | — | — |
-| reference algorithm restated on CPU (C/OpenMP/AVX2 port; JAX/Warp not installable), {ref['cpu_baseline']['cores']} host cores, dense | 0 | — | {fmt(ref['value'])} | {fmt(ref['value'])} | — | — | — |
+def main():
+    b = (ROOT / "BASELINE.md").read_text()
+    b = b[: b.index("## 5. Measured results")]
+    d = load("r2_bench_final_n1.json")
+    ref = load("r2_bench_final_reference_arm.json")
+    strong = {n: load(f"r2_bench_strong_n{n}.json") for n in (1, 2, 4, 8)}
+    rows = []
+    for n, s in strong.items():
+        if s is None:
+            continue
+        eff = s["value"] / strong[1]["value"] / n
+        k = s["roofline"]["kernel_ms_over_ranks"] if "kernel_ms_over_ranks" in s["roofline"] else None
+        weak = (s.get("weak_scaling") or {}).get("ms_per_step")
+        rows.append(f"| differt_b200, strong scaling (fixed config 3, receivers dealt block-cyclically) | {n} | {s['ms_per_step']:.2f} ms | "
+                    f"{fmt(s['value'])} | {fmt(s['executed_tests_per_s'])} | {fmt(s['candidate_pairs_per_s'])} | {eff:.3f} | "
+                    f"{(('%.2f / %.2f ms' % (k['max'], k['min'])) if k else '—')} | {('%.1f ms' % weak) if weak else '—'} |")
+    cb = d["cpu_baseline"]
+    sec5 = f"""## 5. Measured results (round 2, NVIDIA B200 @ 1965 MHz, `profiles/r2_*`)
 
-Other configurations (`--workload`): config 5 per GPU (49 922 triangles, 1 × 16 384 RX, order 4, 2048
-candidates: 3.4·10^7 candidate-pairs, 8.4·10^12 pairs per step): {big['ms_per_step']:.0f} ms per step,
-{fmt(big['value'])} pairs decided /s, {fmt(big['executed_tests_per_s'])} executed tests /s (fraction
-{big['executed_fraction_of_algorithmic']:.3f}).  Config 2 end to end (986 triangles, 1 × 256 RX, ALL 971 210 order-2
-candidates decoded on the device, compact kernel, valid paths merged in reference order): see the
-"config 2" row of §6.  Config 4 per GPU (16 TX × 4096 RX, order 3, 512 of the 4096 candidates = the
-shard one of 8 GPUs gets: 3.4·10^7 candidate-pairs): 202 ms per step, 6.7·10^12 pairs decided /s,
-4.3·10^11 executed tests /s, default mode 1.0 ms.
+Workload = config 3 (urban grid 10 094 triangles, 1 TX × 4096 RX, order 3, 4096 candidates, every candidate
+blockage-decided like the reference, forward + VJP + compaction): 1.68·10^7 candidate-pairs, 6.7·10^7 rays,
+6.77·10^11 (ray, triangle) pairs per step.  `python bench.py` / `torchrun ... bench.py --gpus N`; the problem is
+the same for every N (strong scaling).  `value` counts the pairs DECIDED (SURVEY §8d) in BOTH arms — both stop a
+candidate at its first blocker; "executed" counts the Möller–Trumbore evaluations actually run.
 
-North-star floor (10^9 tests/s per B200 at ≥ 60 % of the HBM roofline ⇔ 1.09·10^11 tests/s): exceeded
-≈4× on executed tests and ≈50× on decided pairs.  Progression within the round (same workload, step
-time): 1198 → 649 → 576 → 288 → 138 → 127 → 117 → 109 → 97 → 95 ms (`profiles/README.md`, `DESIGN.md` §4).
-'''
-k=json.load(open('/root/repo/profiles/r1_kernels.json'))
-lines=["## 6. Per-kernel timings (round 1, `tools/bench_kernels.py`, `profiles/r1_kernels.json`)","",
-'CUDA events, 3 warm-ups, median of 10, B200 @ 1965 MHz, through the Python API unless marked "kernel only".  `GB/s` = algorithmic bytes (SURVEY §8d per-unit figures) ÷ time; fraction against the measured 6549 GB/s copy bandwidth.  The all-pairs kernels are FP32-issue bound (DESIGN.md §4): their `GB/s` is the streamed-operand model (36 B per executed test) and can exceed 1.  Kernel-only `ncu` times of the HBM-bound kernels: K1 193 µs (5.6 TB/s DRAM, 86 % of peak), K5 121 µs (66 %), stage A 461 µs (2.8 TB/s, 43 %), K6b 878 µs (compute-bound at 168 registers).',"",
-"| kernel | ms | throughput | GB/s | frac of HBM peak | note |","|---|---|---|---|---|---|"]
-for r in k["rows"]:
-    thr=[(kk,v) for kk,v in r.items() if kk.endswith("_per_s")][0]
-    g=r.get('gbs'); f=r.get('frac_of_hbm_peak')
-    lines.append(f"| {r['kernel']} | {r['ms']:.3f} | {thr[1]:.3g} {thr[0].replace('_per_s','')}/s | {('%.0f'%g) if g else '—'} | {('%.2f'%f) if f else '—'} | {r['note']} |")
-# the relaxed (smoothing_factor) trace, measured separately (tools/bench_relaxed.py)
-rl=json.load(open('/root/repo/profiles/r1_relaxed_trace.json'))
-lines+=["","### Relaxed (`smoothing_factor`) trace, forward and reverse mode (`tools/bench_relaxed.py`, `profiles/r1_relaxed_trace.json`)","",
-"Street canyon (986 triangles), 1 TX × 256 RX × 4096 sampled order-2 candidates = 1.05·10⁶ paths; the relaxed blockage is a clipped SUM over all triangles, so all 3.1·10⁹ (segment, triangle) pairs are evaluated — no early exit, no ordering.  The `min` over the reference's seven sigmoids per pair is computed as the sigmoid of the min of their arguments (one `expf` + one reciprocal per pair): 40.7 → 32.6 (reciprocal instead of division) → 14.7 (one sigmoid) → 11.8 ms (NaN-propagating `min.NaN.f32`, fused by ptxas into 3-input `FMNMX3.NAN`, instead of compare/select chains).  `ncu --set full` of the blockage kernel (`profiles/r1_ncu_full_relaxed_blockage.json`): issue-slot utilisation 89 % (124 warp instructions per evaluation), DRAM traffic 56 MB per launch (the packed mesh stays in L1/L2: 99.9 % L1 hit rate) — instruction-issue bound like the hard path.","",
-"| kernel | ms | relaxed pair evaluations / s | note |","|---|---|---|---|"]
-for r in rl["rows"]:
-    lines.append(f"| {r['kernel'].strip()} | {r['ms']:.3f} | {r['relaxed_tests_per_s']:.3g} | {r['note']} |")
-open('/root/repo/BASELINE.md','w').write(b+sec5+"\n"+"\n".join(lines)+"\n")
+| arm | GPUs | step | pairs decided /s (`value`) | executed tests /s | candidate-pairs /s | efficiency | blockage kernel, slowest / fastest rank | weak-scaling leg |
+|---|---|---|---|---|---|---|---|---|
+{chr(10).join(rows)}
+| differt_b200, end to end from host buffers (`e2e`) | 1 | {d['e2e']['ms_per_step']:.2f} ms | {fmt(d['e2e']['value'])} | {fmt(d['e2e']['executed_tests_per_s'])} | — | — | — | — |
+| differt_b200, API default mode (blockage only for candidates passing the cheap tests; identical outputs) | 1 | {d['default_mode']['ms_per_step']:.2f} ms | — | — | {fmt(d['default_mode']['candidate_pairs_per_s'])} | — | — | — |
+| reference algorithm restated on CPU (`--impl reference`: C/OpenMP/AVX2 port, early exit like the GPU arm; JAX/Warp not installable), {ref['cpu_baseline']['cores']} host cores | 0 | — | {fmt(ref['value'])} | {fmt(ref['executed_tests_per_s'])} | — | — | — | — |
+| same port, dense (no early exit: the reference's literal `fori_loop`) | 0 | — | {fmt(ref['dense_no_early_exit_tests_per_s'])} | {fmt(ref['dense_no_early_exit_tests_per_s'])} | — | — | — | — |
+
+Ratios (same box, same run): `e2e` ÷ reference arm = **{d['e2e']['value'] / ref['value']:.0f}×** on decided pairs (a ratio of times
+for the same job); executed-vs-executed Möller–Trumbore rate {d['vs_cpu']['executed_tests_ratio']:.0f}× (the GPU arm executes
+{d['executed_fraction_of_algorithmic'] * 100:.2f} % of the pairs, the CPU arm {cb['executed_fraction_of_algorithmic'] * 100:.0f} %: the traversal replaces
+tests by node tests).  Parity of the timed step: {d['parity']['checked_pairs']} pairs re-checked by the oracle, {d['parity']['mismatches']} mismatches.
+Roofline of the blockage kernel: instruction issue, {d['roofline']['frac']:.2f} of 148 × 4 × 1.965 GHz ({d['roofline']['achieved']:.3g} warp
+instructions/s, ncu-counted); DRAM {d['roofline']['traffic'] / 1e9:.2f} GB per step (the path vertices) = {d['roofline']['hbm_model']['dram_gbs_measured']:.0f} GB/s.
+BASELINE.json's HBM accounting (36 B per executed test) gives {d['roofline']['hbm_model']['model_gbs']:.0f} GB/s-equivalent = {d['roofline']['hbm_model']['model_gbs'] / d['roofline']['hbm_model']['hbm_peak_gbs']:.2f} of
+the measured {d['roofline']['hbm_model']['hbm_peak_gbs']:.0f} GB/s — inapplicable as a roofline (the operand never leaves the chip), reported as
+`roofline.hbm_model`.
+"""
+    others = []
+    for label, f1, f8 in (
+        ("config 2: street canyon 986 triangles, 1 × 256 RX, order 2, one 65 536-candidate chunk", "r2_bench_cfg2_canyon1k_n1.json", None),
+        ("config 4: urban 10 094 triangles, 16 TX × 4096 RX, order 3, 4096 candidates (2.7·10^8 candidate-pairs)", "r2_bench_cfg4_urban10k_16tx_n1.json", "r2_bench_cfg4_urban10k_16tx_n8.json"),
+        ("config 5: urban 49 922 triangles, 1 × 16 384 RX, order 4, 2048 candidates (3.4·10^7 candidate-pairs, 8.4·10^12 pairs)", "r2_bench_cfg5_urban50k_order4_n1.json", "r2_bench_cfg5_urban50k_order4_n8_c2048.json"),
+    ):
+        a, c = load(f1), load(f8) if f8 else None
+        if a is None:
+            continue
+        line = (f"| {label} | {a['ms_per_step']:.1f} ms | {fmt(a['value'])} | {fmt(a['candidate_pairs_per_s'])} | "
+                f"{a['executed_fraction_of_algorithmic'] * 100:.2f} % | {a['parity']['mismatches']} / {a['parity']['checked_pairs']} |")
+        if c is not None:
+            line += f" {c['ms_per_step']:.1f} ms | {fmt(c['value'])} | {a['ms_per_step'] / c['ms_per_step'] / 8:.2f} | {c['parity']['mismatches']} / {c['parity']['checked_pairs']} |"
+        else:
+            line += " — | — | — | — |"
+        others.append(line)
+    sweep = []
+    for cnum in (256, 512, 1024, 2048):
+        s = load(f"r2_bench_cfg5_urban50k_order4_n8_c{cnum}.json")
+        if s:
+            sweep.append(f"C = {cnum}: {s['ms_per_step']:.2f} ms, {fmt(s['value'])} pairs/s, {fmt(s['candidate_pairs_per_s'])} candidate-pairs/s")
+    sec5 += f"""
+Other BASELINE configurations (`bench.py --workload …`, forward + VJP every step, same definitions; `profiles/r2_bench_cfg*`):
+
+| configuration | 1 GPU step | pairs decided /s | candidate-pairs /s | executed | parity (mismatches / checked) | 8 GPUs step | pairs decided /s | efficiency | parity |
+|---|---|---|---|---|---|---|---|---|---|
+{chr(10).join(others)}
+
+Config 5 sweep over the number of candidates on 8 GPUs (fwd + bwd): {'; '.join(sweep)}.
+
+Round 1 for comparison (same config 3, weak scaling, CPU arm dense): step 95 ms, 7.1·10^12 pairs decided /s, 6.4 % of
+the pairs executed; round-2 progression on the same workload: 95 → 68 (flat two-level cull behind the ordered
+rows) → 131 / 153 (thread-per-candidate and all-segments-together traversals) → 78 → **29 ms** (`DESIGN.md` §4).
+"""
+    k = load("r2_kernels.json")
+    lines = ["## 6. Per-kernel timings (round 2, `tools/bench_kernels.py`, `profiles/r2_kernels.json`)", "",
+             'CUDA events, 3 warm-ups, median of 10, B200 @ 1965 MHz, through the Python API unless marked "kernel only".  `GB/s` = '
+             "algorithmic bytes (SURVEY §8d per-unit figures) ÷ time against the measured 6549 GB/s copy bandwidth; for the all-pairs "
+             "kernels that is the streamed-operand model and exceeds 1.  `ncu --set full` of the same kernels "
+             "(`profiles/r2_ncu_full_primitives.json`, `r2_ncu_full_bench_step.json`, DRAM bytes ÷ kernel time): K1 192 µs, 5.68 TB/s = "
+             "0.87 of peak; K5 122 µs, 4.31 TB/s = 0.66; stage A 470 µs, 2.77 TB/s = 0.42 with 68 % of the issue slots busy; K6b 709 µs, "
+             "1.43 TB/s = 0.22 at 68 % issue (was 877 µs); all-pairs any-hit / nearest hit at 2^18 rays 3.00 / 6.16 ms → culled traversal "
+             "0.48 / 0.89 ms.", "",
+             "| kernel | ms | throughput | GB/s | frac of HBM peak | note |", "|---|---|---|---|---|---|"]
+    for r in k["rows"]:
+        thr = [(kk, v) for kk, v in r.items() if kk.endswith("_per_s")][0]
+        g, f = r.get("gbs"), r.get("frac_of_hbm_peak")
+        lines.append(f"| {r['kernel']} | {r['ms']:.3f} | {thr[1]:.3g} {thr[0].replace('_per_s', '')}/s | {('%.0f' % g) if g else '—'} | "
+                     f"{('%.2f' % f) if f else '—'} | {r['note']} |")
+    rl = load("r1_relaxed_trace.json")
+    if rl:
+        lines += ["", "### Relaxed (`smoothing_factor`) trace, forward and reverse mode (`tools/bench_relaxed.py`, `profiles/r1_relaxed_trace.json`, round 1)", "",
+                  "| kernel | ms | relaxed pair evaluations / s | note |", "|---|---|---|---|"]
+        for r in rl["rows"]:
+            lines.append(f"| {r['kernel'].strip()} | {r['ms']:.3f} | {r['relaxed_tests_per_s']:.3g} | {r['note']} |")
+    (ROOT / "BASELINE.md").write_text(b + sec5 + "\n" + "\n".join(lines) + "\n")
+
+
+if __name__ == "__main__":
+    main()
