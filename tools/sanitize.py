@@ -22,6 +22,13 @@ print("mesh any", int(mesh.ray_intersect_any_triangle(o, d).sum()))
 idx, tt = drt.first_triangle_hit_by_ray(o, d, tri)
 print("first", int((idx >= 0).sum()))
 print("visible", int(mesh.triangles_visible_from_vertex(torch.tensor([[150.0, 150.0, 60.0]]).cuda(), num_rays=20000).sum()))
+# the same flat queries behind the exact cull (walk.cuh), which the public API only takes for large batches
+from differt_b200 import geometry
+_min_work, geometry._CULL_MIN_WORK = geometry._CULL_MIN_WORK, 0
+print("culled any", int(drt.ray_intersect_any_triangle(o, d, tri).sum()), int(mesh.ray_intersect_any_triangle(o, d).sum()))
+print("culled first", int((drt.first_triangle_hit_by_ray(o, d, tri)[0] >= 0).sum()))
+print("culled visible", int(mesh.triangles_visible_from_vertex(torch.tensor([[150.0, 150.0, 60.0]]).cuda(), num_rays=20000).sum()))
+geometry._CULL_MIN_WORK = _min_work
 tx = np.array([[150.0, 150.0, 48.0]], np.float32)
 rx = scenes.receivers_grid(v, 8)
 for order, n in ((1, 1454), (2, 3000), (3, 3000), (6, 500)):
@@ -33,6 +40,13 @@ for order, n in ((1, 1454), (2, 3000), (3, 3000), (6, 500)):
 rx_big = scenes.receivers_grid(v, 16, 8)
 big = drt.trace_path_candidates(mesh, tx, rx_big, scenes.sampled_candidates(t.shape[0], 2, 2048), dense_blockage=True, with_stats=True)
 print("dense with ordering pass", big.num_valid_paths, big.stats)
+# a mesh of <= 512 triangles keeps the ordering pass + cascade of resident passes: dense, >= 262 144 paths
+vs, ts_ = scenes.street_canyon(20)
+small = drt.Mesh.from_numpy(vs, ts_)
+rx_s = scenes.receivers_grid(vs, 16, 16)
+sp = drt.trace_path_candidates(small, np.array([[100.0, 0.0, 45.0]], np.float32), rx_s,
+                               scenes.sampled_candidates(ts_.shape[0], 2, 1100), dense_blockage=True, with_stats=True)
+print("small mesh, ordering pass + cascade", sp.num_valid_paths, sp.stats)
 comp = drt.trace_valid_path_candidates(mesh, tx, rx, scenes.complete_graph_candidates(t.shape[0], 1), capacity=7)
 print("compact", comp.num_valid_paths)
 print("bvh", int(mesh.ray_intersect_any_triangle(o, d, accel="bvh").sum()), int((mesh.first_triangle_hit_by_ray(o, d, accel="bvh")[0] >= 0).sum()))
