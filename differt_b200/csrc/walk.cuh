@@ -82,6 +82,8 @@ path_walk_kernel(const Tri48 *__restrict__ pack, const CullNode *__restrict__ no
         return RAYS ? next : sub3(next, o);  // jnp.diff (_solvers.py:593) for paths
     };
     const int leaf = lv.num_levels - 1;
+    int start_level = 0;
+    while (start_level < leaf && lv.size[start_level + 1] <= 32) ++start_level;
     const int sub = lane & 7, slot = lane >> 3;  // child / triangle, and which of the (up to) 4 popped entries
     // the 32 largest triangles (first row of the area-sorted pack), one per lane: every candidate is
     // tested against them before it walks the hierarchy — a random segment is blocked by a triangle
@@ -148,9 +150,23 @@ path_walk_kernel(const Tri48 *__restrict__ pack, const CullNode *__restrict__ no
             if ((d.x == 0.0f && d.y == 0.0f && d.z == 0.0f) || !finite3(o) || !finite3(d)) continue;
             const SegCull sc = make_seg_cull(o, d);
 
-            int nn = 1, ng = 0;  // stack heights (warp-uniform)
-            if (lane == 0) node_stack[0] = 0u;  // the virtual root
-            __syncwarp();
+            // first step: lane l tests node l of the deepest level that has at most 32 nodes (one step
+            // instead of walking the 3-node and 20-node levels of a 10 000-triangle mesh one after the other)
+            int nn = 0, ng = 0;  // stack heights (warp-uniform)
+            {
+                const bool keep = lane < level_size[start_level] &&
+                                  !node_culled(sc, nodes[level_offset[start_level] + lane]);
+                const unsigned b0 = __ballot_sync(kFull, keep);
+                const int pos = __popc(b0 & ((1u << lane) - 1u));
+                __syncwarp();
+                if (keep) {
+                    if (start_level == leaf) group_stack[pos] = uint32_t(lane);
+                    else node_stack[pos] = (uint32_t(start_level + 1) << 28) | uint32_t(lane);
+                }
+                if (start_level == leaf) ng = __popc(b0);
+                else nn = __popc(b0);
+                __syncwarp();
+            }
             while (nn > 0 || ng > 0) {
                 if (ng >= 4 || nn == 0) {
                     // ---- group step: up to 4 groups x 8 triangles
@@ -244,6 +260,8 @@ ray_first_walk_kernel(const Tri48 *__restrict__ pack, const uint32_t *__restrict
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *node_stack = node_stack_all[warp], *group_stack = group_stack_all[warp];
     const int leaf = lv.num_levels - 1;
+    int start_level = 0;
+    while (start_level < leaf && lv.size[start_level + 1] <= 32) ++start_level;
     const int sub = lane & 7, slot = lane >> 3;
     const bool fast_ok = eps >= 1.17549435e-38f;
     constexpr int kChunk = DRT_WALK_CHUNK;
@@ -265,9 +283,21 @@ ray_first_walk_kernel(const Tri48 *__restrict__ pack, const uint32_t *__restrict
             const bool dead = (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f) || !finite3(o) || !finite3(d);
             if (!dead) {
                 const SegCull sc = make_ray_cull(o, d);
-                int nn = 1, ng = 0;
-                if (lane == 0) node_stack[0] = 0u;
-                __syncwarp();
+                int nn = 0, ng = 0;
+                {   // first step: the deepest level with at most 32 nodes, one node per lane
+                    const bool keep = lane < level_size[start_level] &&
+                                      !node_culled(sc, nodes[level_offset[start_level] + lane], best_t);
+                    const unsigned b0 = __ballot_sync(kFull, keep);
+                    const int pos = __popc(b0 & ((1u << lane) - 1u));
+                    __syncwarp();
+                    if (keep) {
+                        if (start_level == leaf) group_stack[pos] = uint32_t(lane);
+                        else node_stack[pos] = (uint32_t(start_level + 1) << 28) | uint32_t(lane);
+                    }
+                    if (start_level == leaf) ng = __popc(b0);
+                    else nn = __popc(b0);
+                    __syncwarp();
+                }
                 while (nn > 0 || ng > 0) {
                     if (ng >= 4 || nn == 0) {
                         const int take = ng < 4 ? ng : 4;
