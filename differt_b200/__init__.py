@@ -6,7 +6,7 @@ Importing the package loads ``libdiffert_b200.so``; there is no CPU or PyTorch f
 """
 
 from . import _lib  # noqa: F401  (fails loudly if the CUDA library is missing)
-from . import geometry, launch, rt, scenes, solvers
+from . import em, geometry, launch, rt, scenes, solvers
 from .geometry import (
     consecutive_vertices_are_on_same_side_of_mirror,
     fibonacci_lattice,
@@ -48,6 +48,7 @@ __all__ = [
     "VisiblePathCandidates",
     "generate_visible_path_candidates",
     "consecutive_vertices_are_on_same_side_of_mirror",
+    "em",
     "fibonacci_lattice",
     "first_triangle_hit_by_ray",
     "generate_all_path_candidates",

@@ -93,6 +93,10 @@ PROTOTYPES: dict[str, tuple] = {
         C.c_int,
         [ptr, i64, i64, ptr, ptr, ptr, i32, i64, ptr, i64, ptr, i64, i32, ptr, f32, f32, f32, f32, ptr, ptr, ptr,
          ptr, ptr, size_t, ptr, ptr, ptr]),
+    "drt_em_fresnel_coefficients": (C.c_int, [ptr, i64, ptr, i64, ptr, i64, ptr, ptr, ptr, ptr]),
+    "drt_em_sp_directions": (C.c_int, [ptr, i64, ptr, ptr, ptr, ptr, ptr, ptr]),
+    "drt_em_path_coefficients": (
+        C.c_int, [ptr, i64, i32, ptr, ptr, i64, ptr, ptr, ptr, C.c_double, i32, i32, ptr, ptr, ptr, i64, ptr, ptr]),
     "drt_bvh_bytes": (size_t, [i64]),
     "drt_bvh_workspace_bytes": (size_t, [i64]),
     "drt_bvh_build": (C.c_int, [ptr, i64, ptr, f32, ptr, size_t, ptr]),

@@ -279,17 +279,12 @@ class TracedPaths:
     def num_valid_paths(self) -> int:
         return int(self._valid().sum().item())
 
-    def masked(self) -> "TracedPaths":
-        """Keep the valid paths only, flattened in row-major order (reference ``_paths.py:299-328``).
-
-        The stable compaction runs on the device (``drt_compact_valid_paths``); one 8-byte
-        device→host read sizes the result.
-        """
+    def _valid_flat_indices(self) -> torch.Tensor:
+        """Flat row-major indices of the valid paths, ascending (``drt_compact_valid_paths``: the
+        stable compaction runs on the device; one 8-byte device→host read sizes the result)."""
         k = self.order
         P = numel(self.mask.shape)
         dev = self.vertices.device
-        v = self.vertices.detach().reshape(P, k + 2, 3).contiguous()
-        o = self.objects.reshape(P, k + 2).contiguous()
         m = self._valid().reshape(P).to(torch.uint8).contiguous()
         count = torch.zeros(1, dtype=torch.int64, device=dev)
         ws = torch.empty(max(lib.drt_compact_workspace_bytes(P), 1), dtype=torch.uint8, device=dev)
@@ -300,12 +295,20 @@ class TracedPaths:
                 None, None,
             )
         )
-        n = int(count.item())
-        index = index[:n]
+        return index[: int(count.item())]
+
+    def masked(self, index: torch.Tensor | None = None) -> "TracedPaths":
+        """Keep the valid paths only, flattened in row-major order (reference ``_paths.py:299-328``)."""
+        k = self.order
+        P = numel(self.mask.shape)
+        dev = self.vertices.device
+        if index is None:
+            index = self._valid_flat_indices()
+        n = int(index.shape[0])
         vertices = self.vertices.reshape(P, k + 2, 3)[index]  # keeps the autograd graph
         return TracedPaths(
             vertices=vertices,
-            objects=o[index],
+            objects=self.objects.reshape(P, k + 2)[index],
             mask=torch.ones(n, dtype=torch.bool, device=dev),
             interaction_types=self.interaction_types.reshape(P, k)[index],
             confidence_threshold=self.confidence_threshold,

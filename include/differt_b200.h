@@ -270,6 +270,34 @@ DRT_API int drt_trace_path_candidates_vjp(drt_stream_t stream, int64_t num_verti
                                   const int32_t *path_candidates, const float *g_out_vertices,
                                   float *g_tx, float *g_rx, float *g_vertices);
 
+/* ---------------------------------------------------------------------------------------------
+ * First EM consumer of the traced paths.
+ * drt_em_fresnel_coefficients: reference em/_fresnel.py:46-213.  Complex values are interleaved
+ *     (re, im) float pairs; `n_r` / `cos_theta_i` are read at index i * stride (stride 0 broadcasts a
+ *     scalar); any of the four outputs may be null.
+ * drt_em_path_coefficients: one complex coefficient per path — the field chain of the reference's
+ *     consumers (em/_utils.py:243-302 `sp_directions` / `sp_rotation_matrix`, the composition in
+ *     plugins/deepmimo.py:348-405, 516-665: per interaction J = R_out diag(r_s, r_p) R_in with the slab
+ *     formula when thickness >= 0, projection on the receive polarisation, 1 / length, phase
+ *     exp(-j 2 pi f length / c), lambda / 4 pi) — for paths given as compacted TracedPaths fields
+ *     (vertices [n, order+2, 3], objects [n, order+2]); normals come from the mesh pack (drt_mesh_pack),
+ *     `n_r` [T] complex and `thickness` [T] (nullable: half spaces) are per triangle; polarisations
+ *     0 = V, 1 = H.  Optionally fused with the accumulation per (tx, rx) pair: field[pair_index[i]] +=
+ *     a_i (coherent), power[pair_index[i]] += |a_i|^2; the caller zero-fills `field` / `power`.
+ * ------------------------------------------------------------------------------------------- */
+DRT_API int drt_em_fresnel_coefficients(drt_stream_t stream, int64_t n, const float *n_r, int64_t n_r_stride,
+                                const float *cos_theta_i, int64_t cos_theta_stride, float *r_s /*nullable*/,
+                                float *r_p /*nullable*/, float *t_s /*nullable*/, float *t_p /*nullable*/);
+/* em/_utils.py:84-262 `sp_directions` on flat, contiguous [n, 3] operands; e_r_s equals e_i_s. */
+DRT_API int drt_em_sp_directions(drt_stream_t stream, int64_t n, const float *k_i, const float *k_r,
+                         const float *normals, float *e_i_s, float *e_i_p, float *e_r_p);
+DRT_API int drt_em_path_coefficients(drt_stream_t stream, int64_t num_paths, int32_t order, const float *vertices,
+                             const int32_t *objects, int64_t num_triangles, const void *pack,
+                             const float *n_r, const float *thickness /*nullable*/, double frequency,
+                             int32_t tx_polarization, int32_t rx_polarization, float *out_a /*nullable*/,
+                             float *out_length /*nullable*/, const int64_t *pair_index /*nullable*/,
+                             int64_t num_pairs, float *field /*nullable*/, float *power /*nullable*/);
+
 /* Profile ring (per host thread, 64 slots).  A call made with DRT_TRACE_PROFILE records one event
  * pair on its stream, immediately before and after the blockage kernel, into the next free slot.
  * drt_profile_elapsed_ms waits for that slot's stop event and returns the device time between the

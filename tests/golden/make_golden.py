@@ -52,6 +52,68 @@ def parse_obj_triangles_only(path: Path) -> tuple[np.ndarray, np.ndarray]:
     )
 
 
+def em_kats() -> dict:
+    """Known answers of the EM utilities (SURVEY §8f N4), transcribed from the reference's tests;
+    paths relative to /root/reference/differt/."""
+    return {
+        "_comment": "Transcribed from differt/tests/em/*.py; exact-equality asserts of the reference "
+        "that depend on XLA's libm / FMA contraction are kept with the tolerance given here.",
+        "constants": {
+            "source": "src/differt/em/_constants.py, tests/em/test_constants.py:7-25 (scipy.constants, 1e-6)",
+            "c": 299792458.0, "mu_0": 1.25663706212e-06, "epsilon_0": 8.8541878128e-12, "z_0": 376.73031341259,
+        },
+        "refractive_index": {
+            "source": "tests/em/test_fresnel.py:16-30; Glass at 1 GHz: eps_r = 6.27 f^0 "
+            "(src/differt/em/_material.py:363-366, relative_permittivity :55-67)",
+            "cases": [{"epsilon_r": 1.0, "expected": 1.0}, {"epsilon_r": 6.27, "expected": 2.503997}],
+        },
+        "fresnel_identities": {
+            "source": "tests/em/test_fresnel.py:33-55",
+            "n_1_n_2_range": [0.01, 2.0], "num": 100, "theta_i": "linspace(0, pi/2, 50)",
+            "identities": ["t_s == r_s + 1", "n_r * t_p == r_p + 1"], "atol": 1e-6,
+        },
+        "reflection_coefficients": {
+            "source": "tests/em/test_fresnel.py:58-95",
+            "cases": [
+                {"name": "normal incidence", "n_r": 1.5, "cos_theta_i": 1.0, "expect": "r_s == -r_p"},
+                {"name": "grazing incidence", "n_r": 1.5, "cos_theta_i": "cos(pi/2)", "expect": "r_s**2 == -r_p"},
+                {"name": "Brewster", "n_r": 1.5, "cos_theta_i": "cos(arctan(n_r))", "expect": "r_p == 0"},
+                {"name": "total reflection", "n_r": "1/1.5", "cos_theta_i": "cos(arcsin(n_r))",
+                 "expect": "r_s == r_p == 1"},
+            ],
+        },
+        "sp_directions": {
+            "source": "tests/em/test_utils.py:62-90",
+            "k_i": [["cos30", "-sin30", 0.0], [0.0, -1.0, 0.0]],
+            "k_r": [["cos30", "+sin30", 0.0], [0.0, 1.0, 0.0]],
+            "normals": [[0.0, 1.0, 0.0], [0.0, 1.0, 0.0]],
+            "e_i_s": [[0.0, 0.0, 1.0], [1.0, 0.0, 0.0]],
+            "e_i_p": [["+sin30", "cos30", 0.0], [0.0, 0.0, -1.0]],
+            "e_r_p": [["-sin30", "cos30", 0.0], [0.0, 0.0, 1.0]],
+        },
+        "sp_rotation_matrix": {
+            "source": "tests/em/test_utils.py:93-128; rotation_matrix_along_z_axis "
+            "(src/differt/geometry/_utils.py:282-286) = [[cos, -sin], [sin, cos]]",
+            "e_i_s": [1.0, 0.0, 0.0], "e_i_p": [0.0, 1.0, 0.0],
+            "cases": [
+                {"e_r_s": [0.0, 1.0, 0.0], "e_r_p": [-1.0, 0.0, 0.0], "angle": "-pi/2", "atol": 1e-7},
+                {"e_r_s": ["s", "s", 0.0], "e_r_p": ["-s", "s", 0.0], "angle": "-pi/4", "s": "sqrt(2)/2"},
+                {"e_r_s": [1.0, 0.0, 0.0], "e_r_p": [0.0, -1.0, 0.0], "expected": [[1.0, 0.0], [0.0, -1.0]]},
+            ],
+        },
+        "fspl": {
+            "source": "tests/em/test_utils.py:131-141",
+            "d_range": [1.0, 100.0], "f_range": [0.1e9, 10e9],
+            "identities": ["10 log10(fspl) == fspl(dB=True)", "fspl(dB=True) == 20 log10 d + 20 log10 f - 147.55 (rtol 2e-4)"],
+        },
+        "fspl_vs_los": {
+            "source": "tests/em/test_utils.py:144-170 (the received power of a line-of-sight link equals "
+            "1 / fspl at the direction of maximum radiation)",
+            "frequencies": [0.1e9, 1e9, 10e9], "r_range": [10.0, 1000.0], "rtol": 2e-4,
+        },
+    }
+
+
 def main() -> None:
     v, t = parse_obj_triangles_only(REF / "differt/tests/geometry/two_buildings.obj")
     assert v.shape == (56, 3) and t.shape == (24, 3), (v.shape, t.shape)
@@ -209,6 +271,7 @@ def main() -> None:
         },
     }
     (HERE / "reference_kats.json").write_text(json.dumps(kats, indent=1) + "\n")
+    (HERE / "em_kats.json").write_text(json.dumps(em_kats(), indent=1) + "\n")
     print("wrote", sorted(p.name for p in HERE.iterdir()))
 
 
