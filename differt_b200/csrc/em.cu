@@ -87,15 +87,38 @@ __device__ __forceinline__ float3 perpendicular3(float3 u) {
     float l;
     return normalize3(cross3(u, v), l);
 }
-// plugins/deepmimo.py:348-363
+// plugins/deepmimo.py:348-363: theta = acos(clip(k.z)), phi = atan2(k.y, k.x) and their sines / cosines,
+// evaluated algebraically (cos theta = z, sin theta = sqrt((1 - z)(1 + z)), cos phi = x / rho, sin phi = y / rho:
+// each within 2 ulp of the exact value, like the libm chain it replaces, at a fifth of the instructions)
 __device__ __forceinline__ void spherical_basis(float3 k, float3 &theta_hat, float3 &phi_hat) {
-    const float z = fminf(fmaxf(k.z, -1.0f), 1.0f);
-    const float theta = acosf(z), phi = atan2f(k.y, k.x);
-    float st, ct, sp, cp;
-    sincosf(theta, &st, &ct);
-    sincosf(phi, &sp, &cp);
+    const float ct = fminf(fmaxf(k.z, -1.0f), 1.0f);
+    const float st = __fsqrt_rn((1.0f - ct) * (1.0f + ct));
+    const float rho = __fsqrt_rn(k.x * k.x + k.y * k.y);
+    float cp, sp;
+    if (rho > 0.0f) {
+        cp = __fdiv_rn(k.x, rho), sp = __fdiv_rn(k.y, rho);
+    } else {  // atan2(+-0, +0) = +-0, atan2(+-0, -0) = +-pi
+        cp = signbit(k.x) ? -1.0f : 1.0f, sp = 0.0f;
+    }
     theta_hat = make_float3(ct * cp, ct * sp, -st);
     phi_hat = make_float3(-sp, cp, 0.0f);
+}
+
+// Sum of x over the lanes of `peers` (the lanes of this warp holding the same key), for any peer pattern, in
+// log2(32) shuffle rounds; every lane of the warp must call it.  The lowest lane of each group ends with the sum.
+__device__ __forceinline__ void reduce_peers3(unsigned peers, int lane, float &x, float &y, float &z) {
+    int rel = __popc(peers & ((1u << lane) - 1u));   // rank among the peers
+    peers &= (0xfffffffeu << lane);                  // peers above this lane
+    while (__any_sync(0xffffffffu, peers != 0u)) {
+        const int next = __ffs(peers);               // 1 + lane of the next peer (0: none)
+        const int src = next ? next - 1 : lane;
+        const float tx = __shfl_sync(0xffffffffu, x, src), ty = __shfl_sync(0xffffffffu, y, src),
+                    tz = __shfl_sync(0xffffffffu, z, src);
+        if (next) x += tx, y += ty, z += tz;
+        const bool done = rel & 1;                   // odd ranks have been absorbed by their left neighbour
+        peers &= __ballot_sync(0xffffffffu, !done);
+        rel >>= 1;
+    }
 }
 
 // em/_utils.py:243-262 on flat [n, 3] operands (the host broadcasts)
@@ -138,8 +161,9 @@ struct EmArgs {
 
 template <int K>
 __global__ void __launch_bounds__(128) em_path_kernel(const EmArgs a) {
-    const int64_t p = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    if (p >= a.n) return;
+    const int64_t p0 = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const bool live = p0 < a.n;
+    const int64_t p = live ? p0 : a.n - 1;  // idle lanes of the last warp recompute the last path: they take part in the shuffles
     const float *v = a.vertices + p * (K + 2) * 3;
     float3 prev = ld3(v);
     float s_tot = 0.0f;
@@ -217,16 +241,24 @@ __global__ void __launch_bounds__(128) em_path_kernel(const EmArgs a) {
     sincosf(phase, &sn, &cs);
     ar = cmul(ar, cmk(spread * cs, spread * sn));
     ar = cscale(ar, a.scale);
-    if (a.out_a) a.out_a[2 * p] = ar.re, a.out_a[2 * p + 1] = ar.im;
-    if (a.out_length) a.out_length[p] = s_tot;
+    if (live) {
+        if (a.out_a) reinterpret_cast<float2 *>(a.out_a)[p] = make_float2(ar.re, ar.im);
+        if (a.out_length) a.out_length[p] = s_tot;
+    }
     if (a.pair_index != nullptr) {
-        const int64_t q = a.pair_index[p];
-        if (q >= 0 && q < a.num_pairs) {
+        // paths of one (tx, rx) pair are neighbours in the compacted order: one atomic per pair and warp, not per path
+        int64_t q = live ? a.pair_index[p] : -1;
+        if (q >= a.num_pairs) q = -1;
+        const int lane = threadIdx.x & 31;
+        const unsigned peers = __match_any_sync(0xffffffffu, q);
+        float fr = ar.re, fi = ar.im, pw = ar.re * ar.re + ar.im * ar.im;
+        reduce_peers3(peers, lane, fr, fi, pw);
+        if (q >= 0 && lane == __ffs(peers) - 1) {
             if (a.field) {
-                atomicAdd(a.field + 2 * q, ar.re);
-                atomicAdd(a.field + 2 * q + 1, ar.im);
+                atomicAdd(a.field + 2 * q, fr);
+                atomicAdd(a.field + 2 * q + 1, fi);
             }
-            if (a.power) atomicAdd(a.power + q, ar.re * ar.re + ar.im * ar.im);
+            if (a.power) atomicAdd(a.power + q, pw);
         }
     }
 }
