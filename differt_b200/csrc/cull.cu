@@ -29,6 +29,7 @@ struct TriInfo {
     float3 lo, hi, nrm;
     float r, e, sin_theta, beta;
     bool good;
+    int aligned;  // j if both edges have an exactly zero j-th component (normal = +-e_j, cull.cuh), else -1
 };
 
 __device__ __forceinline__ TriInfo tri_info(const Tri &t) {
@@ -52,6 +53,15 @@ __device__ __forceinline__ TriInfo tri_info(const Tri &t) {
     i.nrm = make_float3(n.x * rn, n.y * rn, n.z * rn);
     // angle between the computed and the true normal: |N_c - N| <= 2.9u |e1||e2| → asin(2.9u / sin theta)
     i.beta = i.good ? 2.4e-7f / st : 0.0f;
+    i.aligned = -1;
+    if (i.good) {
+        const bool zx = t.e1.x == 0.0f && t.e2.x == 0.0f, zy = t.e1.y == 0.0f && t.e2.y == 0.0f,
+                   zz = t.e1.z == 0.0f && t.e2.z == 0.0f;
+        if (int(zx) + int(zy) + int(zz) == 1) {
+            i.aligned = zx ? 0 : (zy ? 1 : 2);
+            i.nrm = make_float3(zx ? 1.f : 0.f, zy ? 1.f : 0.f, zz ? 1.f : 0.f);  // the exact axis (sign is irrelevant)
+        }
+    }
     return i;
 }
 
@@ -162,7 +172,7 @@ __global__ void cull_group_nodes_kernel(int64_t num_groups, const Tri48 *__restr
     float3 lo = make_float3(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
     float3 hi = make_float3(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
     float r = 0.0f, e = 0.0f, st = 1.0f;
-    bool any = false, cullable = true;
+    bool any = false, cullable = true, aligned = true;
     AxisSet axes;
     for (int k = 0; k < kCullGroup; ++k) {
         const Tri48 rec = pack[gidx * kCullGroup + k];
@@ -177,6 +187,7 @@ __global__ void cull_group_nodes_kernel(int64_t num_groups, const Tri48 *__restr
         lo = make_float3(fminf(lo.x, i.lo.x), fminf(lo.y, i.lo.y), fminf(lo.z, i.lo.z));
         hi = make_float3(fmaxf(hi.x, i.hi.x), fmaxf(hi.y, i.hi.y), fmaxf(hi.z, i.hi.z));
         r = fmaxf(r, i.r), e = fmaxf(e, i.e), st = fminf(st, i.sin_theta);
+        aligned = aligned && i.aligned >= 0;
         axes.add(i.nrm, i.beta);
     }
     CullNode node;
@@ -197,7 +208,7 @@ __global__ void cull_group_nodes_kernel(int64_t num_groups, const Tri48 *__restr
                                 fmaxf(hi.y - node.ctr.y, node.ctr.y - lo.y) * 1.000001f,
                                 fmaxf(hi.z - node.ctr.z, node.ctr.z - lo.z) * 1.000001f, 0.f);
         axes.finish(node, st, cullable);
-        node.c1.w = r;
+        node.c1.w = (aligned && cullable) ? -r : r;  // r > 0 for a cullable node of finite triangles unless all sit at the origin
         node.c2.w = e;
     }
     nodes[gidx] = node;
@@ -213,7 +224,7 @@ __global__ void cull_tile_nodes_kernel(int64_t num_tiles, int64_t num_groups, co
     float3 lo = make_float3(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
     float3 hi = make_float3(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
     float r = 0.0f, e = 0.0f, st = 1.0f;
-    bool any = false, cullable = true;
+    bool any = false, cullable = true, aligned = true;
     AxisSet axes;
     for (int k = 0; k < fan; ++k) {
         const int64_t gidx = tidx * fan + k;
@@ -227,7 +238,8 @@ __global__ void cull_tile_nodes_kernel(int64_t num_tiles, int64_t num_groups, co
         }
         lo = make_float3(fminf(lo.x, g.ctr.x - g.half.x), fminf(lo.y, g.ctr.y - g.half.y), fminf(lo.z, g.ctr.z - g.half.z));
         hi = make_float3(fmaxf(hi.x, g.ctr.x + g.half.x), fmaxf(hi.y, g.ctr.y + g.half.y), fmaxf(hi.z, g.ctr.z + g.half.z));
-        r = fmaxf(r, g.c1.w), e = fmaxf(e, g.c2.w), st = fminf(st, g.c0.w);
+        r = fmaxf(r, fabsf(g.c1.w)), e = fmaxf(e, g.c2.w), st = fminf(st, g.c0.w);
+        aligned = aligned && __float_as_int(g.c1.w) < 0;
         axes.add(make_float3(g.c0.x, g.c0.y, g.c0.z), g.half.w);
         axes.add(make_float3(g.c1.x, g.c1.y, g.c1.z), g.half.w);
         axes.add(make_float3(g.c2.x, g.c2.y, g.c2.z), g.half.w);
@@ -249,7 +261,7 @@ __global__ void cull_tile_nodes_kernel(int64_t num_tiles, int64_t num_groups, co
                                 fmaxf(hi.y - node.ctr.y, node.ctr.y - lo.y) * 1.000001f + 1e-6f * r,
                                 fmaxf(hi.z - node.ctr.z, node.ctr.z - lo.z) * 1.000001f + 1e-6f * r, 0.f);
         axes.finish(node, st, cullable);
-        node.c1.w = r * 1.000001f;
+        node.c1.w = (aligned && cullable) ? -(r * 1.000001f) : r * 1.000001f;
         node.c2.w = e;
     }
     tiles[tidx] = node;

@@ -1834,3 +1834,117 @@ def test_smoothed_trace_gradient_vs_autograd_oracle(drt, alpha, order, quads):
 
             for got, exp in zip(grads(smoothing_factor=alpha), grads()):
                 np.testing.assert_allclose(got, exp, rtol=1e-4, atol=1e-6)
+
+
+def test_compute_tx_mlm_reference_properties(drt):
+    """The reference's own MLM test restated (differt/tests/geometry/test_scene.py:761-875: same box,
+    same transmitters, same grids, same assertions), and its masked-mesh test (:877-917) on a scene
+    whose every triangle but the ground is masked (the reference masks all of simple_street_canyon but
+    its two ground triangles; the assertion — order-0 cells all carry the empty path's hash
+    2166136261, no path of two or more bounces exists — does not depend on the buildings)."""
+    vertices = np.array([[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1],
+                         [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], np.float32)
+    triangles = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4],
+                          [1, 2, 6], [1, 6, 5], [2, 3, 7], [2, 7, 6], [3, 0, 4], [3, 4, 7]], np.int32)
+    mesh = drt.Mesh.from_numpy(vertices, triangles)
+    scene = drt.Scene(np.array([0.0, 0.0, 5.0], np.float32), np.empty((0, 3), np.float32), mesh)
+    scene = scene.with_receivers_grid(m=10, n=10, height=1.5)
+    for kwargs in ({}, {"height": 2.0}, {"min_order": 1}):
+        mlm = scene.compute_tx_mlm(max_order=1, dim_x=10, dim_y=10, num_rays=500, **kwargs)
+        assert tuple(mlm.shape) == (10, 10)
+        assert int(mlm.min()) >= 0 and int(mlm.max()) < (1 << 32)  # uint32 values
+    assert torch.all(scene.compute_tx_mlm(max_order=1, min_order=2, dim_x=10, dim_y=10, num_rays=500) == 0)
+    assert tuple(scene.set_assume_quads(True).compute_tx_mlm(max_order=1, dim_x=10, dim_y=10, num_rays=500).shape) == (10, 10)
+    above = scene.compute_tx_mlm(max_order=0, min_order=0, dim_x=5, dim_y=5, num_rays=50000, height=1.5)
+    assert torch.any(above > 0) and above[0, 0] > 0 and above[4, 4] > 0
+    inside = scene.compute_tx_mlm(max_order=2, dim_x=5, dim_y=5, num_rays=1000, height=0.0)
+    assert torch.all(inside == 0)
+    below = scene.compute_tx_mlm(max_order=0, min_order=0, dim_x=5, dim_y=5, num_rays=1000, height=-2.0)
+    assert torch.all(below == 0)
+    multi = drt.Scene(np.array([[0.0, 0.0, 5.0], [0.0, 0.0, 6.0]], np.float32), np.empty((0, 3), np.float32), mesh)
+    assert tuple(multi.compute_tx_mlm(max_order=1, dim_x=10, dim_y=10, num_rays=500).shape) == (2, 10, 10)
+    tx2d = np.tile(np.array([[0.0, 0.0, 5.0], [0.0, 0.0, 6.0], [0.0, 0.0, 7.0]], np.float32), (2, 1, 1))
+    multi = drt.Scene(tx2d, np.empty((0, 3), np.float32), mesh)
+    assert tuple(multi.compute_tx_mlm(max_order=1, dim_x=10, dim_y=10, num_rays=500).shape) == (2, 3, 10, 10)
+
+    v, t = scenes.street_canyon(3)
+    ground = np.zeros(t.shape[0], bool)
+    ground[-2:] = True  # the two ground triangles come last (scenes.street_canyon), like the reference scene's 72:74
+    assert np.allclose(v[t[-2:]][..., 2], 0.0)
+    canyon = drt.Scene(np.array([-33.0, 0.0, 32.0], np.float32), np.empty((0, 3), np.float32),
+                       drt.Mesh.from_numpy(v, t, mask=ground))
+    mlm_0 = canyon.compute_tx_mlm(max_order=0, min_order=0, dim_x=5, dim_y=5, num_rays=50000, height=1.5)
+    assert torch.all(mlm_0 == 2166136261)
+    assert torch.all(canyon.compute_tx_mlm(max_order=2, min_order=2, dim_x=5, dim_y=5, num_rays=50000, height=1.5) == 0)
+
+
+@pytest.mark.parametrize("tilt_some", [False, True])
+def test_cull_axis_aligned_planes_and_in_plane_segments(drt, tilt_some, monkeypatch):
+    """Exactly axis-aligned rectangles on a few shared planes (the floors, the ground and the rows of walls
+    of a city model) and segments lying exactly IN those planes (d_j == 0: what two consecutive reflections
+    on one plane produce): cull.cuh proves that an aligned triangle cannot be hit by such a segment and
+    drops the axis from the grazing guard.  Masks must equal the oracle's, with far fewer tests than the
+    whole mesh per segment; `tilt_some` rotates a third of the rectangles by a fraction of a degree so that
+    aligned and general nodes mix (and in-plane segments graze the tilted ones for real)."""
+    rng = np.random.default_rng(11)
+    quads = []
+    for axis in range(3):
+        for plane in rng.integers(-20, 20, 6) * 16.0:
+            for _ in range(60):
+                c = rng.integers(-300, 300, 3).astype(np.float64)
+                c[axis] = plane
+                a, b = np.zeros(3), np.zeros(3)
+                a[(axis + 1) % 3], b[(axis + 2) % 3] = rng.integers(2, 30), rng.integers(2, 30)
+                quads.append(np.stack((c, c + a, c + a + b, c + b)))
+    quads = np.array(quads)
+    if tilt_some:
+        ang = 0.003
+        rot = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+        quads[::3] = quads[::3] @ rot.T
+    v = quads.reshape(-1, 3).astype(np.float32)
+    base = 4 * np.arange(quads.shape[0])[:, None]
+    t = np.concatenate((base + [0, 1, 2], base + [0, 2, 3]), axis=1).reshape(-1, 3).astype(np.int32)
+    mesh = drt.Mesh.from_numpy(v, t)
+    # order 0: transmitters / receivers exactly on the shared planes (and a few generic ones)
+    tx, rx = [], []
+    for axis in range(3):
+        planes = np.unique(quads[:, 0, axis])[:4]
+        for pts, count in ((tx, 4), (rx, 192)):
+            p = rng.uniform(-320, 320, (len(planes), count, 3))
+            p[..., axis] = planes[:, None]
+            pts.append(p.reshape(-1, 3))
+    tx.append(rng.uniform(-320, 320, (4, 3))), rx.append(rng.uniform(-320, 320, (64, 3)))
+    tx, rx = np.concatenate(tx).astype(np.float32), np.concatenate(rx).astype(np.float32)
+    cand0 = np.zeros((1, 0), np.int32)
+    # orders 2 and 3: consecutive mirrors on one plane (the two triangles of a rectangle, two rectangles of a plane)
+    tri = rng.integers(0, t.shape[0] // 2, 400) * 2
+    same_plane = np.array([rng.choice(np.nonzero((quads[:, 0, a] == quads[q // 2, 0, a]))[0]) * 2
+                           for q in tri for a in [int(np.argmax(np.ptp(quads[q // 2], axis=0) == 0))]])
+    cand2 = np.stack((tri, tri + 1), -1).astype(np.int32)
+    cand3 = np.stack((tri, same_plane + 1, rng.integers(0, t.shape[0], 400)), -1).astype(np.int32)
+    cand3 = cand3[cand3[:, 0] != cand3[:, 1]]
+    dense_tests = 0
+    for cand in (cand0, cand2, cand3):
+        # reflected paths: a transmitter / receiver subset that still has points on every kind of plane
+        tt_, r = (tx[::4], rx[::37]) if cand.shape[1] else (tx, rx)
+        _, _, em = co.trace_path_candidates(v, t, tt_, r, cand)
+        for dense in (True, False):
+            got = drt.trace_path_candidates(mesh, tt_, r, cand, dense_blockage=dense, with_stats=True)
+            np.testing.assert_array_equal(got.mask.cpu().numpy(), em)
+            if dense and cand.shape[1] == 0:
+                dense_tests = got.stats["tests_done"]
+    if not tilt_some:  # in-plane segments no longer walk every triangle of their plane's axis
+        assert dense_tests < 0.2 * tx.shape[0] * rx.shape[0] * t.shape[0]
+    # the flat queries behind the same cull: rays with exactly zero direction components from points on the planes
+    o = np.repeat(rx[:256], 8, axis=0)
+    d = rng.uniform(-400, 400, o.shape).astype(np.float32)
+    d[np.arange(d.shape[0]), rng.integers(0, 3, d.shape[0])] = 0.0
+    from differt_b200 import geometry
+
+    monkeypatch.setattr(geometry, "_CULL_MIN_WORK", 0)  # the public API takes the culled path at any size
+    tvv = orc.triangle_vertices(v, t)
+    np.testing.assert_array_equal(drt.ray_intersect_any_triangle(o, d, tvv).numpy(), co.ray_intersect_any_triangle(o, d, tvv))
+    idx, tt = drt.first_triangle_hit_by_ray(o, d, tvv)
+    i0, t0 = co.first_triangle_hit_by_ray(o, d, tvv)
+    np.testing.assert_array_equal(bits(tt.numpy()), bits(t0))
+    assert np.isfinite(t0).any()
