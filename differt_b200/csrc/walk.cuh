@@ -85,13 +85,20 @@ path_walk_kernel(const Tri48 *__restrict__ pack, const CullNode *__restrict__ no
     int start_level = 0;
     while (start_level < leaf && lv.size[start_level + 1] <= 32) ++start_level;
     const int sub = lane & 7, slot = lane >> 3;  // child / triangle, and which of the (up to) 4 popped entries
-    // the 32 largest triangles (first row of the area-sorted pack), one per lane: every candidate is
-    // tested against them before it walks the hierarchy — a random segment is blocked by a triangle
-    // with a probability proportional to its area (the ground alone blocks a third of the bench batch)
-    Tri head_tri[kWalkHeadRows];
-#pragma unroll
-    for (int h = 0; h < kWalkHeadRows; ++h)
-        head_tri[h] = unpack(head_row[32 * h + lane].a, head_row[32 * h + lane].b, head_row[32 * h + lane].c);
+    // head test: every segment of a candidate against the kHeadPer = 32 / NSEG largest triangles (front of the
+    // area-sorted pack) in ONE Möller–Trumbore evaluation, lane = (segment, triangle) — a random segment is blocked
+    // by a triangle with a probability proportional to its area: the two ground triangles alone block 32 % of the
+    // bench batch, the 8 largest 32.7 %, the 32 largest 35.7 % (a full row of 32 per segment cost four evaluations
+    // for those last 3 %)
+    constexpr int kHeadPer = 32 / NSEG;
+    const int head_seg = lane / kHeadPer;  // >= NSEG: idle lane
+    const bool head_lane = kWalkHeadRows > 0 && head_seg < NSEG;
+    const int head_src = 3 * (head_lane ? head_seg : 0);
+    Tri head_tri;
+    {
+        const Tri48 &hr = head_row[lane % kHeadPer];
+        head_tri = unpack(hr.a, hr.b, hr.c);
+    }
 
     // Work distribution: chunks of kChunk consecutive candidates from a global cursor (the cost of a
     // candidate varies by two orders of magnitude; a static stride would leave most warps idle at the
@@ -113,31 +120,19 @@ path_walk_kernel(const Tri48 *__restrict__ pack, const CullNode *__restrict__ no
         if (unit + 1 < unit1) pf = fetch(path_of(unit + 1));
 
         bool blocked = false;
-#pragma unroll
-        for (int h = 0; h < kWalkHeadRows && !blocked; ++h) {  // head rows: every segment against the largest triangles
-            bool hit = false, weird = false;
-            float3 prev = make_float3(__shfl_sync(kFull, pv, 0), __shfl_sync(kFull, pv, 1), __shfl_sync(kFull, pv, 2));
-#pragma unroll
-            for (int sgm = 0; sgm < NSEG; ++sgm) {
-                const float3 next = make_float3(__shfl_sync(kFull, pv, 3 * sgm + 3), __shfl_sync(kFull, pv, 3 * sgm + 4),
-                                                __shfl_sync(kFull, pv, 3 * sgm + 5));
-                hit = mt_any_fast(prev, seg_dir(next, prev), head_tri[h], eps, thr, weird) || hit;
-                prev = next;
+        if (kWalkHeadRows > 0) {
+            const float3 ho = make_float3(__shfl_sync(kFull, pv, head_src), __shfl_sync(kFull, pv, head_src + 1),
+                                          __shfl_sync(kFull, pv, head_src + 2));
+            const float3 hn = make_float3(__shfl_sync(kFull, pv, head_src + 3), __shfl_sync(kFull, pv, head_src + 4),
+                                          __shfl_sync(kFull, pv, head_src + 5));
+            const float3 hd = seg_dir(hn, ho);
+            bool weird = false;
+            bool hit = head_lane && mt_any_fast(ho, hd, head_tri, eps, thr, weird);
+            if (head_lane && weird) {  // |a| outside the fast reciprocal's range: the general test decides
+                float t;
+                hit = mt_exact(ho, hd, head_tri, eps, t) && t < thr;
             }
-            if (__any_sync(kFull, weird)) {  // re-evaluate with the general test
-                hit = false;
-                prev = make_float3(__shfl_sync(kFull, pv, 0), __shfl_sync(kFull, pv, 1), __shfl_sync(kFull, pv, 2));
-#pragma unroll
-                for (int sgm = 0; sgm < NSEG; ++sgm) {
-                    const float3 next = make_float3(__shfl_sync(kFull, pv, 3 * sgm + 3),
-                                                    __shfl_sync(kFull, pv, 3 * sgm + 4),
-                                                    __shfl_sync(kFull, pv, 3 * sgm + 5));
-                    float t;
-                    hit = (mt_exact(prev, seg_dir(next, prev), head_tri[h], eps, t) && t < thr) || hit;
-                    prev = next;
-                }
-            }
-            tests += 32 * NSEG;
+            tests += NSEG * kHeadPer;
             blocked = __any_sync(kFull, hit);
         }
         for (int sgm = NSEG - 1; sgm >= 0 && !blocked; --sgm) {
