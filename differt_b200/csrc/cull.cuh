@@ -82,11 +82,19 @@ struct SegCull {  // per-segment constants of the node test (warp-uniform)
     float rseg;
 };
 
+// MUFU.RCP alone: relative error <= 2^-22, for normal inputs (every use below is guarded to |x| >= 2^-100).  The
+// node test has slack for it: 2e-5 absolute in g (|d^.c| <= 1) and 1e-5 relative in the slab parameters.
+__device__ __forceinline__ float rcp_fast(const float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ SegCull make_seg_cull(const float3 o, const float3 d) {
     SegCull s;
     s.o = o;
     const float len = sqrtf(dot3(d, d));
-    const float rl = len >= 9.313225746e-10f ? 1.0f / len : 0.0f;  // |d| < 2^-30: d^ = 0 → g < 0 → never culled
+    const float rl = len >= 9.313225746e-10f ? rcp_fast(len) : 0.0f;  // |d| < 2^-30: d^ = 0 → g < 0 → never culled
     s.dhat = make_float3(d.x * rl, d.y * rl, d.z * rl);
     // d^_j == 0 <=> d_j == 0 (header, axis-aligned triangles): a non-zero component that underflowed (or rl = 0)
     // becomes a tiny non-zero value, which only makes g smaller
@@ -94,9 +102,9 @@ __device__ __forceinline__ SegCull make_seg_cull(const float3 o, const float3 d)
     if (d.y != 0.0f && s.dhat.y == 0.0f) s.dhat.y = 1e-37f;
     if (d.z != 0.0f && s.dhat.z == 0.0f) s.dhat.z = 1e-37f;
     const float kTiny = 7.888609052e-31f;  // 2^-100
-    s.inv.x = fabsf(d.x) >= kTiny ? 1.0f / d.x : copysignf(3.402823466e38f, d.x);
-    s.inv.y = fabsf(d.y) >= kTiny ? 1.0f / d.y : copysignf(3.402823466e38f, d.y);
-    s.inv.z = fabsf(d.z) >= kTiny ? 1.0f / d.z : copysignf(3.402823466e38f, d.z);
+    s.inv.x = fabsf(d.x) >= kTiny ? rcp_fast(d.x) : copysignf(3.402823466e38f, d.x);
+    s.inv.y = fabsf(d.y) >= kTiny ? rcp_fast(d.y) : copysignf(3.402823466e38f, d.y);
+    s.inv.z = fabsf(d.z) >= kTiny ? rcp_fast(d.z) : copysignf(3.402823466e38f, d.z);
     const float3 e = add3(o, d);
     s.rseg = fmaxf(fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(e.x))),
                    fmaxf(fabsf(e.y), fabsf(e.z)));
@@ -116,7 +124,8 @@ __device__ __forceinline__ SegCull make_ray_cull(const float3 o, const float3 d)
 // true iff the node is PROVEN to contain no triangle the reference's test would report as hit by s at
 // a parameter t <= tmax (1 for a segment; the best distance so far, or +inf, for a first-hit ray)
 __device__ __forceinline__ bool node_culled(const SegCull &s, const CullNode &n, const float tmax_seg = 1.0f) {
-    if (n.half.x < 0.0f) return true;  // empty node (only never-hit records)
+    // (an empty node — only never-hit records: half.x < 0, sin_theta_min = 0 — is reported as culled where g fails;
+    // no early test on half.x: it would put a second dependent L1 round trip in front of every node test)
     float p0 = fabsf(__fmaf_rn(s.dhat.x, n.c0.x, __fmaf_rn(s.dhat.y, n.c0.y, s.dhat.z * n.c0.z)));
     float p1 = fabsf(__fmaf_rn(s.dhat.x, n.c1.x, __fmaf_rn(s.dhat.y, n.c1.y, s.dhat.z * n.c1.z)));
     float p2 = fabsf(__fmaf_rn(s.dhat.x, n.c2.x, __fmaf_rn(s.dhat.y, n.c2.y, s.dhat.z * n.c2.z)));
@@ -129,7 +138,7 @@ __device__ __forceinline__ bool node_culled(const SegCull &s, const CullNode &n,
     }
     const float pmin = fminf(fminf(p0, p1), p2);
     const float g = __fmaf_rn(n.c0.w, __fmaf_rn(pmin, n.ctr.w, -n.half.w), -2e-5f);
-    if (!(g > 0.0f)) return false;  // grazing, degenerate or NaN: cannot be proven
+    if (!(g > 0.0f)) return n.half.x < 0.0f;  // grazing, degenerate or NaN: cannot be proven (empty: c0.w = 0 → here)
     const float sx = fabsf(s.o.x - n.ctr.x) + n.half.x;
     const float sy = fabsf(s.o.y - n.ctr.y) + n.half.y;
     const float sz = fabsf(s.o.z - n.ctr.z) + n.half.z;
