@@ -686,9 +686,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         # DRAM bytes of the blockage kernels per step, from the same ncu launch list as the instruction counts
         traffic = (inst or {}).get("blockage_dram_bytes_per_step") or None
         roofline = {
-            "kernel": "blockage pass = drt::path_head_kernel<order+1> (resident head tiles, every candidate) + "
-                      "drt::path_cull_kernel<order+1> (exact culled pass over the whole mesh, undecided candidates) "
-                      "+ the ordering pass (drt::hit_count_kernel)",
+            "kernel": "blockage pass = drt::path_walk_kernel<order+1> (one warp per candidate: head test against the "
+                      "largest triangles, then the exact culled traversal of the 8-ary hierarchy, csrc/walk.cuh); on meshes "
+                      "of <= 512 triangles drt::path_head_kernel + drt::hit_count_kernel (resident all-pairs passes)",
             "bound": "fp32_issue", "achieved": achieved, "peak": issue_peak, "unit": "warp-inst/s",
             "frac": achieved / issue_peak if achieved else None, "traffic": traffic,
             "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz (SM clock sampled during the timed region)",

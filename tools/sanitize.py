@@ -68,5 +68,14 @@ mn = torch.nn.functional.normalize(torch.from_numpy(rng.normal(size=(1000, 4, 3)
 drt.image_method(f, f.detach() + 1.0, mv, mn).sum().backward()
 gen = drt.VisiblePathCandidates(50, 3, rng.uniform(size=50) < 0.5, rng.uniform(size=50) < 0.5, None)
 print("digraph", len(gen), int(gen.chunk().sum()))
+# EM consumer: Fresnel coefficients, s/p bases, per-path coefficients with the fused accumulation (ragged last warp)
+ep = drt.trace_paths(small, np.array([[100.0, 0.0, 45.0]], np.float32), rx_s[:37], 1)
+n_r = torch.full((ts_.shape[0],), 2.0 - 0.3j, dtype=torch.complex64)
+a, length, field, power = drt.em.path_coefficients(ep, small, n_r, 2.4e9, thickness=torch.full((ts_.shape[0],), 0.1),
+                                                  accumulate=True)
+print("em", int(a.numel()), float(power.sum()), float(field.abs().sum()))
+(r_s, _), _ = drt.em.fresnel_coefficients(np.linspace(1.1, 3.0, 1001).astype(np.float32), 0.5)
+(e_s, _), _ = drt.em.sp_directions(d[:1001], -d[:1001], torch.nn.functional.normalize(o[:1001], dim=-1))
+print("fresnel", float(r_s.abs().sum()), float(e_s.abs().sum()))
 torch.cuda.synchronize()
 print("sanitize run complete")
