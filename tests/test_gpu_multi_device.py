@@ -11,6 +11,7 @@ from __future__ import annotations
 import os
 import socket
 import sys
+import time
 from pathlib import Path
 
 import numpy as np
@@ -131,7 +132,15 @@ def test_nccl_world_size_two_sharded_trace_equals_single_gpu_and_oracle(tmp_path
     from oracle import c_oracle as co
 
     world = 2
-    mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    # a rank that dies or a fabric that never finishes the rendezvous must fail the test, not hang the suite
+    ctx = mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=False)
+    deadline = time.monotonic() + 240.0
+    while not ctx.join(timeout=5.0):
+        if time.monotonic() > deadline:
+            for proc in ctx.processes:
+                if proc.is_alive():
+                    proc.kill()
+            pytest.fail("the two NCCL ranks did not finish within 240 s")
     v, t, tx, rx = _scene()
     cand = scenes.complete_graph_candidates(t.shape[0], 2)
     ev, eo, em = co.trace_path_candidates(v, t, tx, rx, cand, early_exit=True)
