@@ -31,6 +31,8 @@ _TARGETS = {
     "drt_complete_graph_candidates": "DrtCompleteGraphCandidates",
     "drt_trace_path_candidates_smooth": "DrtTracePathCandidatesSmooth",
     "drt_trace_path_candidates_smooth_vjp": "DrtTracePathCandidatesSmoothVjp",
+    "drt_em_fresnel_coefficients": "DrtEmFresnelCoefficients",
+    "drt_em_path_coefficients": "DrtEmPathCoefficients",
 }
 
 
@@ -222,3 +224,37 @@ def trace_path_candidates_smooth(mesh, tx_vertices, rx_vertices, path_candidates
          jnp.broadcast_to(cand[None, None], (ntx, nrx, C, k)),
          jnp.broadcast_to(jnp.arange(nrx, dtype=jnp.int32)[None, :, None, None], shape)), axis=-1)
     return out_v, objects, out_m
+
+
+def fresnel_coefficients(n_r, cos_theta_i):
+    """Replacement body of ``differt.em.fresnel_coefficients`` (``em/_fresnel.py:46-213``):
+    ``((r_s, r_p), (t_s, t_p))``, broadcast like the reference."""
+    n_r, cos_theta_i = jnp.broadcast_arrays(jnp.asarray(n_r, jnp.complex64), jnp.asarray(cos_theta_i, jnp.float32))
+    out = jax.ShapeDtypeStruct((n_r.size,), jnp.complex64)
+    r_s, r_p, t_s, t_p = jax.ffi.ffi_call("drt_em_fresnel_coefficients", (out, out, out, out))(
+        n_r.reshape(-1), cos_theta_i.reshape(-1))
+    shape = n_r.shape
+    return (r_s.reshape(shape), r_p.reshape(shape)), (t_s.reshape(shape), t_p.reshape(shape))
+
+
+def path_coefficients(paths, mesh, n_r, thickness, frequency: float, *, polarization=("V", "V")):
+    """The field chain of ``differt.plugins.deepmimo.export`` (``plugins/deepmimo.py:516-665, 694-696``) for the
+    valid paths of ``paths`` in one custom call: ``(a [n], length [n], field [*tx, *rx], power [*tx, *rx])``.
+    ``n_r`` / ``thickness`` are per triangle (``n_complex[mesh.face_materials]``)."""
+    masked = paths.masked()  # dynamic shape: outside jit, like the reference's own `paths.masked()` callers
+    n = masked.vertices.shape[0]
+    pair_shape = paths.mask.shape[:-1]
+    pair_index = jnp.nonzero(paths.mask.reshape(-1))[0] // paths.mask.shape[-1]
+    pairs = int(np.prod(pair_shape)) if pair_shape else 1
+    pol = {"V": 0, "H": 1}
+    a, length, field, power = jax.ffi.ffi_call(
+        "drt_em_path_coefficients",
+        (jax.ShapeDtypeStruct((n,), jnp.complex64), jax.ShapeDtypeStruct((n,), jnp.float32),
+         jax.ShapeDtypeStruct((pairs,), jnp.complex64), jax.ShapeDtypeStruct((pairs,), jnp.float32)),
+    )(
+        mesh.vertices, mesh.triangles, masked.vertices, masked.objects.astype(jnp.int32),
+        jnp.asarray(n_r, jnp.complex64), jnp.asarray(thickness, jnp.float32), pair_index.astype(jnp.int64),
+        frequency=np.float64(frequency), tx_polarization=np.int64(pol[polarization[0]]),
+        rx_polarization=np.int64(pol[polarization[1]]),
+    )
+    return a, length, field.reshape(pair_shape), power.reshape(pair_shape)

@@ -2,8 +2,11 @@
 // would compile next to jaxlib (`g++ -shared -fPIC -I$(python -c "import jax; print(jax.ffi.include_dir())")
 // -I include integration/xla_ffi.cc -L differt_b200 -ldiffert_b200 -o libdiffert_b200_xla.so`).
 //
-// NOT BUILT IN THIS IMAGE: jaxlib (and therefore xla/ffi/api/ffi.h) is not installed, so this file is
-// documentation-grade source, kept out of differt_b200/csrc (build.py compiles *.cu only).  It replaces
+// NOT BUILT IN THIS IMAGE: jaxlib (and therefore xla/ffi/api/ffi.h) is not installed, so this file is kept out of
+// differt_b200/csrc (build.py compiles *.cu only) and has never run.  What IS checked here, on every CPU test run
+// (tests/test_abi.py::test_xla_ffi_shim_type_checks): `g++ -fsyntax-only` against include/differt_b200.h and a
+// declaration-only stand-in for the XLA header (integration/stub/xla/ffi/api/ffi.h) — every drt_* call matches the
+// C ABI, every handler's parameter list matches the binding it is registered with.  It replaces
 // the three Warp launchers the reference registers through wp.jax_callable:
 //   _ray_intersect_any_triangle_anyhit_func   differt/src/differt/geometry/_mesh.py:160-181
 //   _first_triangle_hit_by_ray_func           differt/src/differt/geometry/_mesh.py:202-223
@@ -335,4 +338,77 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(DrtTracePathCandidatesSmoothVjp, TraceSmoothVjpImp
                                   .Attr<float>("smoothing_factor")
                                   .Ret<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>());
+
+// Fresnel coefficients (differt/src/differt/em/_fresnel.py:46-213): n_r [n] c64, cos_theta_i [n] f32 (the caller
+// broadcasts) → r_s, r_p, t_s, t_p [n] c64
+static ffi::Error FresnelImpl(cudaStream_t stream, ffi::Buffer<ffi::C64> n_r, ffi::Buffer<ffi::F32> cos_theta_i,
+                              ffi::ResultBuffer<ffi::C64> r_s, ffi::ResultBuffer<ffi::C64> r_p,
+                              ffi::ResultBuffer<ffi::C64> t_s, ffi::ResultBuffer<ffi::C64> t_p) {
+    const int64_t n = static_cast<int64_t>(r_s->element_count());
+    return Check(drt_em_fresnel_coefficients(
+        stream, n, reinterpret_cast<const float *>(n_r.typed_data()), n_r.element_count() == 1 ? 0 : 1,
+        cos_theta_i.typed_data(), cos_theta_i.element_count() == 1 ? 0 : 1, reinterpret_cast<float *>(r_s->typed_data()),
+        reinterpret_cast<float *>(r_p->typed_data()), reinterpret_cast<float *>(t_s->typed_data()),
+        reinterpret_cast<float *>(t_p->typed_data())));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DrtEmFresnelCoefficients, FresnelImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::C64>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::C64>>()
+                                  .Ret<ffi::Buffer<ffi::C64>>()
+                                  .Ret<ffi::Buffer<ffi::C64>>()
+                                  .Ret<ffi::Buffer<ffi::C64>>());
+
+// per-path field chain of deepmimo.export (differt/src/differt/plugins/deepmimo.py:516-665, 694-696) on compacted
+// paths: vertices [n,k+2,3], objects [n,k+2], mesh vertices / triangles (normals come from the pack), n_r [T] c64,
+// thickness [T] f32 (negative: half space), pair_index [n] s64 → a [n] c64, length [n] f32, field [pairs] c64,
+// power [pairs] f32 (the two accumulators are zero-filled here: XLA hands over uninitialised result buffers)
+static ffi::Error PathCoefficientsImpl(cudaStream_t stream, ffi::ScratchAllocator scratch,
+                                       ffi::Buffer<ffi::F32> mesh_vertices, ffi::Buffer<ffi::S32> triangles,
+                                       ffi::Buffer<ffi::F32> vertices, ffi::Buffer<ffi::S32> objects,
+                                       ffi::Buffer<ffi::C64> n_r, ffi::Buffer<ffi::F32> thickness,
+                                       ffi::Buffer<ffi::S64> pair_index, double frequency, int64_t tx_polarization,
+                                       int64_t rx_polarization, ffi::ResultBuffer<ffi::C64> a,
+                                       ffi::ResultBuffer<ffi::F32> length, ffi::ResultBuffer<ffi::C64> field,
+                                       ffi::ResultBuffer<ffi::F32> power) {
+    const int64_t V = mesh_vertices.dimensions()[0], T = triangles.dimensions()[0];
+    const int64_t n = vertices.dimensions()[0];
+    const int32_t order = static_cast<int32_t>(vertices.dimensions()[1]) - 2;
+    auto pack = scratch.Allocate(drt_mesh_pack_bytes(T));
+    if (!pack.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "pack scratch");
+    if (int rc = drt_mesh_pack(stream, V, T, mesh_vertices.typed_data(), triangles.typed_data(), nullptr, *pack))
+        return Check(rc);
+    const int64_t pairs = static_cast<int64_t>(power->element_count());
+    if (cudaMemsetAsync(field->typed_data(), 0, field->size_bytes(), stream) != cudaSuccess ||
+        cudaMemsetAsync(power->typed_data(), 0, power->size_bytes(), stream) != cudaSuccess)
+        return ffi::Error(ffi::ErrorCode::kInternal, "cudaMemsetAsync");
+    return Check(drt_em_path_coefficients(
+        stream, n, order, vertices.typed_data(), objects.typed_data(), T, *pack,
+        reinterpret_cast<const float *>(n_r.typed_data()), thickness.element_count() ? thickness.typed_data() : nullptr,
+        frequency, static_cast<int32_t>(tx_polarization), static_cast<int32_t>(rx_polarization),
+        reinterpret_cast<float *>(a->typed_data()), length->typed_data(), pair_index.typed_data(), pairs,
+        reinterpret_cast<float *>(field->typed_data()), power->typed_data()));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(DrtEmPathCoefficients, PathCoefficientsImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Ctx<ffi::ScratchAllocator>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::C64>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S64>>()
+                                  .Attr<double>("frequency")
+                                  .Attr<int64_t>("tx_polarization")
+                                  .Attr<int64_t>("rx_polarization")
+                                  .Ret<ffi::Buffer<ffi::C64>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::C64>>()
                                   .Ret<ffi::Buffer<ffi::F32>>());

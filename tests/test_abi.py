@@ -150,3 +150,38 @@ def test_pure_c_consumer_runs_on_the_gpu(lib, tmp_path):
     assert res.returncode == 0, res.stdout + res.stderr
     assert "OK: 6 valid order-1 paths" in res.stdout
     assert res.stdout.count("blocked=1") == 6 and res.stdout.count("t=0.500") == 6
+
+
+def test_xla_ffi_shim_type_checks(tmp_path):
+    """integration/xla_ffi.cc against the REAL C header and a declaration-only stand-in for jaxlib's
+    xla/ffi/api/ffi.h (integration/stub): every drt_* call must match include/differt_b200.h, every handler's
+    parameter list must match the binding it is registered with, every target the Python side registers
+    (integration/differt_b200_jax.py) must be defined.  A syntax / type check, not an execution: jaxlib is not
+    installable in this image."""
+    import re
+    import shutil
+    import subprocess
+
+    cuda = Path("/usr/local/cuda")
+    if shutil.which("g++") is None or not (cuda / "include" / "cuda_runtime_api.h").exists():
+        pytest.skip("needs g++ and the CUDA runtime headers")
+    shim = ROOT / "integration" / "xla_ffi.cc"
+    base = ["g++", "-std=c++17", "-fsyntax-only", "-Wall", f"-I{ROOT / 'integration' / 'stub'}", f"-I{ROOT / 'include'}",
+            f"-I{cuda / 'include'}"]
+    res = subprocess.run([*base, str(shim)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    # the check has teeth: a binding that decodes another attribute type, or a call with one argument too many, fails
+    text = shim.read_text()
+    bad = tmp_path / "bad_binding.cc"
+    bad.write_text(text.replace('.Attr<int64_t>("batch_size")', '.Attr<float>("batch_size")', 1))
+    res = subprocess.run([*base, str(bad)], capture_output=True, text=True)
+    assert res.returncode != 0 and "do not match" in res.stderr
+    bad = tmp_path / "bad_call.cc"
+    bad.write_text(text.replace("drt_em_fresnel_coefficients(\n        stream, n,", "drt_em_fresnel_coefficients(\n        stream, n, 0,", 1))
+    assert bad.read_text() != text
+    assert subprocess.run([*base, str(bad)], capture_output=True, text=True).returncode != 0
+    # every FFI target the Python shim registers is a handler symbol of the C++ shim
+    defined = set(re.findall(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((\w+),", text))
+    py = (ROOT / "integration" / "differt_b200_jax.py").read_text()
+    registered = set(re.findall(r'"drt_\w+": "(\w+)"', py))
+    assert registered and registered <= defined, registered - defined
