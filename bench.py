@@ -421,7 +421,11 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     # started first, seconds before anything is timed (see ClockSampler)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # a rank that dies or a fabric that never completes a collective ends the run with an error after 5
+        # minutes instead of NCCL's default 10 (every leg between two collectives is seconds long)
+        import datetime
+
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=5))
 
     if args.cand is not None:  # BASELINE config 5's sweep over the number of candidates
         WORKLOADS[args.workload]["cand"] = args.cand
