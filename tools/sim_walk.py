@@ -2,7 +2,8 @@
 """CPU model of the culled traversal (csrc/walk.cuh) on a sample of the bench workload: counts node
 steps, group steps and Möller–Trumbore tests per candidate for a given grouping of the Morton-ordered
 triangles and a given stack discipline, so that hierarchy / ordering ideas can be ranked before any
-GPU time is spent on them.  The node test is the plain slab test (the margin m of cull.cuh is ~1e-4 m
+GPU time is spent on them.  A development tool, not product code: the path vertices it walks come from the CPU
+oracle (oracle/c_oracle.py).  The node test is the plain slab test (the margin m of cull.cuh is ~1e-4 m
 here and the grazing guard is rare); the triangle test is Möller–Trumbore in float64.
 
     python tools/sim_walk.py [--cand 192] [--rx 48] [--grouping fixed|greedy] [--order lifo|near]
